@@ -1,0 +1,123 @@
+"""The oracle against the reference's own outputs (committed golden vectors) and against itself.
+
+CPU only.  ``ref_*`` fixtures were produced by importing the reference in the
+build container (tests/golden/make_golden.py); ``oracle_*`` fixtures by the
+oracle's exact solver and are used here for regression and for the
+two-independent-solvers agreement that defines the strict oracle.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import lipm_oracle as orc
+
+
+def test_preview_matrices_are_markov_parameters():
+    # Px[i] = C A^(i+1), Pu[i,j] = C A^(i-j) B  
+    p = orc.Problem.make(40, h=0.8)
+    Apow = np.eye(3)
+    for i in range(p.N):
+        markov = p.C @ Apow @ p.B
+        assert np.allclose(np.diag(p.Pu, -i), markov, rtol=1e-12, atol=1e-18)
+        Apow = Apow @ p.A
+        assert np.allclose(p.Px[i], p.C @ Apow, rtol=1e-13)
+    assert np.all(np.triu(p.Pu, 1) == 0)
+
+
+def test_nonstrict_ticks_match_reference(golden):
+    g = golden("ref_nonstrict_ticks")
+    for N in (10, 50, 100, 150):
+        for h in (0.75, 0.62):
+            key = f"N{N}_h{h}"
+            p = orc.Problem.make(N, h=h)
+            for x, lo, hi, want in zip(g[f"{key}/x"], g[f"{key}/z_min"], g[f"{key}/z_max"], g[f"{key}/next"]):
+                got = orc.unconstrained_axis(p, x, hi, lo)
+                assert np.allclose(got, want, rtol=1e-9, atol=1e-12), key
+
+
+def test_nonstrict_default_walk_matches_reference(golden):
+    g = golden("ref_nonstrict_walk")
+    p = orc.Problem.make(150)
+    res = orc.rollout_wieber(p, np.zeros(3), np.zeros(3), g["z_max"], g["z_min"], strict=False,
+                             impulse=float(g["impulse"]), force_tick=int(g["force_tick"]))
+    com, y_hist = orc.reference_outputs(res)
+    assert com.shape == g["com"].shape and y_hist.shape == g["y_hist"].shape
+    scale = np.max(np.abs(g["y_hist"]))
+    assert np.max(np.abs(com - g["com"])) <= 1e-9 * np.max(np.abs(g["com"]))
+    assert np.max(np.abs(y_hist - g["y_hist"])) <= 1e-9 * scale
+    # generate_state_trajectory_wieber: same loop, never pushes
+    res = orc.rollout_wieber(p, np.zeros(3), np.zeros(3), g["z_max"], g["z_min"], strict=False)
+    assert np.max(np.abs(res["x_hist"] - g["nopush_x_hist"][:, :, 0])) <= 1e-9 * np.max(np.abs(g["nopush_x_hist"]))
+    assert np.max(np.abs(res["y_hist"] - g["nopush_y_hist"][:, :, 0])) <= 1e-9 * np.max(np.abs(g["nopush_y_hist"]))
+    # the un-constrained controller lets the ZMP leave the sole by 0.038 m after the push
+    assert 0.03 < res_max_violation(p, g) < 0.045
+
+
+def res_max_violation(p, g):
+    res = orc.rollout_wieber(p, np.zeros(3), np.zeros(3), g["z_max"], g["z_min"], strict=False,
+                             impulse=float(g["impulse"]), force_tick=int(g["force_tick"]))
+    return res["max_violation"]
+
+
+@pytest.mark.parametrize("N", [16, 50, 150])
+def test_strict_two_solvers_agree(golden, N):
+    g = golden("oracle_strict_ticks")
+    p = orc.Problem.make(N)
+    M = orc.admm_matrix(p, 2.0)
+    for k in range(0, len(g[f"N{N}/x"]), 3 if N == 150 else 1):
+        x, lo, hi = g[f"N{N}/x"][k], g[f"N{N}/z_min"][k], g[f"N{N}/z_max"][k]
+        nxt_a, z_a, _, iters = orc.strict_axis_admm(p, x, hi, lo, M=M)
+        assert iters < 5000
+        assert np.max(np.abs(z_a - g[f"N{N}/z"][k])) <= 1e-11
+        assert np.allclose(nxt_a, g[f"N{N}/next"][k], rtol=0, atol=1e-10)
+        # ADMM clips exactly, so its active set is readable by equality; ties aside it equals BVLS's
+        act = np.where(z_a == lo, -1, 0) + np.where(z_a == hi, 1, 0)
+        free_margin = np.minimum(g[f"N{N}/z"][k] - lo, hi - g[f"N{N}/z"][k])
+        decided = (g[f"N{N}/active"][k] != 0) | (free_margin > 1e-9)
+        assert np.array_equal(act[decided], g[f"N{N}/active"][k][decided])
+
+
+def test_strict_exact_regression(golden):
+    g = golden("oracle_strict_ticks")
+    p = orc.Problem.make(50)
+    for k in range(6):
+        nxt, z, act = orc.strict_axis_exact(p, g["N50/x"][k], g["N50/z_max"][k], g["N50/z_min"][k])
+        assert np.allclose(z, g["N50/z"][k], rtol=0, atol=1e-13)
+        assert np.array_equal(act, g["N50/active"][k])
+
+
+def test_strict_equals_unconstrained_when_inactive():
+    # property: wide boxes -> strict optimum is the closed form
+    p = orc.Problem.make(60)
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=3) * np.array([0.02, 0.05, 0.1])
+    lo, hi = np.full(60, -5.0), np.full(60, 5.0)
+    want = orc.unconstrained_axis(p, x, hi, lo)
+    got, z, act = orc.strict_axis_exact(p, x, hi, lo)
+    assert not act.any()
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+    got2, *_ = orc.strict_axis_admm(p, x, hi, lo)
+    assert np.allclose(got2, want, rtol=1e-9, atol=1e-12)
+
+
+def test_strict_walk_properties(golden):
+    g = golden("oracle_strict_walk")
+    # ZMP never leaves the box in strict mode and the final y state is the surveyed one
+    assert g["margin"].min() > -1e-12
+    assert not (g["flags"] & (orc.FLAG_VIOL_LO | orc.FLAG_VIOL_HI)).any()
+    assert np.allclose(g["y_hist"][-1], [-0.0142, 0.0317, -0.0638], atol=1e-4)
+    # the FIRST preview row (the one that is applied) sits on a bound on ~100 y ticks and few x ticks
+    active = (g["flags"] & 3) != 0
+    assert 80 < active[:, 1].sum() < 140 and active[:, 0].sum() < 30
+
+
+def test_strict_walk_admm_rollout_matches_exact_prefix(golden):
+    g = golden("oracle_strict_walk")
+    p = orc.Problem.make(150)
+    ticks = 40
+    start = int(g["force_tick"]) - 5          # straddle the push: the hardest ticks
+    x0, y0 = g["x_hist"][start], g["y_hist"][start]
+    res = orc.rollout_wieber(p, x0, y0, g["z_max"][start:], g["z_min"][start:], strict=True,
+                             impulse=float(g["impulse"]), force_tick=5, solver="admm", n_ticks=ticks)
+    assert np.max(np.abs(res["x_hist"] - g["x_hist"][start:start + ticks + 1])) < 1e-10
+    assert np.max(np.abs(res["y_hist"] - g["y_hist"][start:start + ticks + 1])) < 1e-10
