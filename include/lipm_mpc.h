@@ -1,0 +1,138 @@
+/*
+ * lipm_mpc.h -- C ABI of the batched LIPM / ZMP-preview MPC engine (B200, sm_100a).
+ *
+ * Drop-in boundary for the hot path of
+ *   plevankiem/model-predictive-control-for-bipedal-locomotion
+ * The reference has no FFI: the path is plain Python methods of ZMPController
+ * (src/mpc_bipedal/controllers/zmp_controller.py).  Each entry point below cites the
+ * reference code it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - all floating-point data is IEEE float64 (the reference is NumPy float64 throughout);
+ *   - "dev" pointers are device pointers on the plan's device, owned by the caller;
+ *   - every function returns LIPM_OK (0) or a negative LIPM_E_* code and never throws;
+ *     lipm_last_error() returns a thread-local message for the last failure;
+ *   - calls that take a stream are asynchronous on that stream (pass 0 for the legacy stream);
+ *   - a plan is immutable after creation; rollouts on one plan must not overlap in time
+ *     (they share the plan's tile counter) -- use one plan per concurrent stream;
+ *   - one axis-solve of one tick of one scenario is one "QP solve"; a scenario with n bound
+ *     samples costs 2*(n-1) solves (reference loop zmp_controller.py:93-104).
+ */
+#ifndef LIPM_MPC_H
+#define LIPM_MPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lipm_plan lipm_plan_t;
+
+/* return codes */
+#define LIPM_OK 0
+#define LIPM_E_INVALID (-1)     /* bad argument (message says which)                        */
+#define LIPM_E_CUDA (-2)        /* a CUDA runtime call failed                               */
+#define LIPM_E_UNSUPPORTED (-3) /* valid request this build cannot serve (e.g. horizon)     */
+#define LIPM_E_NUMERIC (-4)     /* factorisation broke down (non-finite / non-SPD matrix)   */
+
+/* mode of a solve / rollout -- MPCConfig.strict (config.py:39) */
+#define LIPM_MODE_UNCONSTRAINED 0 /* closed form, zmp_controller.py:196-198                 */
+#define LIPM_MODE_STRICT 1        /* box-constrained QP, zmp_controller.py:173-195          */
+
+/* per-sample flag bits written by rollouts: flags[b][t][axis] */
+#define LIPM_FLAG_ACTIVE_LO 1u     /* applied ZMP sample sits on its lower bound (strict)   */
+#define LIPM_FLAG_ACTIVE_HI 2u     /* ... on its upper bound                                */
+#define LIPM_FLAG_VIOL_LO 4u       /* realised ZMP  <  z_min - viol_tol                     */
+#define LIPM_FLAG_VIOL_HI 8u       /* realised ZMP  >  z_max + viol_tol                     */
+#define LIPM_FLAG_NOT_CONVERGED 16u /* the QP that produced this sample hit max_iter        */
+
+/* matrices a test / host mirror can read back with lipm_plan_export */
+#define LIPM_EXPORT_PX 0        /* [N,3]   zmp_controller.py:163-165                        */
+#define LIPM_EXPORT_PU 1        /* [N,N]   zmp_controller.py:166-171                        */
+#define LIPM_EXPORT_ABC 2       /* [15]    A (9, row-major), B (3), C (3)  zmp_controller.py:18-20 */
+#define LIPM_EXPORT_ADMM_M 3    /* [N,N]   (Q I + R Pu^-T Pu^-1 + rho I)^-1                 */
+#define LIPM_EXPORT_HINV 4      /* [N,N]   (Q I + R Pu^-T Pu^-1)^-1                         */
+#define LIPM_EXPORT_GAIN 5      /* [N+3]   first-jerk gain row: kz (N) then kx (3)          */
+#define LIPM_EXPORT_GPX 6       /* [N,3]   R Pu^-T Pu^-1 Px                                 */
+
+typedef struct lipm_plan_desc {
+    int32_t horizon;   /* N  = MPCConfig.horizon                                            */
+    double h, g, dt;   /* CoM height, gravity, sample time (dt = 1.5/N unless overridden)   */
+    double Q, R;       /* tracking / jerk weights (zmp_controller.py:186, :174)             */
+    double rho;        /* ADMM penalty          (<=0 -> default 2.0)                        */
+    double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.6)                        */
+    double eps;        /* ADMM stop: max(primal, dual residual) <= eps, metres (<=0 -> 1e-12) */
+    int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000)                           */
+    double viol_tol;   /* box-violation tolerance for LIPM_FLAG_VIOL_* (<0 -> 1e-9)         */
+    int32_t device;    /* CUDA device ordinal                                               */
+} lipm_plan_desc_t;
+
+/*
+ * Build, ON THE DEVICE, everything that is fixed for one (N, h, g, dt, Q, R):
+ * A, B, C (zmp_controller.py:15-21), Px and Pu (:162-171 -- the reference rebuilds these with
+ * a Python double loop on every solve), the ZMP-coordinate Hessian H = Q I + R Pu^-T Pu^-1,
+ * its Cholesky-based inverses (H^-1 for the unconstrained mode, (H + rho I)^-1 for ADMM) and
+ * the first-jerk gain row.  Replaces the per-call matrix construction in predict_wieber_axis.
+ */
+int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc);
+void lipm_plan_destroy(lipm_plan_t* plan);
+
+/* Copy one of the plan's matrices to host memory (blocking).  `capacity` counts doubles. */
+int lipm_plan_export(const lipm_plan_t* plan, int which, double* host_out, size_t capacity);
+
+/*
+ * Whole receding-horizon walks for B independent scenarios: replaces
+ * ZMPController.generate_com_trajectory_wieber (zmp_controller.py:59-108) and
+ * generate_state_trajectory_wieber (:110-147; pass force_tick = NULL).
+ *
+ *   B            scenarios
+ *   n_max        allocated samples per scenario in the [.., n_max, ..] arrays
+ *   n_steps      dev int32 [B]   bound samples of each scenario (2 <= n <= n_max); NULL -> n_max
+ *   x0, y0       dev [B,3]       initial axis states [pos, vel, acc]
+ *   z_min,z_max  dev [Bz,n_max,2] ZMP box per sample (x,y interleaved as the reference's (n,2)
+ *                                arrays); bounds_batch = Bz is 1 (shared by all scenarios) or B.
+ *                                The last row is repeated `horizon` times past the end (:81-88).
+ *   impulse      dev [B]         dt*F_ext/m, subtracted from the y velocity after the update of
+ *                                tick force_tick[b] (:105-106); NULL -> no push
+ *   force_tick   dev int32 [B]   the reference uses n_steps//2 (:90); negative -> no push
+ * outputs (any may be NULL to skip)
+ *   x_hist,y_hist dev [B,n_max,3] state histories; sample 0 is the initial state
+ *   flags        dev uint8 [B,n_max,2]
+ *   max_violation dev [B,2]      per axis: max over samples of max(z_min - zmp, zmp - z_max, 0)
+ *   status       dev int32 [B,2] per axis: number of ticks whose QP hit max_iter (0 = all converged)
+ *   iters        dev int32 [B,2] per axis: ADMM iterations executed, summed over ticks
+ */
+int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n_steps,
+                 const double* x0, const double* y0, const double* z_min, const double* z_max,
+                 int bounds_batch, const double* impulse, const int32_t* force_tick,
+                 double* x_hist, double* y_hist, uint8_t* flags, double* max_violation,
+                 int32_t* status, int32_t* iters, void* stream);
+
+/*
+ * One control tick for a batch of independent axis problems: replaces
+ * ZMPController.predict_wieber_axis (zmp_controller.py:149-201).
+ *
+ *   state      dev [B,3]      current axis state
+ *   z_min,z_max dev [Bz,N]    bound window rows i+1 .. i+N of that axis (Bz = 1 or B)
+ *   next_state dev [B,3]      A x + B u0
+ *   zmp_plan   dev [B,N] or NULL  the optimal previewed ZMP sequence Px x + Pu J
+ *   jerk_plan  dev [B,N] or NULL  the optimal jerk sequence J  (X_burst of the reference)
+ *   status     dev int32 [B] or NULL  0 converged / 1 hit max_iter (strict mode)
+ *   iters      dev int32 [B] or NULL  ADMM iterations executed
+ */
+int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, const double* z_min,
+                    const double* z_max, int bounds_batch, double* next_state, double* zmp_plan,
+                    double* jerk_plan, int32_t* status, int32_t* iters, void* stream);
+
+/* Library / build information. */
+const char* lipm_last_error(void);
+const char* lipm_version(void);
+/* Largest horizon the resident-matrix strict kernel of this build serves. */
+int lipm_max_strict_horizon(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIPM_MPC_H */

@@ -1,0 +1,242 @@
+// C ABI entry points (include/lipm_mpc.h).  Argument checking, plan lifetime, dispatch.
+#include "lipm_internal.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace lipm {
+
+namespace {
+thread_local char g_error[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DeviceGuard {
+    int previous = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&previous) != cudaSuccess) return;
+        ok = (previous == device) || (cudaSetDevice(device) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (previous >= 0) cudaSetDevice(previous);
+    }
+};
+
+void free_plan_buffers(lipm_plan* p) {
+    void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_gain, p->d_info, p->d_tile_counter};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+}
+
+}  // namespace
+}  // namespace lipm
+
+using namespace lipm;
+
+extern "C" {
+
+const char* lipm_last_error(void) { return g_error; }
+
+const char* lipm_version(void) { return "lipm_mpc 0.1 (sm_100a; fp64 DMMA ADMM, gain-row unconstrained)"; }
+
+int lipm_max_strict_horizon(void) { return kMaxStrictHorizon; }
+
+int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
+    if (!out || !desc) { set_error("lipm_plan_create: null argument"); return LIPM_E_INVALID; }
+    *out = nullptr;
+    lipm_plan_desc_t d = *desc;
+    if (d.horizon < 2 || d.horizon > 4096) { set_error("horizon %d out of range [2, 4096]", d.horizon); return LIPM_E_INVALID; }
+    if (!(d.h > 0) || !(d.g > 0) || !(d.dt > 0) || !(d.Q > 0) || !(d.R > 0) ||
+        !std::isfinite(d.h) || !std::isfinite(d.g) || !std::isfinite(d.dt) || !std::isfinite(d.Q) || !std::isfinite(d.R)) {
+        set_error("h, g, dt, Q, R must be finite and positive (got %g %g %g %g %g)", d.h, d.g, d.dt, d.Q, d.R);
+        return LIPM_E_INVALID;
+    }
+    if (!(d.rho > 0)) d.rho = 2.0;
+    if (!(d.alpha > 0)) d.alpha = 1.6;
+    if (d.alpha >= 2.0) { set_error("alpha must be in (0, 2), got %g", d.alpha); return LIPM_E_INVALID; }
+    if (!(d.eps > 0)) d.eps = 1e-12;
+    if (d.max_iter <= 0) d.max_iter = 2000;
+    if (d.viol_tol < 0 || !std::isfinite(d.viol_tol)) d.viol_tol = 1e-9;
+    const double pu00 = std::pow(d.dt, 3) / 6.0 - d.dt * d.h / d.g;
+    if (pu00 == 0.0) { set_error("Pu[0,0] = dt^3/6 - dt*h/g is zero: Pu is singular"); return LIPM_E_INVALID; }
+
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (this library has no CPU path)");
+        return LIPM_E_CUDA;
+    }
+    if (d.device < 0 || d.device >= count) { set_error("device %d out of range (%d devices)", d.device, count); return LIPM_E_INVALID; }
+    DeviceGuard guard(d.device);
+    if (!guard.ok) { set_error("cannot select device %d", d.device); return LIPM_E_CUDA; }
+
+    lipm_plan* plan = new (std::nothrow) lipm_plan();
+    if (!plan) { set_error("out of host memory"); return LIPM_E_INVALID; }
+    std::memset(plan, 0, sizeof(*plan));
+    plan->desc = d;
+    plan->N = d.horizon;
+    plan->NP = padded8(d.horizon);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d.device) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed");
+        delete plan;
+        return LIPM_E_CUDA;
+    }
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", d.device, prop.major, prop.minor);
+        delete plan;
+        return LIPM_E_UNSUPPORTED;
+    }
+    plan->sm_count = prop.multiProcessorCount;
+    const int rc = build_plan_matrices(plan);
+    if (rc != LIPM_OK) {
+        free_plan_buffers(plan);
+        delete plan;
+        return rc;
+    }
+    *out = plan;
+    return LIPM_OK;
+}
+
+void lipm_plan_destroy(lipm_plan_t* plan) {
+    if (!plan) return;
+    DeviceGuard guard(plan->desc.device);
+    free_plan_buffers(plan);
+    delete plan;
+}
+
+int lipm_plan_export(const lipm_plan_t* plan, int which, double* host_out, size_t capacity) {
+    if (!plan || !host_out) { set_error("lipm_plan_export: null argument"); return LIPM_E_INVALID; }
+    const size_t N = (size_t)plan->N;
+    const double* src = nullptr;
+    size_t count = 0;
+    switch (which) {
+        case LIPM_EXPORT_PX: src = plan->d_px; count = N * 3; break;
+        case LIPM_EXPORT_PU: src = plan->d_pu; count = N * N; break;
+        case LIPM_EXPORT_ABC: src = plan->d_abc; count = 15; break;
+        case LIPM_EXPORT_ADMM_M: src = plan->d_minv; count = N * N; break;
+        case LIPM_EXPORT_HINV: src = plan->d_hinv; count = N * N; break;
+        case LIPM_EXPORT_GAIN: src = plan->d_gain; count = N + 3; break;
+        case LIPM_EXPORT_GPX: src = plan->d_gpx; count = N * 3; break;
+        default: set_error("lipm_plan_export: unknown selector %d", which); return LIPM_E_INVALID;
+    }
+    if (capacity < count) { set_error("lipm_plan_export: need %zu doubles, got %zu", count, capacity); return LIPM_E_INVALID; }
+    DeviceGuard guard(plan->desc.device);
+    LIPM_CUDA_TRY(cudaMemcpy(host_out, src, count * sizeof(double), cudaMemcpyDeviceToHost));
+    return LIPM_OK;
+}
+
+int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n_steps, const double* x0,
+                 const double* y0, const double* z_min, const double* z_max, int bounds_batch,
+                 const double* impulse, const int32_t* force_tick, double* x_hist, double* y_hist,
+                 uint8_t* flags, double* max_violation, int32_t* status, int32_t* iters, void* stream) {
+    if (!plan) { set_error("lipm_rollout: null plan"); return LIPM_E_INVALID; }
+    if (mode != LIPM_MODE_STRICT && mode != LIPM_MODE_UNCONSTRAINED) { set_error("lipm_rollout: bad mode %d", mode); return LIPM_E_INVALID; }
+    if (B < 0 || n_max < 2) { set_error("lipm_rollout: need B >= 0 and n_max >= 2 (got %d, %d)", B, n_max); return LIPM_E_INVALID; }
+    if (B == 0) return LIPM_OK;
+    if (!x0 || !y0 || !z_min || !z_max) { set_error("lipm_rollout: x0, y0, z_min, z_max are required"); return LIPM_E_INVALID; }
+    if (bounds_batch != 1 && bounds_batch != B) { set_error("lipm_rollout: bounds_batch must be 1 or B (got %d, B=%d)", bounds_batch, B); return LIPM_E_INVALID; }
+    if ((long long)B * 2 > 0x7fffffffLL / 8) { set_error("lipm_rollout: batch too large"); return LIPM_E_INVALID; }
+    DeviceGuard guard(plan->desc.device);
+
+    ColumnBatch cb;
+    std::memset(&cb, 0, sizeof(cb));
+    cb.ncols = 2 * B;
+    cb.B = B;
+    cb.bounds_batch = bounds_batch;
+    cb.bound_scn_stride = (long long)n_max * 2;
+    cb.bound_stride = 2;
+    cb.bound_axis_offset = 1;
+    cb.bound_index_bias = 1;
+    cb.n_max = n_max;
+    cb.n_steps = n_steps;
+    cb.n_uniform = n_max;
+    cb.ticks_override = 0;
+    cb.init[0] = x0; cb.init[1] = y0;
+    cb.z_min = z_min; cb.z_max = z_max;
+    cb.impulse = impulse; cb.force_tick = force_tick;
+    cb.hist[0] = x_hist; cb.hist[1] = y_hist;
+    cb.write_initial = 1;
+    cb.hist_scn_stride = (long long)n_max * 3;
+    cb.hist_index_bias = 0;
+    cb.flags = flags;
+    cb.max_violation = max_violation;
+    cb.status = status;
+    cb.iters = iters;
+    cb.zmp_plan = nullptr;
+    return mode == LIPM_MODE_STRICT ? launch_strict_rollout(plan, cb, (cudaStream_t)stream)
+                                    : launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream);
+}
+
+int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, const double* z_min,
+                    const double* z_max, int bounds_batch, double* next_state, double* zmp_plan,
+                    double* jerk_plan, int32_t* status, int32_t* iters, void* stream) {
+    if (!plan) { set_error("lipm_solve_tick: null plan"); return LIPM_E_INVALID; }
+    if (mode != LIPM_MODE_STRICT && mode != LIPM_MODE_UNCONSTRAINED) { set_error("lipm_solve_tick: bad mode %d", mode); return LIPM_E_INVALID; }
+    if (B < 0) { set_error("lipm_solve_tick: negative batch"); return LIPM_E_INVALID; }
+    if (B == 0) return LIPM_OK;
+    if (!state || !z_min || !z_max || !next_state) { set_error("lipm_solve_tick: state, z_min, z_max, next_state are required"); return LIPM_E_INVALID; }
+    if (bounds_batch != 1 && bounds_batch != B) { set_error("lipm_solve_tick: bounds_batch must be 1 or B"); return LIPM_E_INVALID; }
+    if (jerk_plan && !zmp_plan) { set_error("lipm_solve_tick: jerk_plan needs zmp_plan as well"); return LIPM_E_INVALID; }
+    DeviceGuard guard(plan->desc.device);
+    const int N = plan->N;
+
+    // A single tick is a "walk" whose bound series is the window itself (rows 0..N-1, no bias)
+    // and whose only produced sample (index 1) lands in next_state.  The per-axis [B,2] outputs
+    // of the walk kernels are not used here: columns are the B problems themselves.
+    ColumnBatch cb;
+    std::memset(&cb, 0, sizeof(cb));
+    cb.ncols = B;
+    cb.B = B;                    // every column maps to "axis 0"
+    cb.bounds_batch = bounds_batch;
+    cb.bound_scn_stride = N;
+    cb.bound_stride = 1;
+    cb.bound_axis_offset = 0;
+    cb.bound_index_bias = 0;
+    cb.n_max = N;
+    cb.n_steps = nullptr;
+    cb.n_uniform = N;
+    cb.ticks_override = 1;
+    cb.init[0] = state; cb.init[1] = state;
+    cb.z_min = z_min; cb.z_max = z_max;
+    cb.hist[0] = next_state; cb.hist[1] = nullptr;
+    cb.write_initial = 0;
+    cb.hist_scn_stride = 3;
+    cb.hist_index_bias = 1;
+    cb.zmp_plan = (mode == LIPM_MODE_STRICT) ? zmp_plan : nullptr;
+
+    // status / iters of the walk kernels are laid out [B,2]; stage them when requested
+    int32_t* stage = nullptr;
+    if (status || iters) {
+        LIPM_CUDA_TRY(cudaMallocAsync(&stage, sizeof(int32_t) * 4 * (size_t)B, (cudaStream_t)stream));
+        cb.status = stage;
+        cb.iters = stage + 2 * (size_t)B;
+    }
+    int rc = mode == LIPM_MODE_STRICT ? launch_strict_rollout(plan, cb, (cudaStream_t)stream)
+                                      : launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream);
+    if (rc == LIPM_OK && stage) {
+        if (status) LIPM_CUDA_TRY(cudaMemcpy2DAsync(status, sizeof(int32_t), stage, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        if (iters) LIPM_CUDA_TRY(cudaMemcpy2DAsync(iters, sizeof(int32_t), stage + 2 * (size_t)B, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    if (stage) cudaFreeAsync(stage, (cudaStream_t)stream);
+    if (rc != LIPM_OK) return rc;
+
+    if (zmp_plan && mode == LIPM_MODE_UNCONSTRAINED) {
+        rc = launch_unconstrained_plan(plan, B, state, z_min, z_max, bounds_batch, zmp_plan, (cudaStream_t)stream);
+        if (rc != LIPM_OK) return rc;
+    }
+    if (jerk_plan) rc = launch_jerk_from_zmp(plan, B, state, zmp_plan, jerk_plan, (cudaStream_t)stream);
+    return rc;
+}
+
+}  // extern "C"

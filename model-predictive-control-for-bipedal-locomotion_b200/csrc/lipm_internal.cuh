@@ -1,0 +1,106 @@
+// Internal declarations shared by the translation units of liblipm_mpc.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#include "lipm_mpc.h"
+
+namespace lipm {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char* fmt, ...);
+#define LIPM_CUDA_TRY(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t err__ = (expr);                                                      \
+        if (err__ != cudaSuccess) {                                                      \
+            ::lipm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                              __FILE__, __LINE__);                                       \
+            return LIPM_E_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------ geometry helpers
+// DMMA.8x8x4 tiles: rows and the contraction index are padded to a multiple of 8.
+__host__ __device__ inline int padded8(int n) { return (n + 7) & ~7; }
+// Row pitch (in doubles) of the per-column vectors kept in shared memory as the B operand
+// [column][k].  pitch % 16 is 4 or 12, which makes the B-fragment load (lane -> column
+// lane/4, k lane%4) hit 16 distinct 8-byte banks per half warp.
+__host__ __device__ inline int column_pitch(int np) { return np + 4; }
+
+constexpr int kRowGroups = 4;       // warps along the row dimension of the iteration matrix
+constexpr int kMaxRowBlocksPerWarp = 5;
+constexpr int kMaxStrictHorizon = 8 * kRowGroups * kMaxRowBlocksPerWarp;  // 160
+
+// ------------------------------------------------------------------ the plan
+}  // namespace lipm
+
+struct lipm_plan {
+    lipm_plan_desc_t desc;
+    int N;        // horizon
+    int NP;       // padded8(N)
+    int sm_count;
+    // model scalars (host copies)
+    double T, hg;         // dt, h/g
+    double pu00;          // Pu[0,0] = T^3/6 - T h/g
+    // device matrices (all float64)
+    double* d_px;         // [N,3]
+    double* d_pu;         // [N,N] dense lower-triangular Toeplitz
+    double* d_abc;        // [15]
+    double* d_tinv;       // [N]   first column of Pu^-1 (Pu^-1 is lower-triangular Toeplitz)
+    double* d_g;          // [N,N] G = R Pu^-T Pu^-1
+    double* d_gpx;        // [NP,3] G Px, zero rows beyond N
+    double* d_work;       // [N,N] factorisation scratch
+    double* d_hinv;       // [N,N] (Q I + G)^-1
+    double* d_minv;       // [N,N] (Q I + G + rho I)^-1
+    double* d_mfrag;      // [(NP/8) x (NP/4) x 32] ADMM matrix in DMMA A-fragment order
+    double* d_gain;       // [N+3] kz, kx
+    int* d_info;          // [4] factorisation status words
+    unsigned int* d_tile_counter;  // dynamic tile scheduler of the strict kernel
+};
+
+namespace lipm {
+
+// plan construction (lipm_plan.cu)
+int build_plan_matrices(lipm_plan* plan);
+
+// One "column" = one axis of one scenario.  The rollout kernels receive this flat description.
+struct ColumnBatch {
+    int ncols;              // number of columns (2B for walks, B for single ticks)
+    int B;                  // scenarios; column c -> scenario c % B, axis c / B
+    int bounds_batch;       // 1 (shared) or B
+    long long bound_scn_stride;   // doubles between consecutive scenarios' bound series
+    int bound_stride;       // doubles between consecutive samples of one axis (2 walks, 1 ticks)
+    int bound_axis_offset;  // doubles between the x and the y series (1 for walks)
+    int bound_index_bias;   // window row j of tick i reads sample min(i + 1 + j, n-1) - bias
+    int n_max;              // allocated samples per scenario in the histories
+    const int32_t* n_steps; // [B] or nullptr (-> n_uniform)
+    int n_uniform;
+    int ticks_override;     // >0: run exactly this many ticks (single-tick API); else n-1
+    const double* init[2];  // x0, y0 ([B,3])
+    const double* z_min;
+    const double* z_max;
+    const double* impulse;  // [B] or nullptr
+    const int32_t* force_tick;  // [B] or nullptr
+    double* hist[2];        // x_hist, y_hist or nullptr
+    int write_initial;      // store sample 0 (walks) or not (single ticks)
+    long long hist_scn_stride;  // doubles between scenarios in hist (n_max*3 walks, 3 ticks)
+    int hist_index_bias;    // sample s is stored at row s - bias
+    uint8_t* flags;         // [B,n_max,2] or nullptr
+    double* max_violation;  // [B,2] or nullptr
+    int32_t* status;        // [B,2] or nullptr
+    int32_t* iters;         // [B,2] or nullptr
+    double* zmp_plan;       // [ncols,N] or nullptr: final previewed ZMP of the last tick
+};
+
+int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+int launch_jerk_from_zmp(lipm_plan* plan, int ncols, const double* state, const double* zmp_plan,
+                         double* jerk_plan, cudaStream_t stream);
+int launch_unconstrained_plan(lipm_plan* plan, int ncols, const double* state, const double* z_min,
+                              const double* z_max, int bounds_batch, double* zmp_plan,
+                              cudaStream_t stream);
+
+}  // namespace lipm

@@ -1,0 +1,232 @@
+"""ZMP preview controller: the reference's Python surface on top of the batched CUDA engine.
+
+Mirrors ``src/mpc_bipedal/controllers/zmp_controller.py`` of the reference: same
+class, method names, argument meaning, return shapes (NumPy float64) and error
+behaviour.  The per-tick QP, the state update and the whole receding-horizon
+loop run on the GPU (``mpc_bipedal.engine`` -> ``liblipm_mpc.so``); the
+single-walk methods are the B=1 case of ``generate_com_trajectory_batched``.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from ..config import MPCConfig
+from ..generators.cop_generator import State
+from ..models.lipm_model import discrete_model
+
+
+class ZMPController:
+    """ZMP controller using model predictive control (Wieber 2006) for a walking biped."""
+
+    def __init__(self, config: MPCConfig):
+        self.config = config
+        self.A, self.B, self.C = discrete_model(config.dt, config.h, config.g)   # reference :15-21
+        self.external_force = True
+        # ADMM settings of the strict mode (library defaults when left at 0 / -1)
+        self.solver_options: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------ engine access
+    def _plan(self, horizon: Optional[int] = None):
+        from .. import engine   # imported lazily: needs the built library and a CUDA device
+        c = self.config
+        return engine.get_plan(c.horizon if horizon is None else horizon, c.h, c.g, c.dt, c.Q, c.R,
+                               **self.solver_options)
+
+    def _mode(self) -> int:
+        return 1 if self.config.strict else 0
+
+    # ------------------------------------------------------------------ dispatcher (reference :23-57)
+    def generate_com_trajectory(self, x_init: np.ndarray, y_init: np.ndarray, z_max: np.ndarray = None,
+                                z_min: np.ndarray = None, v_ref: np.ndarray = None,
+                                state_ref: np.ndarray = None):
+        method = self.config.method.lower()
+        if method == "wieber":
+            if z_max is None or z_min is None:
+                raise ValueError("z_max and z_min are required for wieber method")
+            return self.generate_com_trajectory_wieber(x_init, y_init, z_max, z_min)
+        elif method == "herdt":
+            if v_ref is None or state_ref is None:
+                raise ValueError("v_ref and state_ref are required for herdt method")
+            return self.generate_com_trajectory_herdt(x_init, y_init, v_ref, state_ref)
+        else:
+            raise ValueError(f"Unknown method: {method}. Must be 'wieber' or 'herdt'")
+
+    # ------------------------------------------------------------------ batched entry (new, additive)
+    def generate_com_trajectory_batched(self, x_init, y_init, z_max, z_min, *, F_ext=None, m=None,
+                                        force_tick=None, n_steps=None, add_force: Optional[bool] = None,
+                                        strict: Optional[bool] = None, to_numpy: bool = True):
+        """Walks of B independent scenarios in one device launch.
+
+        x_init, y_init: (B,3).  z_max, z_min: (n,2) shared by all scenarios or (B,n,2).
+        F_ext, m: (B,) or scalars (default: config values); the push ``dt*F_ext/m`` hits the y
+        velocity after tick ``force_tick`` (default ``n_steps // 2`` as the reference, :90).
+        n_steps: (B,) int, bound samples per scenario (default: all n).
+        Returns dict(com (B,n,2), x_hist, y_hist (B,n,3), zmp (B,n,2), flags (B,n,2) uint8,
+        max_violation (B,), status (B,), iters (B,2)).
+        """
+        import torch
+        from .. import engine
+
+        cfg = self.config
+        plan = self._plan()
+        x_init = np.asarray(x_init, dtype=np.float64).reshape(-1, 3) if not torch.is_tensor(x_init) else x_init
+        y_init = np.asarray(y_init, dtype=np.float64).reshape(-1, 3) if not torch.is_tensor(y_init) else y_init
+        B = x_init.shape[0]
+        n = z_min.shape[-2]
+        push = cfg.add_force if add_force is None else add_force
+        impulse = tick = None
+        if push:
+            F = np.broadcast_to(np.asarray(cfg.F_ext if F_ext is None else F_ext, dtype=np.float64), (B,))
+            mass = np.broadcast_to(np.asarray(cfg.m if m is None else m, dtype=np.float64), (B,))
+            impulse = cfg.dt * F / mass                                      # reference :106
+            if force_tick is None:
+                steps = np.full((B,), n) if n_steps is None else np.asarray(n_steps)
+                tick = (steps // 2).astype(np.int32)                         # reference :90
+            else:
+                tick = np.broadcast_to(np.asarray(force_tick, dtype=np.int32), (B,)).copy()
+        mode = self._mode() if strict is None else (1 if strict else 0)
+        out = plan.rollout(mode, x_init, y_init, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick)
+        x_hist, y_hist = out["x_hist"], out["y_hist"]
+        c = torch.as_tensor(self.C, device=x_hist.device)
+        res = {
+            "com": torch.stack([x_hist[..., 0], y_hist[..., 0]], dim=-1),
+            "x_hist": x_hist, "y_hist": y_hist,
+            "zmp": torch.stack([x_hist @ c, y_hist @ c], dim=-1),            # reference run_mpc.py:294
+            "flags": out["flags"],
+            "max_violation": out["max_violation"].amax(dim=1),
+            "status": out["status"].sum(dim=1),
+            "iters": out["iters"],
+        }
+        if to_numpy:
+            res = {k: v.cpu().numpy() for k, v in res.items()}
+        return res
+
+    # ------------------------------------------------------------------ single walk (reference :59-147)
+    def _single_walk(self, x_init, y_init, z_max, z_min, push: bool):
+        z_max = np.ascontiguousarray(z_max, dtype=np.float64)
+        z_min = np.ascontiguousarray(z_min, dtype=np.float64)
+        res = self.generate_com_trajectory_batched(
+            np.asarray(x_init, dtype=np.float64).reshape(1, 3), np.asarray(y_init, dtype=np.float64).reshape(1, 3),
+            z_max, z_min, add_force=push)
+        if self.config.strict and int(res["status"][0]) != 0:
+            raise RuntimeError("QP solver did not find a solution (infeasible or other).")   # reference :193-194
+        return res
+
+    def generate_com_trajectory_wieber(self, x_init: np.ndarray, y_init: np.ndarray, z_max: np.ndarray,
+                                       z_min: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """CoM trajectory of one walk: ``(com (n,2), y_hist (n,3,1))``."""
+        n_steps = len(z_min)
+        force_time = n_steps // 2
+        print(f"Time of the external force: {(force_time * self.config.dt):.2f}s")
+        res = self._single_walk(x_init, y_init, z_max, z_min, push=bool(self.config.add_force))
+        return res["com"][0], res["y_hist"][0][:, :, None]
+
+    def generate_state_trajectory_wieber(self, x_init: np.ndarray, y_init: np.ndarray, z_max: np.ndarray,
+                                         z_min: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Full state histories ``(x_hist, y_hist)``, each (n,3,1); never pushes (reference :110-147)."""
+        res = self._single_walk(x_init, y_init, z_max, z_min, push=False)
+        return res["x_hist"][0][:, :, None], res["y_hist"][0][:, :, None]
+
+    # ------------------------------------------------------------------ one tick (reference :149-201)
+    def predict_wieber_axis(self, x_init: np.ndarray, nb_steps: int, z_max: np.ndarray, z_min: np.ndarray) -> np.ndarray:
+        """Next axis state (3,1) from state (3,1) and the bound window (nb_steps,1)."""
+        plan = self._plan(int(nb_steps))
+        lo = np.ascontiguousarray(z_min, dtype=np.float64).reshape(1, nb_steps)
+        hi = np.ascontiguousarray(z_max, dtype=np.float64).reshape(1, nb_steps)
+        res = plan.solve_tick(self._mode(), np.asarray(x_init, dtype=np.float64).reshape(1, 3), lo, hi)
+        if self.config.strict and int(res["status"][0].item()) != 0:
+            raise RuntimeError("QP solver did not find a solution (infeasible or other).")
+        return res["next_state"].cpu().numpy().reshape(3, 1)
+
+    def predict_wieber_axis_batched(self, states, z_max, z_min, want_plan: bool = False):
+        """B independent ticks at once: states (B,3), z_max/z_min (B,N) or (N,)."""
+        plan = self._plan()
+        return plan.solve_tick(self._mode(), states, z_min, z_max, want_plan=want_plan)
+
+    # ------------------------------------------------------------------ Herdt helpers (host side)
+    def find_nb_steps(self, state_ref) -> list:
+        """Per sample ``(steps_to_next_footstep_change, samples_of_current_footstep)``.
+
+        Same table as the reference's O(n^2) scan (`:203-433`), computed in O(n) from four
+        index maps: next DOUBLE_SUPPORT after i, next SINGLE_SUPPORT after i, last DOUBLE_SUPPORT
+        before i and the start of the DOUBLE_SUPPORT run that contains an index.
+        """
+        n = len(state_ref)
+        is_ds = [s == State.DOUBLE_SUPPORT for s in state_ref]
+        is_ss = [s == State.SINGLE_SUPPORT for s in state_ref]
+        next_ds, next_ss = [None] * n, [None] * n
+        seen_ds = seen_ss = None
+        for i in range(n - 1, -1, -1):
+            next_ds[i], next_ss[i] = seen_ds, seen_ss
+            if is_ds[i]:
+                seen_ds = i
+            if is_ss[i]:
+                seen_ss = i
+        prev_ds, run_start = [None] * n, [None] * n
+        last_ds = None
+        for i in range(n):
+            prev_ds[i] = last_ds
+            if is_ds[i]:
+                run_start[i] = run_start[i - 1] if i > 0 and is_ds[i - 1] else i
+                last_ds = i
+
+        to_next = [0] * n
+        for i in range(n):
+            remaining = n - i
+            s = state_ref[i]
+            if s == State.STANDING:
+                ds = next_ds[i]
+                ss = next_ss[ds] if ds is not None else None
+                to_next[i] = remaining if ss is None else ss - i - 1
+            elif s in (State.DOUBLE_SUPPORT, State.SINGLE_SUPPORT):
+                to_next[i] = remaining if next_ds[i] is None else next_ds[i] - i
+            else:
+                to_next[i] = remaining
+
+        result = [(0, 0)] * n
+        for i in range(n):
+            remaining = n - i
+            s = state_ref[i]
+            end = n if next_ds[i] is None else next_ds[i]
+            if s == State.STANDING:
+                if i == 0:
+                    total = to_next[0]
+                elif prev_ds[i] is not None:
+                    total = to_next[prev_ds[i]]
+                else:
+                    total = result[0][1]
+            elif s == State.DOUBLE_SUPPORT:
+                total = end - run_start[i]
+            elif s == State.SINGLE_SUPPORT:
+                total = end - run_start[prev_ds[i]] if prev_ds[i] is not None else remaining
+            else:
+                total = remaining
+            result[i] = (to_next[i], total)
+        return result
+
+    def _polytope_halfspace(self, vertices: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Convex polygon vertices -> ``A x <= b`` via Qhull facets (reference :828-865)."""
+        from scipy.spatial import ConvexHull
+
+        verts = np.asarray(vertices, dtype=float)
+        if verts.ndim != 2 or verts.shape[1] != 2 or len(verts) < 3:
+            raise ValueError("Polytope must be array-like of shape (k, 2), k>=3")
+        eq = ConvexHull(verts).equations            # rows [a, b, c], a x + b y + c <= 0 inside
+        A, b = eq[:, :2], -eq[:, 2]
+        worst = np.max(verts @ A.T - b)
+        if worst > 1e-10:
+            raise ValueError(f"Polytope half-space conversion failed: max violation = {worst}")
+        return A, b
+
+    # ------------------------------------------------------------------ Herdt (next scope row)
+    def generate_com_trajectory_herdt(self, x_init, y_init, v_ref, state_ref):
+        raise NotImplementedError(
+            "Herdt free-footstep MPC is not part of this build yet (SURVEY.md section 8(f), rank 1); "
+            "the Wieber path (method='wieber') is the implemented hot path")
+
+    def predict_herdt_joint(self, *args, **kwargs):
+        raise NotImplementedError(
+            "Herdt free-footstep MPC is not part of this build yet (SURVEY.md section 8(f), rank 1)")

@@ -1,0 +1,270 @@
+"""ctypes binding of the CUDA library (C ABI: ``include/lipm_mpc.h``).
+
+PyTorch is used for what it is good at here -- device memory, streams, NCCL --
+and nothing else: every tensor is handed to the library as a raw device pointer
+and the current stream handle.  There is no CPU path; importing this module on
+a machine without the built library or calling it without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+MODE_UNCONSTRAINED = 0
+MODE_STRICT = 1
+
+FLAG_ACTIVE_LO = 1
+FLAG_ACTIVE_HI = 2
+FLAG_VIOL_LO = 4
+FLAG_VIOL_HI = 8
+FLAG_NOT_CONVERGED = 16
+
+EXPORT_PX, EXPORT_PU, EXPORT_ABC, EXPORT_ADMM_M, EXPORT_HINV, EXPORT_GAIN, EXPORT_GPX = range(7)
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBRARY_PATH = os.path.join(_PKG_ROOT, "_lib", "liblipm_mpc.so")
+
+EXPORTED_SYMBOLS = (
+    "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout",
+    "lipm_solve_tick", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
+)
+
+
+class LipmError(RuntimeError):
+    """A call into liblipm_mpc failed; the message comes from ``lipm_last_error``."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"liblipm_mpc error {code}: {message}")
+        self.code = code
+
+
+class _PlanDesc(ctypes.Structure):
+    _fields_ = [
+        ("horizon", ctypes.c_int32),
+        ("h", ctypes.c_double), ("g", ctypes.c_double), ("dt", ctypes.c_double),
+        ("Q", ctypes.c_double), ("R", ctypes.c_double),
+        ("rho", ctypes.c_double), ("alpha", ctypes.c_double), ("eps", ctypes.c_double),
+        ("max_iter", ctypes.c_int32),
+        ("viol_tol", ctypes.c_double),
+        ("device", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the in-tree shared library; build it first with ``__graft_entry__.build()``."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBRARY_PATH):
+        raise ImportError(
+            f"{LIBRARY_PATH} not found: the CUDA library has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIBRARY_PATH)
+    vp, i32, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    lib.lipm_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_PlanDesc)]
+    lib.lipm_plan_create.restype = i32
+    lib.lipm_plan_destroy.argtypes = [vp]
+    lib.lipm_plan_destroy.restype = None
+    lib.lipm_plan_export.argtypes = [vp, i32, vp, ctypes.c_size_t]
+    lib.lipm_plan_export.restype = i32
+    lib.lipm_rollout.argtypes = [vp, i32, i32, i32] + [vp] * 5 + [i32] + [vp] * 9
+    lib.lipm_rollout.restype = i32
+    lib.lipm_solve_tick.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.lipm_solve_tick.restype = i32
+    lib.lipm_last_error.restype = ctypes.c_char_p
+    lib.lipm_version.restype = ctypes.c_char_p
+    lib.lipm_max_strict_horizon.restype = i32
+    _lib = lib
+    return lib
+
+
+def _check(code: int) -> None:
+    if code != 0:
+        raise LipmError(code, load_library().lipm_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dev_tensor(value, dtype, device, shape=None) -> torch.Tensor:
+    t = torch.as_tensor(value, dtype=dtype)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+@dataclass(frozen=True)
+class PlanKey:
+    horizon: int
+    h: float
+    g: float
+    dt: float
+    Q: float
+    R: float
+    rho: float = 0.0
+    alpha: float = 0.0
+    eps: float = 0.0
+    max_iter: int = 0
+    viol_tol: float = -1.0
+    device: int = 0
+
+
+class LipmPlan:
+    """Device-resident matrices for one ``(N, h, g, dt, Q, R)`` -- see ``lipm_plan_create``."""
+
+    def __init__(self, horizon: int, h: float, g: float, dt: Optional[float], Q: float, R: float, *,
+                 rho: float = 0.0, alpha: float = 0.0, eps: float = 0.0, max_iter: int = 0,
+                 viol_tol: float = -1.0, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("liblipm_mpc needs a CUDA device (B200 / sm_100a); there is no CPU path")
+        self._lib = load_library()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.init()
+        with torch.cuda.device(self.device_index):
+            torch.zeros(1, device=self.device)     # make sure the primary context exists
+        self.horizon = int(horizon)
+        self.dt = 1.5 / horizon if dt is None else float(dt)
+        desc = _PlanDesc(self.horizon, h, g, self.dt, Q, R, rho, alpha, eps, max_iter, viol_tol, self.device_index)
+        handle = ctypes.c_void_p()
+        _check(self._lib.lipm_plan_create(ctypes.byref(handle), ctypes.byref(desc)))
+        self._handle = handle
+        self.h, self.g, self.Q, self.R = h, g, Q, R
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.lipm_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ read-back
+    def export(self, which: int) -> np.ndarray:
+        N = self.horizon
+        shape = {EXPORT_PX: (N, 3), EXPORT_PU: (N, N), EXPORT_ABC: (15,), EXPORT_ADMM_M: (N, N),
+                 EXPORT_HINV: (N, N), EXPORT_GAIN: (N + 3,), EXPORT_GPX: (N, 3)}[which]
+        out = np.empty(shape, dtype=np.float64)
+        _check(self._lib.lipm_plan_export(self._handle, which, out.ctypes.data, out.size))
+        return out
+
+    # ------------------------------------------------------------------ walks
+    def rollout(self, mode: int, x0, y0, z_min, z_max, *, n_steps=None, impulse=None, force_tick=None,
+                want_flags: bool = True, want_iters: bool = True,
+                out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Batched walks (``lipm_rollout``).  Inputs may be host or device arrays.
+
+        x0, y0: (B,3); z_min, z_max: (n,2) shared or (B,n,2); n_steps: (B,) int32 or None;
+        impulse: (B,) = dt*F_ext/m or None; force_tick: (B,) int32 or None.
+        Returns device tensors x_hist, y_hist (B,n,3), flags (B,n,2) uint8,
+        max_violation (B,2), status (B,2) int32, iters (B,2) int32.
+        """
+        dev = self.device
+        x0 = _dev_tensor(x0, torch.float64, dev)
+        y0 = _dev_tensor(y0, torch.float64, dev)
+        if x0.ndim != 2 or x0.shape[1] != 3 or x0.shape != y0.shape:
+            raise ValueError("x0 and y0 must both have shape (B, 3)")
+        B = x0.shape[0]
+        z_min = _dev_tensor(z_min, torch.float64, dev)
+        z_max = _dev_tensor(z_max, torch.float64, dev)
+        if z_min.shape != z_max.shape or z_min.shape[-1] != 2 or z_min.ndim not in (2, 3):
+            raise ValueError("z_min and z_max must both have shape (n, 2) or (B, n, 2)")
+        bounds_batch = 1 if z_min.ndim == 2 else z_min.shape[0]
+        if bounds_batch not in (1, B):
+            raise ValueError("bounds batch must be 1 or B")
+        n_max = z_min.shape[-2]
+        n_steps_t = None if n_steps is None else _dev_tensor(n_steps, torch.int32, dev, (B,))
+        impulse_t = None if impulse is None else _dev_tensor(impulse, torch.float64, dev, (B,))
+        force_t = None if force_tick is None else _dev_tensor(force_tick, torch.int32, dev, (B,))
+        if out is None:
+            out = {}
+        def buf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+                t = torch.zeros(shape, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+        x_hist = buf("x_hist", (B, n_max, 3), torch.float64)
+        y_hist = buf("y_hist", (B, n_max, 3), torch.float64)
+        flags = buf("flags", (B, n_max, 2), torch.uint8) if want_flags else None
+        viol = buf("max_violation", (B, 2), torch.float64)
+        status = buf("status", (B, 2), torch.int32)
+        iters = buf("iters", (B, 2), torch.int32) if want_iters else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(self._lib.lipm_rollout(
+            self._handle, mode, B, n_max, _ptr(n_steps_t), _ptr(x0), _ptr(y0), _ptr(z_min), _ptr(z_max),
+            bounds_batch, _ptr(impulse_t), _ptr(force_t), _ptr(x_hist), _ptr(y_hist), _ptr(flags),
+            _ptr(viol), _ptr(status), _ptr(iters), stream))
+        # keep inputs alive until the stream has consumed them
+        out["_keepalive"] = (x0, y0, z_min, z_max, n_steps_t, impulse_t, force_t)
+        return out
+
+    # ------------------------------------------------------------------ single ticks
+    def solve_tick(self, mode: int, state, z_min, z_max, *, want_plan: bool = False) -> Dict[str, torch.Tensor]:
+        """One control tick for B independent axis problems (``lipm_solve_tick``).
+
+        state: (B,3); z_min, z_max: (N,) shared or (B,N).  Returns next_state (B,3), status (B,),
+        iters (B,) and, with ``want_plan``, zmp_plan and jerk_plan (B,N).
+        """
+        dev = self.device
+        N = self.horizon
+        state = _dev_tensor(state, torch.float64, dev)
+        if state.ndim != 2 or state.shape[1] != 3:
+            raise ValueError("state must have shape (B, 3)")
+        B = state.shape[0]
+        z_min = _dev_tensor(z_min, torch.float64, dev)
+        z_max = _dev_tensor(z_max, torch.float64, dev)
+        if z_min.shape != z_max.shape or z_min.shape[-1] != N or z_min.ndim not in (1, 2):
+            raise ValueError(f"z_min and z_max must both have shape ({N},) or (B, {N})")
+        bounds_batch = 1 if z_min.ndim == 1 else z_min.shape[0]
+        if bounds_batch not in (1, B):
+            raise ValueError("bounds batch must be 1 or B")
+        nxt = torch.empty((B, 3), dtype=torch.float64, device=dev)
+        status = torch.zeros((B,), dtype=torch.int32, device=dev)
+        iters = torch.zeros((B,), dtype=torch.int32, device=dev)
+        zmp_plan = torch.empty((B, N), dtype=torch.float64, device=dev) if want_plan else None
+        jerk_plan = torch.empty((B, N), dtype=torch.float64, device=dev) if want_plan else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(self._lib.lipm_solve_tick(
+            self._handle, mode, B, _ptr(state), _ptr(z_min), _ptr(z_max), bounds_batch, _ptr(nxt),
+            _ptr(zmp_plan), _ptr(jerk_plan), _ptr(status), _ptr(iters), stream))
+        res = {"next_state": nxt, "status": status, "iters": iters, "_keepalive": (state, z_min, z_max)}
+        if want_plan:
+            res["zmp_plan"], res["jerk_plan"] = zmp_plan, jerk_plan
+        return res
+
+
+_plan_cache: Dict[PlanKey, LipmPlan] = {}
+
+
+def get_plan(horizon: int, h: float, g: float, dt: float, Q: float, R: float, *, device: Optional[int] = None,
+             **solver) -> LipmPlan:
+    """Plans are immutable and cheap to keep: cache one per parameter set and device."""
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = PlanKey(int(horizon), float(h), float(g), float(dt), float(Q), float(R), device=dev, **solver)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        plan = LipmPlan(horizon, h, g, dt, Q, R, device=dev, **solver)
+        _plan_cache[key] = plan
+    return plan
+
+
+def library_version() -> str:
+    return load_library().lipm_version().decode()

@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's own outputs and the oracle.
+
+All tests need a B200 (``-m gpu``).  Tolerances (north_star): FP64 path <= 1e-9 relative on
+trajectories; flag bits bit-exact, except at ties, which are defined explicitly where used.
+``ref_*`` golden files are outputs of the reference itself; ``oracle_*`` of the exact oracle.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lipm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from mpc_bipedal import engine as eng
+    return eng
+
+
+@pytest.fixture(scope="module")
+def plan150(engine):
+    return engine.get_plan(150, 0.75, 9.81, 1.5 / 150, 1.0, 1e-6)
+
+
+def rel_err(got, want):
+    return float(np.max(np.abs(np.asarray(got) - np.asarray(want))) / max(np.max(np.abs(want)), 1e-300))
+
+
+# ----------------------------------------------------------------------------- plan matrices
+@pytest.mark.parametrize("N,h", [(150, 0.75), (100, 0.62), (16, 0.9), (37, 0.75)])
+def test_plan_matrices(engine, N, h):
+    plan = engine.get_plan(N, h, 9.81, 1.5 / N, 1.0, 1e-6)
+    p = orc.Problem.make(N, h=h)
+    # Px, Pu, A, B, C: bit-identical to the reference's float64 loop (zmp_controller.py:15-21,162-171)
+    assert np.array_equal(plan.export(engine.EXPORT_PX), p.Px)
+    assert np.array_equal(plan.export(engine.EXPORT_PU), p.Pu)
+    abc = plan.export(engine.EXPORT_ABC)
+    assert np.array_equal(abc[:9].reshape(3, 3), p.A) and np.array_equal(abc[9:12], p.B) and np.array_equal(abc[12:], p.C)
+    c = p._cache()
+    M = np.linalg.inv(c["Hz"] + 2.0 * np.eye(N))
+    assert rel_err(plan.export(engine.EXPORT_ADMM_M), M) < 1e-11
+    assert rel_err(plan.export(engine.EXPORT_HINV), np.linalg.inv(c["Hz"])) < 1e-11
+    assert rel_err(plan.export(engine.EXPORT_GPX), c["GPx"]) < 1e-11
+    # first-jerk gain row against the reference's closed form -inv(Pu'Pu + R/Q I) Pu' (Px x - zref)
+    K = (c["Hu_inv"] @ p.Pu.T)[0]
+    gain = plan.export(engine.EXPORT_GAIN)
+    assert rel_err(gain[:N], K) < 1e-9
+    assert rel_err(gain[N:], -K @ p.Px) < 1e-9
+
+
+# ----------------------------------------------------------------------------- unconstrained mode
+def test_nonstrict_ticks_match_reference(engine, golden):
+    g = golden("ref_nonstrict_ticks")
+    for N in (10, 50, 100, 150):
+        for h in (0.75, 0.62):
+            key = f"N{N}_h{h}"
+            plan = engine.get_plan(N, h, 9.81, 1.5 / N, 1.0, 1e-6)
+            res = plan.solve_tick(engine.MODE_UNCONSTRAINED, g[f"{key}/x"], g[f"{key}/z_min"], g[f"{key}/z_max"],
+                                  want_plan=True)
+            got = res["next_state"].cpu().numpy()
+            assert rel_err(got, g[f"{key}/next"]) < REL, key
+            # the full jerk sequence is the reference's X_burst: check it through Pu J + Px x = zmp plan
+            p = orc.Problem.make(N, h=h)
+            zmp, jerk = res["zmp_plan"].cpu().numpy(), res["jerk_plan"].cpu().numpy()
+            for k in range(len(got)):
+                x = g[f"{key}/x"][k]
+                zref = (g[f"{key}/z_max"][k] + g[f"{key}/z_min"][k]) / 2
+                want_jerk = -p._cache()["Hu_inv"] @ p.Pu.T @ (p.Px @ x - zref)
+                assert rel_err(jerk[k], want_jerk) < 1e-8, key
+                assert np.max(np.abs(p.Pu @ jerk[k] + p.Px @ x - zmp[k])) < 1e-11
+
+
+def test_nonstrict_default_walk_matches_reference(engine, plan150, golden):
+    g = golden("ref_nonstrict_walk")
+    zero = np.zeros((1, 3))
+    out = plan150.rollout(engine.MODE_UNCONSTRAINED, zero, zero, g["z_min"], g["z_max"],
+                          impulse=[float(g["impulse"])], force_tick=[int(g["force_tick"])])
+    y_hist = out["y_hist"][0].cpu().numpy()
+    x_hist = out["x_hist"][0].cpu().numpy()
+    assert rel_err(y_hist, g["y_hist"][:, :, 0]) < REL
+    assert rel_err(np.stack([x_hist[:, 0], y_hist[:, 0]], 1), g["com"]) < REL
+    # max ZMP-y violation 0.038 m after the push
+    viol = out["max_violation"][0].cpu().numpy()
+    assert 0.03 < viol[1] < 0.045 and viol[0] < 1e-3
+    flags = out["flags"][0].cpu().numpy()
+    assert (flags[:, 1] & (engine.FLAG_VIOL_LO | engine.FLAG_VIOL_HI)).any()
+    assert not (flags & (engine.FLAG_ACTIVE_LO | engine.FLAG_ACTIVE_HI | engine.FLAG_NOT_CONVERGED)).any()
+    # no push: generate_state_trajectory_wieber
+    out = plan150.rollout(engine.MODE_UNCONSTRAINED, zero, zero, g["z_min"], g["z_max"])
+    assert rel_err(out["x_hist"][0].cpu().numpy(), g["nopush_x_hist"][:, :, 0]) < REL
+    assert rel_err(out["y_hist"][0].cpu().numpy(), g["nopush_y_hist"][:, :, 0]) < REL
+
+
+# ----------------------------------------------------------------------------- strict mode
+@pytest.mark.parametrize("N", [16, 50, 150])
+def test_strict_ticks_match_exact_oracle(engine, golden, N):
+    g = golden("oracle_strict_ticks")
+    plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    x, lo, hi = g[f"N{N}/x"], g[f"N{N}/z_min"], g[f"N{N}/z_max"]
+    res = plan.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    assert (res["status"].cpu().numpy() == 0).all()
+    z = res["zmp_plan"].cpu().numpy()
+    assert np.max(np.abs(z - g[f"N{N}/z"])) < 1e-10
+    assert np.max(np.abs(res["next_state"].cpu().numpy() - g[f"N{N}/next"])) < 1e-9
+    assert (z >= lo).all() and (z <= hi).all()                      # exactly feasible: clipped values
+    # active set by equality; tie = oracle row free but within 1e-9 of a bound
+    act = np.where(z == lo, -1, 0) + np.where(z == hi, 1, 0)
+    want = g[f"N{N}/active"]
+    free_margin = np.minimum(g[f"N{N}/z"] - lo, hi - g[f"N{N}/z"])
+    decided = (want != 0) | (free_margin > 1e-9)
+    assert np.array_equal(act[decided], want[decided])
+    # jerk plan consistent with the ZMP plan
+    p = orc.Problem.make(N)
+    jerk = res["jerk_plan"].cpu().numpy()
+    for k in range(0, len(x), 5):
+        assert np.max(np.abs(p.Pu @ jerk[k] + p.Px @ x[k] - z[k])) < 1e-11
+
+
+def check_flags(flags, want_flags, margin_of_got, engine, tie=1e-9):
+    """Flags must be bit-exact except at ties: samples whose realised ZMP is within `tie` of a
+    bound, where 'on the bound' vs 'just inside' is decided by the last bits of the solve."""
+    diff = flags != want_flags
+    assert not (diff & (np.abs(margin_of_got) > tie)).any()
+    return int(diff.sum())
+
+
+def test_strict_default_walk_matches_exact_oracle(engine, plan150, golden):
+    g = golden("oracle_strict_walk")
+    zero = np.zeros((1, 3))
+    out = plan150.rollout(engine.MODE_STRICT, zero, zero, g["z_min"], g["z_max"],
+                          impulse=[float(g["impulse"])], force_tick=[int(g["force_tick"])])
+    assert (out["status"].cpu().numpy() == 0).all()
+    x_hist, y_hist = out["x_hist"][0].cpu().numpy(), out["y_hist"][0].cpu().numpy()
+    assert rel_err(x_hist, g["x_hist"]) < REL
+    assert rel_err(y_hist, g["y_hist"]) < REL
+    p = orc.Problem.make(150)
+    zmp = np.stack([x_hist @ p.C, y_hist @ p.C], 1)
+    margin = np.minimum(zmp - g["z_min"], g["z_max"] - zmp)
+    assert margin.min() > -1e-12                                    # strict: ZMP stays in the box
+    flags = out["flags"][0].cpu().numpy()
+    ties = check_flags(flags, g["flags"], margin, engine)
+    assert ties <= 8
+    assert out["max_violation"].max().item() < 1e-12
+    iters = out["iters"][0].cpu().numpy()
+    assert 5 * 419 < iters[0] < 80 * 419 and 5 * 419 < iters[1] < 80 * 419
+
+
+def test_strict_equals_unconstrained_when_box_is_wide(engine, plan150):
+    rng = np.random.default_rng(0)
+    B, n = 40, 60
+    x0 = rng.normal(size=(B, 3)) * [0.02, 0.05, 0.1]
+    y0 = rng.normal(size=(B, 3)) * [0.02, 0.05, 0.1]
+    lo, hi = np.full((n, 2), -50.0), np.full((n, 2), 50.0)
+    a = plan150.rollout(engine.MODE_STRICT, x0, y0, lo, hi)
+    a = {k: v.cpu().numpy() for k, v in a.items() if not k.startswith("_")}
+    b = plan150.rollout(engine.MODE_UNCONSTRAINED, x0, y0, lo, hi)
+    b = {k: v.cpu().numpy() for k, v in b.items() if not k.startswith("_")}
+    assert (a["status"] == 0).all() and not a["flags"].any()
+    assert rel_err(a["x_hist"], b["x_hist"]) < REL and rel_err(a["y_hist"], b["y_hist"]) < REL
+
+
+def push_sweep_inputs(B, seed=0):
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.generators import CoPGenerator
+    cfg = MPCConfig.from_json(os.path.join(REPO, "configs", "default.json"))
+    z_max, z_min, _ = CoPGenerator(cfg).generate_cop_trajectory(save_footsteps=False)
+    rng = np.random.default_rng(seed)
+    F = rng.uniform(0.0, 1000.0, B)
+    tick = rng.integers(100, 320, B).astype(np.int32)
+    return cfg, z_max, z_min, cfg.dt * F / cfg.m, tick
+
+
+def test_batch_results_do_not_depend_on_batch_layout(engine, plan150):
+    """A scenario's output is bit-identical whatever batch / tile / position it is solved in
+    (multi-GPU row: sharding must not change results)."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(37)
+    n = 90                                     # first 90 samples: standing + first steps, short test
+    z_max, z_min = z_max[:n], z_min[:n]
+    tick = (tick % 60 + 10).astype(np.int32)
+    zero = np.zeros((37, 3))
+    full = plan150.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, impulse=impulse, force_tick=tick)
+    full = {k: v.cpu().numpy() for k, v in full.items() if not k.startswith("_")}
+    pick = np.array([36, 5, 20])
+    sub = plan150.rollout(engine.MODE_STRICT, zero[pick], zero[pick], z_min, z_max, impulse=impulse[pick],
+                          force_tick=tick[pick])
+    sub = {k: v.cpu().numpy() for k, v in sub.items() if not k.startswith("_")}
+    for key in ("x_hist", "y_hist", "flags", "iters", "max_violation", "status"):
+        assert np.array_equal(sub[key], full[key][pick]), key
+    # per-scenario bounds (B,n,2) give the same bits as the shared (n,2) series
+    per = plan150.rollout(engine.MODE_STRICT, zero[pick], zero[pick], np.repeat(z_min[None], 3, 0),
+                          np.repeat(z_max[None], 3, 0), impulse=impulse[pick], force_tick=tick[pick])
+    assert np.array_equal(per["y_hist"].cpu().numpy(), sub["y_hist"])
+
+
+def test_ragged_walks(engine, plan150):
+    """n_steps per scenario: each walk equals the same walk run alone on its truncated series;
+    the last bound row is what gets repeated past the end (zmp_controller.py:81-88)."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(5, seed=3)
+    n_steps = np.array([70, 2, 64, 33, 70], np.int32)
+    tick = (n_steps // 2).astype(np.int32)
+    zero = np.zeros((5, 3))
+    for mode in (engine.MODE_STRICT, engine.MODE_UNCONSTRAINED):
+        out = plan150.rollout(mode, zero, zero, z_min[:70], z_max[:70], n_steps=n_steps, impulse=impulse, force_tick=tick)
+        out = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+        for b, n in enumerate(n_steps):
+            one = plan150.rollout(mode, zero[:1], zero[:1], z_min[:n], z_max[:n], impulse=impulse[b:b + 1],
+                                  force_tick=tick[b:b + 1])
+            assert np.array_equal(one["y_hist"][0].cpu().numpy(), out["y_hist"][b, :n]), (mode, b)
+            assert np.array_equal(one["x_hist"][0].cpu().numpy(), out["x_hist"][b, :n])
+            assert np.array_equal(one["flags"][0].cpu().numpy(), out["flags"][b, :n])
+            assert not out["y_hist"][b, n:].any()              # untouched past the end
+
+
+def test_push_sweep_full_size_properties(engine, plan150):
+    """BASELINE config 2 at full size (4096 scenarios, N=150, strict): size-independent properties."""
+    B = 4096
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(B)
+    impulse[:8] = 0.0                                            # eight scenarios without push
+    zero = np.zeros((B, 3))
+    out = plan150.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, impulse=impulse, force_tick=tick)
+    status = out["status"].cpu().numpy()
+    assert (status == 0).all()
+    assert out["max_violation"].max().item() < 1e-9             # strict keeps the ZMP in the box
+    y_hist = out["y_hist"].cpu().numpy()
+    x_hist = out["x_hist"].cpu().numpy()
+    assert np.isfinite(y_hist).all() and np.isfinite(x_hist).all()
+    # the push acts on y only: every x trajectory is the same walk, bit for bit
+    assert (x_hist == x_hist[0]).all()
+    # scenarios without push coincide; identical (F, tick) pairs coincide
+    assert (y_hist[:8] == y_hist[0]).all()
+    # before its push every scenario follows the push-free walk exactly
+    for b in (8, 100, 4095):
+        assert np.array_equal(y_hist[b, : tick[b] + 1], y_hist[0, : tick[b] + 1])
+        assert not np.array_equal(y_hist[b, tick[b] + 1], y_hist[0, tick[b] + 1])
+    # spot-check two scenarios against the oracle (ADMM, FP64)
+    p = orc.Problem.make(150)
+    b = 100
+    want = orc.rollout_wieber(p, np.zeros(3), np.zeros(3), z_max, z_min, strict=True, impulse=impulse[b],
+                              force_tick=int(tick[b]), solver="admm", n_ticks=int(tick[b]) + 12)
+    m = len(want["y_hist"])
+    assert rel_err(y_hist[b, :m], want["y_hist"]) < REL
+
+
+def test_errors_are_loud(engine):
+    plan = engine.get_plan(300, 0.75, 9.81, 1.5 / 300, 1.0, 1e-6)
+    zero = np.zeros((2, 3))
+    lo, hi = -np.ones((400, 2)), np.ones((400, 2))
+    with pytest.raises(engine.LipmError, match="horizon 300"):
+        plan.rollout(engine.MODE_STRICT, zero, zero, lo, hi)
+    out = plan.rollout(engine.MODE_UNCONSTRAINED, zero, zero, lo, hi)       # unconstrained has no such limit
+    assert np.isfinite(out["x_hist"].cpu().numpy()).all()
+    with pytest.raises(ValueError):
+        plan.rollout(engine.MODE_UNCONSTRAINED, zero, zero, lo[:, :1], hi[:, :1])
+    with pytest.raises(engine.LipmError):
+        engine.LipmPlan(150, 0.75, 9.81, None, 1.0, -1.0)
+    with pytest.raises(engine.LipmError):
+        engine.LipmPlan(1, 0.75, 9.81, None, 1.0, 1e-6)
+
+
+def test_reference_python_surface_on_gpu(golden):
+    """The reference's own call sequence (scripts/run_mpc.py:273-294) through the mirrored API."""
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.controllers import ZMPController
+    from mpc_bipedal.generators import CoPGenerator
+
+    cfg = MPCConfig.from_json(os.path.join(REPO, "configs", "default.json"))
+    z_max, z_min, _ = CoPGenerator(cfg).generate_cop_trajectory(save_footsteps=False)
+    ctrl = ZMPController(cfg)
+    zero = np.zeros((3, 1))
+    com, y_hist = ctrl.generate_com_trajectory(zero, zero.copy(), z_max, z_min)
+    g = golden("oracle_strict_walk")
+    assert com.shape == (420, 2) and y_hist.shape == (420, 3, 1)
+    assert rel_err(y_hist[:, :, 0], g["y_hist"]) < REL
+    zmp_y = np.tensordot(y_hist[:, :, 0], ctrl.C, axes=([1], [0]))
+    assert (zmp_y >= z_min[:, 1] - 1e-12).all() and (zmp_y <= z_max[:, 1] + 1e-12).all()
+    # one tick, both modes, reference signature: (3,1), N, (N,1), (N,1) -> (3,1)
+    nxt = ctrl.predict_wieber_axis(zero, 150, z_max[1:151, 1:2], z_min[1:151, 1:2])
+    assert nxt.shape == (3, 1) and np.max(np.abs(nxt[:, 0] - g["y_hist"][1])) < 1e-10
+    cfg.strict = False
+    gn = golden("ref_nonstrict_walk")
+    nxt = ctrl.predict_wieber_axis(zero, 150, z_max[1:151, 1:2], z_min[1:151, 1:2])
+    assert np.max(np.abs(nxt[:, 0] - gn["y_hist"][1, :, 0])) < 1e-12
+    x_state, y_state = ctrl.generate_state_trajectory_wieber(zero, zero.copy(), z_max, z_min)
+    assert x_state.shape == (420, 3, 1)
+    assert rel_err(x_state, gn["nopush_x_hist"]) < REL and rel_err(y_state, gn["nopush_y_hist"]) < REL
