@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""Headline benchmark: QP solves/sec of the batched N=150 strict LIPM-MPC push sweep.
+
+Workload (BASELINE.json configs[1]): 4096 scenarios per GPU, each a full configs/default.json
+walk (420 bound samples -> 419 ticks x 2 axes = 838 strict QP solves), with a push
+F_ext ~ U(0,1000) N at a tick ~ U{100..319}, m = 40 kg, seed 0, bounds shared by all scenarios.
+One "step" = one sweep = B x 838 solves.  Scenarios shard across GPUs with no data-path
+collective; the only exchange is one NCCL all-gather of the per-scenario outcomes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (see the keys below).  `--impl reference` times the CPU restatement of the
+reference path (oracle port; the reference's own strict path needs cvxpy/OSQP, which are not
+installed, and its Python sources do not travel to the GPU box) on all host cores.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PACKAGE_DIR = os.path.join(REPO, "model-predictive-control-for-bipedal-locomotion_b200")
+for _p in (REPO, PACKAGE_DIR):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "QP solves/sec (N=150 LIPM MPC, strict, batched push sweep)"
+UNIT = "solves/s"
+SCENARIOS_PER_GPU = 4096
+WORKLOAD = "push-sweep-4096 (BASELINE configs[1]): default.json walk n=420, N=150, strict, F_ext~U(0,1000)N, tick~U{100..319}"
+
+
+def sweep_inputs(B, seed=0):
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.generators import CoPGenerator
+
+    cfg = MPCConfig.from_json(os.path.join(REPO, "configs", "default.json"))
+    z_max, z_min, _ = CoPGenerator(cfg).generate_cop_trajectory(save_footsteps=False)
+    rng = np.random.default_rng(seed)
+    F = rng.uniform(0.0, 1000.0, B)
+    tick = rng.integers(100, 320, B).astype(np.int32)
+    return cfg, z_max, z_min, F, tick
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(walks_per_thread=16, steps=1):
+    """Oracle port (oracle/lipm_oracle.c: same ADMM, cached matrices, warm start) on all host cores.
+
+    A bounded sample of the same workload: `walks_per_thread` x threads full default.json strict
+    walks (838 solves each) per step, OpenMP over scenarios.  The reference itself would also
+    rebuild Px/Pu in Python and go through cvxpy/OSQP on every solve (not runnable here), so this
+    port is an optimistic stand-in for it."""
+    from oracle.c_oracle import COracle
+
+    try:
+        oracle = COracle(150, native=True)           # -march=native, built on this host
+    except Exception:
+        oracle = COracle(150)                        # portable prebuilt (x86-64-v3)
+    threads = oracle.max_threads()
+    n_walks = walks_per_thread * threads
+    cfg, z_max, z_min, F, tick = sweep_inputs(n_walks)
+    zero = np.zeros((n_walks, 3))
+    impulse = cfg.dt * F / cfg.m
+    oracle.rollout(True, zero[:threads], zero[:threads], z_min, z_max, impulse=impulse[:threads],
+                   force_tick=tick[:threads])        # warm-up
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        res = oracle.rollout(True, zero, zero, z_min, z_max, impulse=impulse, force_tick=tick)
+        times.append(time.perf_counter() - t0)
+    assert (res["status"] == 0).all()
+    solves = n_walks * 2 * (len(z_min) - 1)
+    return {"value": solves / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_walks} full default.json strict walks ({solves} solves) per step; C restatement "
+                      f"(oracle/lipm_oracle.c), FP64 ADMM rho=2 alpha=1.6 eps=1e-12, matrices cached, warm start, "
+                      f"OpenMP over scenarios on {threads} threads",
+            "mean_iters_per_solve": float(res["iters"].sum()) / solves,
+            "seconds_per_step": float(np.mean(times))}, times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base, times = cpu_baseline(steps=max(1, min(args.steps, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": 1, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "horizon": 150, "mode": "strict",
+                   "note": "CPU restatement of the reference path; the reference's strict branch needs cvxpy+OSQP "
+                           "(absent) and its sources are not on this box"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def measure_fp64_peak(torch, device, n=4096, reps=5):
+    """cuBLAS DGEMM throughput measured like MEASURED_PEAKS.json measures bf16 (best of reps)."""
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(device)
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record()
+        torch.cuda.synchronize(device)
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from mpc_bipedal import engine
+    from mpc_bipedal.controllers import ZMPController
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    B = args.batch
+    cfg, z_max, z_min, F, tick = sweep_inputs(B, seed=rank)
+    n = len(z_min)
+    solves_per_step = B * 2 * (n - 1)
+    plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R)
+    mode = engine.MODE_STRICT if args.mode == "strict" else engine.MODE_UNCONSTRAINED
+
+    # device-resident inputs for `value`
+    d = lambda a, dt: torch.as_tensor(a, dtype=dt).to(device)
+    x0 = torch.zeros((B, 3), dtype=torch.float64, device=device)
+    y0 = torch.zeros((B, 3), dtype=torch.float64, device=device)
+    zmin_d, zmax_d = d(z_min, torch.float64), d(z_max, torch.float64)
+    imp_d, tick_d = d(cfg.dt * F / cfg.m, torch.float64), d(tick, torch.int32)
+    out = {}
+    gathered = [torch.empty((B, 2), dtype=torch.float64, device=device) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def step():
+        plan.rollout(mode, x0, y0, zmin_d, zmax_d, impulse=imp_d, force_tick=tick_d, out=out)
+        if world > 1:   # the path's only exchange: per-scenario outcomes
+            dist.all_gather(gathered, out["max_violation"])
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+
+    events = []
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            flush.fill_(1)                      # evict L2 between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record()
+            events.append((e0, e1))
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+    step_ms = [a.elapsed_time(b) for a, b in events]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = total_ms.item() * 1e-3
+    value = world * solves_per_step * args.steps / total_s
+
+    iters = out["iters"].sum().item() if mode == engine.MODE_STRICT else 0
+    status_bad = int((out["status"] != 0).sum().item())
+    max_viol = out["max_violation"].max().item()
+
+    # ---- end to end through the public API with host buffers ---------------------------------------
+    ctrl = ZMPController(cfg)
+    ctrl.config.strict = (args.mode == "strict")
+    hx0 = np.zeros((B, 3)); hy0 = np.zeros((B, 3))
+    e2e_steps = max(1, min(args.steps, 3))
+    ctrl.generate_com_trajectory_batched(hx0, hy0, z_max, z_min, F_ext=F, force_tick=tick)   # warm
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = ctrl.generate_com_trajectory_batched(hx0, hy0, z_max, z_min, F_ext=F, force_tick=tick)
+    torch.cuda.synchronize(device)
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    h2d = hx0.nbytes + hy0.nbytes + z_max.nbytes + z_min.nbytes + F.nbytes + tick.nbytes
+    d2h = int(sum(v.nbytes for v in res.values()))
+    e2e_value = world * solves_per_step / e2e_s.item()
+
+    if rank == 0:
+        N = cfg.horizon
+        kernel_s = np.mean(step_ms) * 1e-3
+        flops = 2.0 * N * N * iters                      # K_exec * 2 N^2 per solve
+        peak = measure_fp64_peak(torch, device)
+        achieved = flops / kernel_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenarios_per_gpu": B, "horizon": N, "samples_per_walk": n,
+                       "mode": args.mode, "solves_per_step_per_gpu": solves_per_step,
+                       "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "admm": {"rho": 2.0, "alpha": 1.6, "eps": 1e-12,
+                                "mean_iters_per_solve": iters / max(solves_per_step, 1)}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                    "api": "ZMPController.generate_com_trajectory_batched (NumPy in, NumPy out)"},
+            "gpu_launches": args.steps,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_strict_rollout (FP64 DMMA.8x8x4 ADMM)",
+                         "peak_source": "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run "
+                                        "(MEASURED_PEAKS.json has no FP64 entry)",
+                         "algorithmic_flops_per_step": flops},
+            "checks": {"not_converged_columns": status_bad, "max_zmp_violation_m": max_viol},
+            "latency": {"p50_step_ms": float(np.median(step_ms)),
+                        "p50_tick_ms_amortised": float(np.median(step_ms)) / (n - 1)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _ = cpu_baseline()
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=SCENARIOS_PER_GPU, help="scenarios per GPU")
+    ap.add_argument("--mode", choices=["strict", "unconstrained"], default="strict")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

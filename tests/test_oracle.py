@@ -121,3 +121,63 @@ def test_strict_walk_admm_rollout_matches_exact_prefix(golden):
                              impulse=float(g["impulse"]), force_tick=5, solver="admm", n_ticks=ticks)
     assert np.max(np.abs(res["x_hist"] - g["x_hist"][start:start + ticks + 1])) < 1e-10
     assert np.max(np.abs(res["y_hist"] - g["y_hist"][start:start + ticks + 1])) < 1e-10
+
+
+# ----------------------------------------------------------------------------- C restatement
+def test_c_oracle_matrices_and_walks(golden):
+    from oracle.c_oracle import COracle
+
+    c = COracle(150)
+    p = orc.Problem.make(150)
+    m = c.export()
+    assert np.array_equal(m["Px"], p.Px) and np.array_equal(m["Pu"], p.Pu)     # bit-identical to the reference loop
+    assert np.max(np.abs(m["M"] - orc.admm_matrix(p, 2.0))) < 1e-12
+    K = (p._cache()["Hu_inv"] @ p.Pu.T)[0]
+    assert np.max(np.abs(m["gain"][:150] - K)) / np.max(np.abs(K)) < 1e-9
+
+    # non-strict walk against the reference's own output
+    g = golden("ref_nonstrict_walk")
+    zero = np.zeros((1, 3))
+    res = c.rollout(False, zero, zero, g["z_min"], g["z_max"], impulse=[float(g["impulse"])],
+                    force_tick=[int(g["force_tick"])])
+    assert np.max(np.abs(res["y_hist"][0] - g["y_hist"][:, :, 0])) <= 1e-9 * np.max(np.abs(g["y_hist"]))
+    assert np.max(np.abs(res["x_hist"][0, :, 0] - g["com"][:, 0])) <= 1e-9 * np.max(np.abs(g["com"]))
+
+    # strict walk against the exact (BVLS) oracle, flags included
+    g = golden("oracle_strict_walk")
+    res = c.rollout(True, zero, zero, g["z_min"], g["z_max"], impulse=[float(g["impulse"])],
+                    force_tick=[int(g["force_tick"])])
+    assert (res["status"] == 0).all()
+    assert np.max(np.abs(res["x_hist"][0] - g["x_hist"])) <= 1e-9 * np.max(np.abs(g["x_hist"]))
+    assert np.max(np.abs(res["y_hist"][0] - g["y_hist"])) <= 1e-9 * np.max(np.abs(g["y_hist"]))
+    zmp = np.stack([res["x_hist"][0] @ p.C, res["y_hist"][0] @ p.C], 1)
+    margin = np.minimum(zmp - g["z_min"], g["z_max"] - zmp)
+    diff = res["flags"][0] != g["flags"]
+    assert not (diff & (np.abs(margin) > 1e-9)).any()          # flags bit-exact away from ties
+    assert diff.sum() <= 8
+    assert 10 < res["iters"].sum() / 838 < 60
+
+
+def test_c_oracle_ragged_and_batched():
+    from oracle.c_oracle import COracle
+
+    c = COracle(40)
+    rng = np.random.default_rng(5)
+    n = 55
+    centre = np.cumsum((rng.random((n, 2)) < 0.1) * rng.uniform(-0.05, 0.05, (n, 2)), 0)
+    z_min, z_max = centre - 0.04, centre + 0.04
+    B = 6
+    x0 = rng.normal(size=(B, 3)) * [0.01, 0.02, 0.05]
+    y0 = rng.normal(size=(B, 3)) * [0.01, 0.02, 0.05]
+    n_steps = np.array([55, 2, 30, 55, 17, 41], np.int32)
+    imp = rng.uniform(0, 0.05, B)
+    tick = (n_steps // 2).astype(np.int32)
+    res = c.rollout(True, x0, y0, z_min, z_max, n_steps=n_steps, impulse=imp, force_tick=tick, threads=3)
+    p = orc.Problem.make(40)
+    for b in (0, 2, 4):
+        nb = n_steps[b]
+        want = orc.rollout_wieber(p, x0[b], y0[b], z_max[:nb], z_min[:nb], strict=True, impulse=imp[b],
+                                  force_tick=int(tick[b]), solver="exact")
+        assert np.max(np.abs(res["y_hist"][b, :nb] - want["y_hist"])) < 1e-9
+        assert np.max(np.abs(res["x_hist"][b, :nb] - want["x_hist"])) < 1e-9
+        assert not res["y_hist"][b, nb:].any()
