@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
     double* sR = sGPx + P.NP * 3;
     double* sX = sR + C * P.KP;
     double* sRes = sX + C * 3;
-    double* sImp = sRes + kRowGroups * C;
+    double* sImp = sRes + 2 * kRowGroups * C;   // sRes: [rg][C] residuals, then [rg][C] rhs magnitudes
     double* sViol = sImp + C;
     const double** sLo = reinterpret_cast<const double**>(sViol + C);
     const double** sHi = sLo + C;
@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                     }
                 }
 
-                double res[2] = {0.0, 0.0};
+                // residuals and the magnitude of the new right-hand side (stop test is relative to it)
+                double res[2] = {0.0, 0.0}, mag[2] = {0.0, 0.0};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     if (!done[e]) {
@@ -332,19 +333,26 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                             const double zn = fmin(fmax(tn, lo[r][e]), hi[r][e]);
                             res[e] = fmax(res[e], fmax(fabs(v - zn), P.rho * fabs(zn - zo)));
                             tv[r][e] = tn;
-                            acc[r][e] = fma(P.rho, 2.0 * zn - tn, -q[r][e]);
+                            const double rn = fma(P.rho, 2.0 * zn - tn, -q[r][e]);
+                            mag[e] = fmax(mag[e], fabs(rn));
+                            acc[r][e] = rn;
                         }
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    res[e] = fmax(res[e], __shfl_xor_sync(0xffffffffu, res[e], 4));
-                    res[e] = fmax(res[e], __shfl_xor_sync(0xffffffffu, res[e], 8));
-                    res[e] = fmax(res[e], __shfl_xor_sync(0xffffffffu, res[e], 16));
+#pragma unroll
+                    for (int o = 4; o <= 16; o <<= 1) {
+                        res[e] = fmax(res[e], __shfl_xor_sync(0xffffffffu, res[e], o));
+                        mag[e] = fmax(mag[e], __shfl_xor_sync(0xffffffffu, mag[e], o));
+                    }
                 }
                 if (g == 0) {
-                    sRes[rg * C + lc0 + 0] = res[0];
-                    sRes[rg * C + lc0 + 1] = res[1];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        sRes[rg * C + lc0 + e] = res[e];
+                        sRes[(kRowGroups + rg) * C + lc0 + e] = mag[e];
+                    }
                 }
                 __syncthreads();   // every warp has consumed R; residual partials are visible
 
@@ -355,11 +363,14 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
 #pragma unroll
                         for (int r = 0; r < NRB; ++r)
                             if (r < nrb) rOut0[e * KP + r * 8] = acc[r][e];
-                        double cr = sRes[lc0 + e];
+                        double cr = sRes[lc0 + e], cm = sRes[kRowGroups * C + lc0 + e];
 #pragma unroll
-                        for (int q4 = 1; q4 < kRowGroups; ++q4) cr = fmax(cr, sRes[q4 * C + lc0 + e]);
+                        for (int q4 = 1; q4 < kRowGroups; ++q4) {
+                            cr = fmax(cr, sRes[q4 * C + lc0 + e]);
+                            cm = fmax(cm, sRes[(kRowGroups + q4) * C + lc0 + e]);
+                        }
                         ++iters[e];
-                        done[e] = (cr <= P.eps);
+                        done[e] = (cr <= P.eps * fmax(1.0, cm));
                     }
                     all_mine = all_mine && done[e];
                 }
@@ -433,7 +444,7 @@ template <int NRB, int NCB>
 size_t strict_smem_bytes(int NP) {
     constexpr int C = 8 * NCB;
     const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
-    size_t doubles = nfrag + (size_t)NP * 3 + (size_t)C * column_pitch(NP) + C * 3 + kRowGroups * C + 2 * C;
+    size_t doubles = nfrag + (size_t)NP * 3 + (size_t)C * column_pitch(NP) + C * 3 + 2 * kRowGroups * C + 2 * C;
     size_t bytes = doubles * sizeof(double);
     bytes += 5 * C * sizeof(void*);   // sLo sHi sHist sZplan sFlag
     bytes += sizeof(unsigned long long);

@@ -189,8 +189,12 @@ static int admm_solve(const oracle_plan *p, const double *x, const double *lo, c
             res = fmax(res, fmax(fabs(v - zn), rho * fabs(zn - zo)));
             tv[i] = tn;
         }
-        for (int i = 0; i < N; ++i) rhs[i] = rho * (2.0 * clip(tv[i], lo[i], hi[i]) - tv[i]) - q[i];
-        if (res <= p->eps) { *converged = 1; break; }
+        double mag = 0.0;                              /* stop test is relative to the rhs magnitude */
+        for (int i = 0; i < N; ++i) {
+            rhs[i] = rho * (2.0 * clip(tv[i], lo[i], hi[i]) - tv[i]) - q[i];
+            mag = fmax(mag, fabs(rhs[i]));
+        }
+        if (res <= p->eps * fmax(1.0, mag)) { *converged = 1; break; }
     }
     return it;
 }
