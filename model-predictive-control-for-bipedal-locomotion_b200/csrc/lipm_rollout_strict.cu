@@ -17,18 +17,25 @@
 // epilogue does the relaxation, the box projection, the dual update, the residuals and the next
 // right-hand side.
 //
-// Residency (one persistent CTA per SM, C = 8*NCB columns per tile, a tile = all ticks of C walks):
-//   shared memory : M in A-fragment order (N=150: 184,832 B, loaded once by bulk async copy),
-//                   the right-hand sides R[column][k] (B operand), G Px, per-column bookkeeping;
-//   registers     : t, lo, hi, q of the thread's accumulator elements (C-fragment layout), so
-//                   the epilogue touches shared memory only to publish the new right-hand side;
-//   HBM           : bounds are read once per tick, the 3-vector state and a flag byte are written
-//                   once per tick.  Nothing else leaves the SM during a walk.
-// Warp (rg, cb) owns row blocks rg*NRB .. rg*NRB+NRB-1 and column block cb.
+// Organisation (one persistent CTA per SM):
+//   * The CTA holds M once, in shared memory, in A-fragment order (N=150: 184,832 B, fetched by
+//     bulk async copies).  It is the only large operand and it never moves again.
+//   * The CTA is split into NG independent SOLVER GROUPS of 4 warps.  A group owns 8 columns
+//     (one DMMA column block) for ALL their ticks: it pulls an 8-column unit from a global
+//     counter, walks it to the end, pulls the next.  Groups only share M; they synchronise
+//     among their own 128 threads with named barriers, so one group's epilogue / bound loads /
+//     state update overlap the other groups' contractions and the FP64 tensor pipe stays fed.
+//     Work is scheduled at 8-column granularity (y-axis units, which iterate longer, first).
+//   * Inside a group, warp rg owns row blocks rg*NRB .. rg*NRB+NRB-1 of M (row groups are rotated
+//     by the group index so the short last row group lands on a different scheduler per group).
+//   * registers : t, lo, hi, q of the thread's accumulator elements (C-fragment layout): the
+//     epilogue touches shared memory only to publish the next right-hand side R[column][k];
+//   * HBM       : bounds are read once per tick, the 3-vector state and a flag byte are written
+//     once per tick.  Nothing else leaves the SM during a walk.
 //
 // Determinism: a column stops updating the moment ITS residual test passes (columns are frozen
-// individually; the tile keeps iterating for the others), and every accumulation has a fixed
-// order, so a scenario's result is bit-identical whatever batch, tile or GPU it lands in.
+// individually; the group keeps iterating for the others), and every accumulation has a fixed
+// order, so a scenario's result is bit-identical whatever batch, unit or GPU it lands in.
 #include "lipm_internal.cuh"
 
 namespace lipm {
@@ -48,7 +55,7 @@ struct StrictParams {
     const double* mfrag;
     const double* gpx;
     unsigned int* tile_counter;
-    unsigned int num_tiles;
+    unsigned int num_units;   // 8-column work units
     size_t nfrag;           // doubles in mfrag
 };
 
@@ -96,40 +103,123 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "memory");
 }
 
-template <int NRB, int NCB>
-__global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(const StrictParams P) {
-    constexpr int C = 8 * NCB;
+constexpr int kGroupThreads = 32 * kRowGroups;   // 128: one warp per row group
+constexpr int kGroupCols = 8;                    // one DMMA column block
+
+// Named barriers: id 0 is __syncthreads; group g uses id 1 + g.
+__device__ __forceinline__ void group_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroupThreads) : "memory");
+}
+__device__ __forceinline__ bool group_sync_and(int id, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %2, 0;\n"
+        "bar.red.and.pred q, %1, %3, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(out)
+        : "r"(id), "r"((uint32_t)pred), "n"(kGroupThreads)
+        : "memory");
+    return out != 0;
+}
+
+// acc[r] += M[row block r of this warp] * R[:, this group's 8 columns]   (NR row blocks, all k)
+template <int NR, int NRB>
+__device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* __restrict__ aBase,
+                                         int aStride, const double* __restrict__ bBase, int KB) {
+#pragma unroll 2
+    for (int kb = 0; kb < KB; ++kb) {
+        const double bfrag = bBase[kb * 4];
+        double afrag[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) afrag[r] = aBase[r * aStride + kb * 32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], afrag[r], bfrag);
+    }
+}
+template <int NR, int NRB>
+struct ContractDispatch {
+    static __device__ __forceinline__ void run(int nrb, double (&acc)[NRB][2], const double* aBase, int aStride,
+                                               const double* bBase, int KB) {
+        if (nrb == NR) contract<NR, NRB>(acc, aBase, aStride, bBase, KB);
+        else ContractDispatch<NR - 1, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
+    }
+};
+template <int NRB>
+struct ContractDispatch<0, NRB> {
+    static __device__ __forceinline__ void run(int, double (&)[NRB][2], const double*, int, const double*, int) {}
+};
+
+// Per-group shared-memory block (the big operand M and G Px are CTA-wide and come first).
+struct GroupSmem {
+    double* R;        // [8][KP]  right-hand sides (B operand), also the warm-start staging buffer
+    double* X;        // [8][3]   current axis state
+    double* Res;      // [2][4][8] residual and rhs-magnitude partials per row group
+    double* Imp;      // [8]
+    double* Viol;     // [8]
+    const double** Lo;
+    const double** Hi;
+    double** Hist;
+    double** Zplan;
+    uint8_t** Flag;
+    int* Nser;
+    int* Nticks;
+    int* Ftick;
+    int* Iter;
+    int* NotConv;
+    int* Unit;        // [0] unit index, [1] ticks of the longest column
+};
+
+__host__ __device__ inline size_t group_smem_bytes(int KP) {
+    return sizeof(double) * ((size_t)kGroupCols * KP + kGroupCols * 3 + 2 * kRowGroups * kGroupCols + 2 * kGroupCols) +
+           sizeof(void*) * 5 * kGroupCols + sizeof(int) * (5 * kGroupCols + 2);
+}
+
+__device__ __forceinline__ GroupSmem carve_group(unsigned char* base, int KP) {
+    GroupSmem s;
+    s.R = reinterpret_cast<double*>(base);
+    s.X = s.R + kGroupCols * KP;
+    s.Res = s.X + kGroupCols * 3;
+    s.Imp = s.Res + 2 * kRowGroups * kGroupCols;
+    s.Viol = s.Imp + kGroupCols;
+    s.Lo = reinterpret_cast<const double**>(s.Viol + kGroupCols);
+    s.Hi = s.Lo + kGroupCols;
+    s.Hist = reinterpret_cast<double**>(const_cast<double**>(s.Hi + kGroupCols));
+    s.Zplan = s.Hist + kGroupCols;
+    s.Flag = reinterpret_cast<uint8_t**>(s.Zplan + kGroupCols);
+    s.Nser = reinterpret_cast<int*>(s.Flag + kGroupCols);
+    s.Nticks = s.Nser + kGroupCols;
+    s.Ftick = s.Nticks + kGroupCols;
+    s.Iter = s.Ftick + kGroupCols;
+    s.NotConv = s.Iter + kGroupCols;
+    s.Unit = s.NotConv + kGroupCols;
+    return s;
+}
+
+template <int NRB, int NG>
+__global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const StrictParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    // ---- shared memory carve-up -------------------------------------------------------------
+    // ---- shared memory: [ M fragments | G Px | mbarrier | group 0 | group 1 | ... ] --------------
     double* sM = reinterpret_cast<double*>(smem_raw);
     double* sGPx = sM + P.nfrag;
-    double* sR = sGPx + P.NP * 3;
-    double* sX = sR + C * P.KP;
-    double* sRes = sX + C * 3;
-    double* sImp = sRes + 2 * kRowGroups * C;   // sRes: [rg][C] residuals, then [rg][C] rhs magnitudes
-    double* sViol = sImp + C;
-    const double** sLo = reinterpret_cast<const double**>(sViol + C);
-    const double** sHi = sLo + C;
-    double** sHist = reinterpret_cast<double**>(const_cast<double**>(sHi + C));
-    double** sZplan = sHist + C;
-    uint8_t** sFlag = reinterpret_cast<uint8_t**>(sZplan + C);
-    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sFlag + C);
-    int* sNser = reinterpret_cast<int*>(sBar + 1);
-    int* sNticks = sNser + C;
-    int* sFtick = sNticks + C;
-    int* sIter = sFtick + C;
-    int* sNotConv = sIter + C;
-    int* sTile = sNotConv + C;   // [0] tile index, [1] ticks of the longest column
+    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sGPx + P.NP * 3);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const int grp = warp >> 2;                    // solver group
+    const int gtid = tid & (kGroupThreads - 1);   // thread index inside the group
+    const int rg = (warp + grp) & 3;              // row group (rotated per group)
     const int g = lane >> 2, t = lane & 3;
-    const int rg = warp / NCB, cb = warp % NCB;
     const int N = P.N, KB = P.KB, KP = P.KP;
     const ColumnBatch& B = P.cb;
+    const int bar_id = 1 + grp;
+    const size_t gbytes = (group_smem_bytes(KP) + 15) & ~(size_t)15;
+    const GroupSmem S = carve_group(reinterpret_cast<unsigned char*>(sBar + 2) + grp * gbytes, KP);
 
-    // ---- stationary operands: iteration matrix and G Px, one bulk copy per CTA ----------------
+    // ---- stationary operands: iteration matrix and G Px, bulk copies issued by one thread -------
     if (tid == 0) mbar_init(sBar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -145,43 +235,37 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
         bulk_load(sGPx, P.gpx, g_bytes, sBar);
     }
     mbar_wait(sBar, 0);
+    // From here on the groups never meet again: only group barriers below.
 
     // ---- this thread's accumulator elements ----------------------------------------------------
-    // element (r, e): row j = (rg*NRB + r)*8 + g, local column lc[e] = cb*8 + 2t + e
+    // element (r, e): row j = (rg*NRB + r)*8 + g, local column lc0 + e = 2t + e
     int nrb = P.RBLK - rg * NRB;
     nrb = nrb < 0 ? 0 : (nrb > NRB ? NRB : nrb);
     const int row0 = rg * NRB * 8 + g;
-    const int lc0 = cb * 8 + 2 * t;
-    // A fragments of row block r; row blocks past the end of the matrix alias the last real one
-    // (their products are computed and discarded) so that the contraction loop has no branches.
-    const double* aTile[NRB];
-#pragma unroll
-    for (int r = 0; r < NRB; ++r) {
-        int I = rg * NRB + r;
-        I = I < P.RBLK ? I : P.RBLK - 1;
-        aTile[r] = sM + (size_t)I * KB * 32 + lane;
-    }
-    const double* bBase = sR + (cb * 8 + g) * KP + t;
-    double* rOut0 = sR + lc0 * KP + row0;          // element (r, e) lives at rOut0[e*KP + r*8]
+    const int lc0 = 2 * t;
+    const int aStride = KB * 32;
+    const double* aBase = sM + (size_t)(rg * NRB) * aStride + lane;
+    const double* bBase = S.R + g * KP + t;
+    double* rOut0 = S.R + lc0 * KP + row0;         // element (r, e) lives at rOut0[e*KP + r*8]
     const bool is_head = (rg == 0) && (g == 0);    // holds preview row 0 of columns lc0, lc0+1
 
     // ADMM state of this thread's elements: tv = relaxed iterate + dual (z = clip(tv), w = tv - z)
     double tv[NRB][2], lo[NRB][2], hi[NRB][2], q[NRB][2];
 
     for (;;) {
-        // ---- fetch a tile (y-axis columns, which iterate longer, are handed out first) -------
-        __syncthreads();
-        if (tid == 0) {
-            sTile[0] = (int)atomicAdd(P.tile_counter, 1u);
-            sTile[1] = 0;
+        // ---- fetch an 8-column unit (y-axis units, which iterate longer, are handed out first) --
+        group_sync(bar_id);
+        if (gtid == 0) {
+            S.Unit[0] = (int)atomicAdd(P.tile_counter, 1u);
+            S.Unit[1] = 0;
         }
-        __syncthreads();
-        const unsigned int tile = (unsigned int)sTile[0];
-        if (tile >= P.num_tiles) break;
-        const int col0 = (int)(P.num_tiles - 1u - tile) * C;
+        group_sync(bar_id);
+        const unsigned int unit = (unsigned int)S.Unit[0];
+        if (unit >= P.num_units) break;
+        const int col0 = (int)(P.num_units - 1u - unit) * kGroupCols;
 
-        if (tid < C) {
-            const int c = col0 + tid;
+        if (gtid < kGroupCols) {
+            const int c = col0 + gtid;
             const bool valid = c < B.ncols;
             const int axis = valid ? c / B.B : 0;
             const int b = valid ? c - axis * B.B : 0;
@@ -192,11 +276,12 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
             const long long bz = (B.bounds_batch == 1) ? 0 : b;
             const double* plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
             const double* phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
-            double* ph = B.hist[axis] ? B.hist[axis] + (long long)b * B.hist_scn_stride : nullptr;
+            double* ph = axis ? B.hist[1] : B.hist[0];
+            if (ph) ph += (long long)b * B.hist_scn_stride;
             uint8_t* pf = B.flags ? B.flags + ((long long)b * B.n_max) * 2 + axis : nullptr;
             double x0 = 0.0, x1 = 0.0, x2 = 0.0;
             if (valid) {
-                const double* s = B.init[axis] + (long long)b * 3;
+                const double* s = (axis ? B.init[1] : B.init[0]) + (long long)b * 3;
                 x0 = s[0]; x1 = s[1]; x2 = s[2];
             }
             double viol = 0.0;
@@ -209,29 +294,29 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                                           (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
             }
             const bool push = valid && axis == 1 && B.impulse != nullptr;
-            sLo[tid] = plo; sHi[tid] = phi; sHist[tid] = ph; sFlag[tid] = pf;
-            sZplan[tid] = (valid && B.zmp_plan) ? B.zmp_plan + (long long)c * N : nullptr;
-            sNser[tid] = n; sNticks[tid] = ticks;
-            sImp[tid] = push ? B.impulse[b] : 0.0;
-            sFtick[tid] = push ? (B.force_tick ? B.force_tick[b] : -1) : -1;
-            sX[tid * 3 + 0] = x0; sX[tid * 3 + 1] = x1; sX[tid * 3 + 2] = x2;
-            sViol[tid] = viol; sIter[tid] = 0; sNotConv[tid] = 0;
-            atomicMax(&sTile[1], ticks);
+            S.Lo[gtid] = plo; S.Hi[gtid] = phi; S.Hist[gtid] = ph; S.Flag[gtid] = pf;
+            S.Zplan[gtid] = (valid && B.zmp_plan) ? B.zmp_plan + (long long)c * N : nullptr;
+            S.Nser[gtid] = n; S.Nticks[gtid] = ticks;
+            S.Imp[gtid] = push ? B.impulse[b] : 0.0;
+            S.Ftick[gtid] = push ? (B.force_tick ? B.force_tick[b] : -1) : -1;
+            S.X[gtid * 3 + 0] = x0; S.X[gtid * 3 + 1] = x1; S.X[gtid * 3 + 2] = x2;
+            S.Viol[gtid] = viol; S.Iter[gtid] = 0; S.NotConv[gtid] = 0;
+            atomicMax(&S.Unit[1], ticks);
         }
-        __syncthreads();
-        const int max_ticks = sTile[1];
+        group_sync(bar_id);
+        const int max_ticks = S.Unit[1];
 
         for (int i = 0; i < max_ticks; ++i) {
             bool live[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) live[e] = i < sNticks[lc0 + e];
+            for (int e = 0; e < 2; ++e) live[e] = i < S.Nticks[lc0 + e];
 
             // ---- bound window of this tick: row j reads sample min(i + bias + j, n - 1) ------
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const double* plo = sLo[lc0 + e];
-                const double* phi = sHi[lc0 + e];
-                const int last = sNser[lc0 + e] - 1;
+                const double* plo = S.Lo[lc0 + e];
+                const double* phi = S.Hi[lc0 + e];
+                const int last = S.Nser[lc0 + e] - 1;
 #pragma unroll
                 for (int r = 0; r < NRB; ++r) {
                     const int j = row0 + r * 8;
@@ -260,26 +345,26 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
 #pragma unroll
                         for (int e = 0; e < 2; ++e) rOut0[e * KP + r * 8] = tv[r][e];
                     }
-                __syncthreads();
+                group_sync(bar_id);
 #pragma unroll
                 for (int r = 0; r < NRB; ++r) {
                     const int j = row0 + r * 8;
                     if (r < nrb && j < N) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const double shifted = sR[(lc0 + e) * KP + (j + 1 < N ? j + 1 : N - 1)];
+                            const double shifted = S.R[(lc0 + e) * KP + (j + 1 < N ? j + 1 : N - 1)];
                             // last row: keep the primal value, drop the dual
                             tv[r][e] = (j + 1 < N) ? shifted : fmin(fmax(shifted, lo[r][e]), hi[r][e]);
                         }
                     }
                 }
-                __syncthreads();
+                group_sync(bar_id);
             }
 
             // ---- linear term and first right-hand side ----------------------------------------
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const double x0 = sX[(lc0 + e) * 3 + 0], x1 = sX[(lc0 + e) * 3 + 1], x2 = sX[(lc0 + e) * 3 + 2];
+                const double x0 = S.X[(lc0 + e) * 3 + 0], x1 = S.X[(lc0 + e) * 3 + 1], x2 = S.X[(lc0 + e) * 3 + 2];
 #pragma unroll
                 for (int r = 0; r < NRB; ++r) {
                     const int j = row0 + r * 8;
@@ -296,7 +381,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                     if (r < nrb) rOut0[e * KP + r * 8] = fma(P.rho, 2.0 * zc - tv[r][e], -qv);
                 }
             }
-            __syncthreads();
+            group_sync(bar_id);
 
             // ---- ADMM ---------------------------------------------------------------------------
             bool done[2] = {!live[0], !live[1]};
@@ -306,17 +391,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
 #pragma unroll
                 for (int r = 0; r < NRB; ++r) acc[r][0] = acc[r][1] = 0.0;
 
-                if (__any_sync(0xffffffffu, !done[0] || !done[1])) {
-#pragma unroll 2
-                    for (int kb = 0; kb < KB; ++kb) {
-                        const double bfrag = bBase[kb * 4];
-                        double afrag[NRB];
-#pragma unroll
-                        for (int r = 0; r < NRB; ++r) afrag[r] = aTile[r][kb * 32];
-#pragma unroll
-                        for (int r = 0; r < NRB; ++r) dmma884(acc[r][0], acc[r][1], afrag[r], bfrag);
-                    }
-                }
+                ContractDispatch<NRB, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
 
                 // residuals and the magnitude of the new right-hand side (stop test is relative to it)
                 double res[2] = {0.0, 0.0}, mag[2] = {0.0, 0.0};
@@ -325,7 +400,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                     if (!done[e]) {
 #pragma unroll
                         for (int r = 0; r < NRB; ++r) {
-                            if (r >= nrb) continue;   // aliased row block: product discarded
+                            if (r >= nrb) continue;
                             const double v = acc[r][e];
                             const double zo = fmin(fmax(tv[r][e], lo[r][e]), hi[r][e]);
                             const double wo = tv[r][e] - zo;
@@ -350,11 +425,11 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                 if (g == 0) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        sRes[rg * C + lc0 + e] = res[e];
-                        sRes[(kRowGroups + rg) * C + lc0 + e] = mag[e];
+                        S.Res[rg * kGroupCols + lc0 + e] = res[e];
+                        S.Res[(kRowGroups + rg) * kGroupCols + lc0 + e] = mag[e];
                     }
                 }
-                __syncthreads();   // every warp has consumed R; residual partials are visible
+                group_sync(bar_id);   // every warp of the group has consumed R; partials are visible
 
                 bool all_mine = true;
 #pragma unroll
@@ -363,18 +438,18 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
 #pragma unroll
                         for (int r = 0; r < NRB; ++r)
                             if (r < nrb) rOut0[e * KP + r * 8] = acc[r][e];
-                        double cr = sRes[lc0 + e], cm = sRes[kRowGroups * C + lc0 + e];
+                        double cr = S.Res[lc0 + e], cm = S.Res[kRowGroups * kGroupCols + lc0 + e];
 #pragma unroll
                         for (int q4 = 1; q4 < kRowGroups; ++q4) {
-                            cr = fmax(cr, sRes[q4 * C + lc0 + e]);
-                            cm = fmax(cm, sRes[(kRowGroups + q4) * C + lc0 + e]);
+                            cr = fmax(cr, S.Res[q4 * kGroupCols + lc0 + e]);
+                            cm = fmax(cm, S.Res[(kRowGroups + q4) * kGroupCols + lc0 + e]);
                         }
                         ++iters[e];
                         done[e] = (cr <= P.eps * fmax(1.0, cm));
                     }
                     all_mine = all_mine && done[e];
                 }
-                if (__syncthreads_and(all_mine)) break;   // new R visible; partials consumed
+                if (group_sync_and(bar_id, all_mine)) break;   // new R visible; partials consumed
             }
 
             // ---- apply the first sample: state update, push, outputs --------------------------
@@ -383,7 +458,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                 for (int e = 0; e < 2; ++e) {
                     const int lc = lc0 + e;
                     if (!live[e]) continue;
-                    const double x0 = sX[lc * 3 + 0], x1 = sX[lc * 3 + 1], x2 = sX[lc * 3 + 2];
+                    const double x0 = S.X[lc * 3 + 0], x1 = S.X[lc * 3 + 1], x2 = S.X[lc * 3 + 2];
                     const double l0 = lo[0][e], h0 = hi[0][e];
                     const double z0 = fmin(fmax(tv[0][e], l0), h0);
                     const double pred = fma(P.px02, x2, fma(P.T, x1, x0));
@@ -393,29 +468,29 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                     double n2 = fma(P.T, jerk, x2);
                     const double zmp = n0 - P.hg * n2;
                     const double below = l0 - zmp, above = zmp - h0;
-                    sViol[lc] = fmax(sViol[lc], fmax(fmax(below, above), 0.0));
+                    S.Viol[lc] = fmax(S.Viol[lc], fmax(fmax(below, above), 0.0));
                     unsigned f = (below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                  (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u);
                     if (P.strict_flags)
                         f |= (z0 == l0 ? LIPM_FLAG_ACTIVE_LO : 0u) | (z0 == h0 ? LIPM_FLAG_ACTIVE_HI : 0u);
-                    if (!done[e]) { f |= LIPM_FLAG_NOT_CONVERGED; sNotConv[lc] += 1; }
-                    if (i == sFtick[lc]) n1 -= sImp[lc];
+                    if (!done[e]) { f |= LIPM_FLAG_NOT_CONVERGED; S.NotConv[lc] += 1; }
+                    if (i == S.Ftick[lc]) n1 -= S.Imp[lc];
                     const long long sample = i + 1;
-                    double* ph = sHist[lc];
+                    double* ph = S.Hist[lc];
                     if (ph) {
                         double* dst = ph + (sample - B.hist_index_bias) * 3;
                         dst[0] = n0; dst[1] = n1; dst[2] = n2;
                     }
-                    if (sFlag[lc]) sFlag[lc][sample * 2] = (uint8_t)f;
-                    sX[lc * 3 + 0] = n0; sX[lc * 3 + 1] = n1; sX[lc * 3 + 2] = n2;
-                    sIter[lc] += iters[e];
+                    if (S.Flag[lc]) S.Flag[lc][sample * 2] = (uint8_t)f;
+                    S.X[lc * 3 + 0] = n0; S.X[lc * 3 + 1] = n1; S.X[lc * 3 + 2] = n2;
+                    S.Iter[lc] += iters[e];
                 }
             }
             if (B.zmp_plan) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    double* pz = sZplan[lc0 + e];
-                    if (pz && i == sNticks[lc0 + e] - 1) {
+                    double* pz = S.Zplan[lc0 + e];
+                    if (pz && i == S.Nticks[lc0 + e] - 1) {
 #pragma unroll
                         for (int r = 0; r < NRB; ++r) {
                             const int j = row0 + r * 8;
@@ -424,48 +499,41 @@ __global__ void __launch_bounds__(32 * kRowGroups * NCB, 1) k_strict_rollout(con
                     }
                 }
             }
-            __syncthreads();
+            group_sync(bar_id);
         }
 
         // ---- per-column summaries -----------------------------------------------------------------
-        if (tid < C) {
-            const int c = col0 + tid;
+        if (gtid < kGroupCols) {
+            const int c = col0 + gtid;
             if (c < B.ncols) {
                 const int axis = c / B.B, b = c - axis * B.B;
-                if (B.max_violation) B.max_violation[b * 2 + axis] = sViol[tid];
-                if (B.status) B.status[b * 2 + axis] = sNotConv[tid];
-                if (B.iters) B.iters[b * 2 + axis] = sIter[tid];
+                if (B.max_violation) B.max_violation[b * 2 + axis] = S.Viol[gtid];
+                if (B.status) B.status[b * 2 + axis] = S.NotConv[gtid];
+                if (B.iters) B.iters[b * 2 + axis] = S.Iter[gtid];
             }
         }
     }
 }
 
-template <int NRB, int NCB>
+template <int NG>
 size_t strict_smem_bytes(int NP) {
-    constexpr int C = 8 * NCB;
     const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
-    size_t doubles = nfrag + (size_t)NP * 3 + (size_t)C * column_pitch(NP) + C * 3 + 2 * kRowGroups * C + 2 * C;
-    size_t bytes = doubles * sizeof(double);
-    bytes += 5 * C * sizeof(void*);   // sLo sHi sHist sZplan sFlag
-    bytes += sizeof(unsigned long long);
-    bytes += (5 * C + 2) * sizeof(int);
-    return bytes + 16;
+    const size_t gbytes = (group_smem_bytes(column_pitch(NP)) + 15) & ~(size_t)15;
+    return sizeof(double) * (nfrag + (size_t)NP * 3) + 2 * sizeof(unsigned long long) + NG * gbytes;
 }
 
-template <int NRB, int NCB>
+template <int NRB, int NG>
 int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) {
-    const size_t smem = strict_smem_bytes<NRB, NCB>(plan->NP);
-    auto kernel = k_strict_rollout<NRB, NCB>;
-    static bool configured = false;   // attribute is per function and per device context
-    (void)configured;
+    const size_t smem = strict_smem_bytes<NG>(plan->NP);
+    auto kernel = k_strict_rollout<NRB, NG>;
     LIPM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StrictParams Q = P;
-    constexpr int C = 8 * NCB;
-    Q.num_tiles = (unsigned)((P.cb.ncols + C - 1) / C);
-    if (Q.num_tiles == 0) return LIPM_OK;
-    const unsigned grid = Q.num_tiles < (unsigned)plan->sm_count ? Q.num_tiles : (unsigned)plan->sm_count;
+    Q.num_units = (unsigned)((P.cb.ncols + kGroupCols - 1) / kGroupCols);
+    if (Q.num_units == 0) return LIPM_OK;
+    const unsigned ctas = (Q.num_units + NG - 1) / NG;
+    const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
-    kernel<<<grid, 32 * kRowGroups * NCB, smem, stream>>>(Q);
+    kernel<<<grid, kGroupThreads * NG, smem, stream>>>(Q);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;
 }
@@ -492,14 +560,14 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
     P.pu00 = plan->pu00;
     P.mfrag = plan->d_mfrag; P.gpx = plan->d_gpx;
     P.tile_counter = plan->d_tile_counter;
-    P.num_tiles = 0;
+    P.num_units = 0;
     P.nfrag = (size_t)(plan->NP / 8) * (plan->NP / 4) * 32;
 
     const int nrb = (P.RBLK + kRowGroups - 1) / kRowGroups;
     switch (nrb) {
-        case 1: return launch_variant<1, 3>(plan, P, stream);
-        case 2: return launch_variant<2, 3>(plan, P, stream);
-        case 3: return launch_variant<3, 3>(plan, P, stream);
+        case 1: return launch_variant<1, 4>(plan, P, stream);
+        case 2: return launch_variant<2, 4>(plan, P, stream);
+        case 3: return launch_variant<3, 4>(plan, P, stream);
         case 4: return launch_variant<4, 3>(plan, P, stream);
         case 5: return launch_variant<5, 3>(plan, P, stream);
         default: break;
