@@ -231,6 +231,7 @@ def run_ours(args, rank, world, local_rank):
     value = world * solves_per_step * args.steps / total_s
 
     iters = out["iters"].sum().item() if mode == engine.MODE_STRICT else 0
+    stats = plan.stats() if mode == engine.MODE_STRICT else {"group_iterations": 0, "units": 0}
     status_bad = int((out["status"] != 0).sum().item())
     max_viol = out["max_violation"].max().item()
 
@@ -266,7 +267,8 @@ def run_ours(args, rank, world, local_rank):
                        "mode": args.mode, "solves_per_step_per_gpu": solves_per_step,
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "admm": {"rho": 2.0, "alpha": 1.6, "eps": 1e-12,
-                                "mean_iters_per_solve": iters / max(solves_per_step, 1)}},
+                                "mean_iters_per_solve": iters / max(solves_per_step, 1),
+                                "useful_column_slot_fraction": iters / max(8 * stats["group_iterations"], 1)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "api": "ZMPController.generate_com_trajectory_batched (NumPy in, NumPy out)"},
             "gpu_launches": args.steps,

@@ -63,7 +63,7 @@ typedef struct lipm_plan_desc {
     double Q, R;       /* tracking / jerk weights (zmp_controller.py:186, :174)             */
     double rho;        /* ADMM penalty          (<=0 -> default 2.0)                        */
     double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.6)                        */
-    double eps;        /* ADMM stop: max(primal, dual residual) <= eps * max(1, |rhs|_inf) (<=0 -> 1e-12) */
+    double eps;        /* ADMM stop: primal, rho*dual residual <= eps * max(1, |q|_inf) (<=0 -> 1e-12) */
     int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000)                           */
     double viol_tol;   /* box-violation tolerance for LIPM_FLAG_VIOL_* (<0 -> 1e-9)         */
     int32_t device;    /* CUDA device ordinal                                               */
@@ -125,6 +125,14 @@ int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n
 int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, const double* z_min,
                     const double* z_max, int bounds_batch, double* next_state, double* zmp_plan,
                     double* jerk_plan, int32_t* status, int32_t* iters, void* stream);
+
+/*
+ * Work accounting of the last strict launch on this plan (blocking read-back):
+ *   host_out[0] = ADMM iterations executed by 8-column solver groups (each occupies 8 column
+ *                 slots of the tensor pipe, converged or not); host_out[1] = 8-column units walked.
+ * Useful-work fraction = sum(iters) / (8 * host_out[0]).
+ */
+int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out);
 
 /* Library / build information. */
 const char* lipm_last_error(void);

@@ -34,7 +34,7 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_gain, p->d_info, p->d_tile_counter};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_gain, p->d_info, p->d_tile_counter, p->d_stats};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }
@@ -133,6 +133,13 @@ int lipm_plan_export(const lipm_plan_t* plan, int which, double* host_out, size_
     if (capacity < count) { set_error("lipm_plan_export: need %zu doubles, got %zu", count, capacity); return LIPM_E_INVALID; }
     DeviceGuard guard(plan->desc.device);
     LIPM_CUDA_TRY(cudaMemcpy(host_out, src, count * sizeof(double), cudaMemcpyDeviceToHost));
+    return LIPM_OK;
+}
+
+int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out) {
+    if (!plan || !host_out) { set_error("lipm_plan_stats: null argument"); return LIPM_E_INVALID; }
+    DeviceGuard guard(plan->desc.device);
+    LIPM_CUDA_TRY(cudaMemcpy(host_out, plan->d_stats, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return LIPM_OK;
 }
 

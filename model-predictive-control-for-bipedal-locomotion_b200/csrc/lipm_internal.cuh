@@ -58,7 +58,8 @@ struct lipm_plan {
     double* d_mfrag;      // [(NP/8) x (NP/4) x 32] ADMM matrix in DMMA A-fragment order
     double* d_gain;       // [N+3] kz, kx
     int* d_info;          // [4] factorisation status words
-    unsigned int* d_tile_counter;  // dynamic tile scheduler of the strict kernel
+    unsigned int* d_tile_counter;  // dynamic work-unit scheduler of the strict kernel
+    unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch
 };
 
 namespace lipm {

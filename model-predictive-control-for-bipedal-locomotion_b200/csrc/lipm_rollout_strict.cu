@@ -55,6 +55,7 @@ struct StrictParams {
     const double* mfrag;
     const double* gpx;
     unsigned int* tile_counter;
+    unsigned long long* stats;   // [0] group iterations executed (8 column slots each), [1] units
     unsigned int num_units;   // 8-column work units
     size_t nfrag;           // doubles in mfrag
 };
@@ -125,18 +126,32 @@ __device__ __forceinline__ bool group_sync_and(int id, bool pred) {
     return out != 0;
 }
 
-// acc[r] += M[row block r of this warp] * R[:, this group's 8 columns]   (NR row blocks, all k)
+// Non-negative doubles order like their high words; 20 mantissa bits are plenty for a stop test,
+// and the maxima then run on the integer pipe instead of competing with DMMA for the FP64 pipe.
+__device__ __forceinline__ uint32_t mag_hi(double x) { return (uint32_t)__double2hiint(x) & 0x7fffffffu; }
+
+// acc[r] += M[row block r of this warp] * R[:, this group's 8 columns]   (NR row blocks, all k).
+// Fragments are double buffered: the loads of k-block kb+1 are in flight while kb is multiplied.
 template <int NR, int NRB>
 __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* __restrict__ aBase,
-                                         int aStride, const double* __restrict__ bBase, int KB) {
-#pragma unroll 2
-    for (int kb = 0; kb < KB; ++kb) {
-        const double bfrag = bBase[kb * 4];
-        double afrag[NR];
+                                         const int aStride, const double* __restrict__ bBase, const int KB) {
+    double a0[NR], a1[NR], b0, b1;
+    b0 = bBase[0];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) afrag[r] = aBase[r * aStride + kb * 32];
+    for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride];
+#pragma unroll 1
+    for (int kb = 0; kb < KB; kb += 2) {     // KB = NP/4 is even because NP is a multiple of 8
+        b1 = bBase[(kb + 1) * 4];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], afrag[r], bfrag);
+        for (int r = 0; r < NR; ++r) a1[r] = aBase[r * aStride + (kb + 1) * 32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a0[r], b0);
+        const int kn = (kb + 2 < KB) ? kb + 2 : kb;   // last trip reloads a valid block, unused
+        b0 = bBase[kn * 4];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride + kn * 32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a1[r], b1);
     }
 }
 template <int NR, int NRB>
@@ -152,60 +167,35 @@ struct ContractDispatch<0, NRB> {
     static __device__ __forceinline__ void run(int, double (&)[NRB][2], const double*, int, const double*, int) {}
 };
 
-// Per-group shared-memory block (the big operand M and G Px are CTA-wide and come first).
-struct GroupSmem {
-    double* R;        // [8][KP]  right-hand sides (B operand), also the warm-start staging buffer
-    double* X;        // [8][3]   current axis state
-    double* Res;      // [2][4][8] residual and rhs-magnitude partials per row group
-    double* Imp;      // [8]
-    double* Viol;     // [8]
-    const double** Lo;
-    const double** Hi;
-    double** Hist;
-    double** Zplan;
-    uint8_t** Flag;
-    int* Nser;
-    int* Nticks;
-    int* Ftick;
-    int* Iter;
-    int* NotConv;
-    int* Unit;        // [0] unit index, [1] ticks of the longest column
+// Shared memory of one solver group, fixed-size part (compile-time offsets from the group base).
+struct GroupFixed {
+    double X[kGroupCols * 3];                 // current axis state
+    double Imp[kGroupCols];                   // dt*F/m of the push
+    double Viol[kGroupCols];                  // running max box violation
+    const double* Lo[kGroupCols];             // bound series of each column
+    const double* Hi[kGroupCols];
+    double* Hist[kGroupCols];
+    double* Zplan[kGroupCols];
+    uint8_t* Flag[kGroupCols];
+    uint32_t Res[3][kRowGroups][kGroupCols];  // high words: primal, dual residual; |q| partials
+    int Nser[kGroupCols], Nticks[kGroupCols], Ftick[kGroupCols], Iter[kGroupCols], NotConv[kGroupCols];
+    int Unit[2];                              // [0] unit index, [1] ticks of the longest column
 };
 
-__host__ __device__ inline size_t group_smem_bytes(int KP) {
-    return sizeof(double) * ((size_t)kGroupCols * KP + kGroupCols * 3 + 2 * kRowGroups * kGroupCols + 2 * kGroupCols) +
-           sizeof(void*) * 5 * kGroupCols + sizeof(int) * (5 * kGroupCols + 2);
+// Layout: [ mbarrier | NG x GroupFixed | G Px | NG x R[8][KP] | M fragments ]
+__host__ __device__ inline size_t smem_fixed_bytes(int NG) {
+    return 16 + (size_t)NG * ((sizeof(GroupFixed) + 15) & ~(size_t)15);
 }
 
-__device__ __forceinline__ GroupSmem carve_group(unsigned char* base, int KP) {
-    GroupSmem s;
-    s.R = reinterpret_cast<double*>(base);
-    s.X = s.R + kGroupCols * KP;
-    s.Res = s.X + kGroupCols * 3;
-    s.Imp = s.Res + 2 * kRowGroups * kGroupCols;
-    s.Viol = s.Imp + kGroupCols;
-    s.Lo = reinterpret_cast<const double**>(s.Viol + kGroupCols);
-    s.Hi = s.Lo + kGroupCols;
-    s.Hist = reinterpret_cast<double**>(const_cast<double**>(s.Hi + kGroupCols));
-    s.Zplan = s.Hist + kGroupCols;
-    s.Flag = reinterpret_cast<uint8_t**>(s.Zplan + kGroupCols);
-    s.Nser = reinterpret_cast<int*>(s.Flag + kGroupCols);
-    s.Nticks = s.Nser + kGroupCols;
-    s.Ftick = s.Nticks + kGroupCols;
-    s.Iter = s.Ftick + kGroupCols;
-    s.NotConv = s.Iter + kGroupCols;
-    s.Unit = s.NotConv + kGroupCols;
-    return s;
-}
-
-template <int NRB, int NG>
+template <int NRB, int NG, int NPC>
 __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const StrictParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    // ---- shared memory: [ M fragments | G Px | mbarrier | group 0 | group 1 | ... ] --------------
-    double* sM = reinterpret_cast<double*>(smem_raw);
-    double* sGPx = sM + P.nfrag;
-    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sGPx + P.NP * 3);
+    // Geometry: compile-time for the specialised horizons (NPC > 0), run-time otherwise.
+    const int N = P.N;
+    const int NP = NPC > 0 ? NPC : P.NP;
+    const int KB = NP / 4, RBLK = NP / 8, KP = NP + 4;
+    const int aStride = KB * 32;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -213,18 +203,22 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
     const int gtid = tid & (kGroupThreads - 1);   // thread index inside the group
     const int rg = (warp + grp) & 3;              // row group (rotated per group)
     const int g = lane >> 2, t = lane & 3;
-    const int N = P.N, KB = P.KB, KP = P.KP;
     const ColumnBatch& B = P.cb;
     const int bar_id = 1 + grp;
-    const size_t gbytes = (group_smem_bytes(KP) + 15) & ~(size_t)15;
-    const GroupSmem S = carve_group(reinterpret_cast<unsigned char*>(sBar + 2) + grp * gbytes, KP);
+
+    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem_raw);
+    constexpr size_t kFixedStride = (sizeof(GroupFixed) + 15) & ~(size_t)15;
+    GroupFixed& S = *reinterpret_cast<GroupFixed*>(smem_raw + 16 + grp * kFixedStride);
+    double* sGPx = reinterpret_cast<double*>(smem_raw + 16 + NG * kFixedStride);
+    double* sR = sGPx + NP * 3 + grp * (kGroupCols * KP);     // this group's right-hand sides
+    double* sM = sGPx + NP * 3 + NG * (kGroupCols * KP);
 
     // ---- stationary operands: iteration matrix and G Px, bulk copies issued by one thread -------
     if (tid == 0) mbar_init(sBar, 1);
     __syncthreads();
     if (tid == 0) {
-        const uint32_t m_bytes = (uint32_t)(P.nfrag * sizeof(double));
-        const uint32_t g_bytes = (uint32_t)(P.NP * 3 * sizeof(double));
+        const uint32_t m_bytes = (uint32_t)((size_t)RBLK * KB * 32 * sizeof(double));
+        const uint32_t g_bytes = (uint32_t)(NP * 3 * sizeof(double));
         mbar_expect_tx(sBar, m_bytes + g_bytes);
         const uint32_t chunk = 32768;
         for (uint32_t off = 0; off < m_bytes; off += chunk) {
@@ -239,15 +233,15 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
     // ---- this thread's accumulator elements ----------------------------------------------------
     // element (r, e): row j = (rg*NRB + r)*8 + g, local column lc0 + e = 2t + e
-    int nrb = P.RBLK - rg * NRB;
+    int nrb = RBLK - rg * NRB;
     nrb = nrb < 0 ? 0 : (nrb > NRB ? NRB : nrb);
     const int row0 = rg * NRB * 8 + g;
     const int lc0 = 2 * t;
-    const int aStride = KB * 32;
     const double* aBase = sM + (size_t)(rg * NRB) * aStride + lane;
-    const double* bBase = S.R + g * KP + t;
-    double* rOut0 = S.R + lc0 * KP + row0;         // element (r, e) lives at rOut0[e*KP + r*8]
+    const double* bBase = sR + g * KP + t;
+    double* rOut0 = sR + lc0 * KP + row0;          // element (r, e) lives at rOut0[e*KP + r*8]
     const bool is_head = (rg == 0) && (g == 0);    // holds preview row 0 of columns lc0, lc0+1
+    const double two_rho = 2.0 * P.rho;
 
     // ADMM state of this thread's elements: tv = relaxed iterate + dual (z = clip(tv), w = tv - z)
     double tv[NRB][2], lo[NRB][2], hi[NRB][2], q[NRB][2];
@@ -305,6 +299,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
         }
         group_sync(bar_id);
         const int max_ticks = S.Unit[1];
+        unsigned int group_iters = 0;
 
         for (int i = 0; i < max_ticks; ++i) {
             bool live[2];
@@ -352,7 +347,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                     if (r < nrb && j < N) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const double shifted = S.R[(lc0 + e) * KP + (j + 1 < N ? j + 1 : N - 1)];
+                            const double shifted = sR[(lc0 + e) * KP + (j + 1 < N ? j + 1 : N - 1)];
                             // last row: keep the primal value, drop the dual
                             tv[r][e] = (j + 1 < N) ? shifted : fmin(fmax(shifted, lo[r][e]), hi[r][e]);
                         }
@@ -361,7 +356,8 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                 group_sync(bar_id);
             }
 
-            // ---- linear term and first right-hand side ----------------------------------------
+            // ---- linear term, its magnitude (scale of the stop test) and first right-hand side ----
+            uint32_t qmag[2] = {0u, 0u};
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const double x0 = S.X[(lc0 + e) * 3 + 0], x1 = S.X[(lc0 + e) * 3 + 1], x2 = S.X[(lc0 + e) * 3 + 2];
@@ -376,12 +372,30 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                         tv[r][e] = 0.0;
                     }
                     q[r][e] = qv;
+                    qmag[e] = max(qmag[e], mag_hi(qv));
                     // rho (z - w) - q with z = clip(t), w = t - z  ->  rho (2z - t) - q
                     const double zc = fmin(fmax(tv[r][e], lo[r][e]), hi[r][e]);
                     if (r < nrb) rOut0[e * KP + r * 8] = fma(P.rho, 2.0 * zc - tv[r][e], -qv);
                 }
             }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) qmag[e] = max(qmag[e], __shfl_xor_sync(0xffffffffu, qmag[e], o));
+                if (g == 0) S.Res[2][rg][lc0 + e] = qmag[e];
+            }
             group_sync(bar_id);
+            // stop thresholds of my two columns: eps * max(1, |q|_inf), as high words
+            uint32_t thr_p[2], thr_d[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                uint32_t m = S.Res[2][0][lc0 + e];
+#pragma unroll
+                for (int q4 = 1; q4 < kRowGroups; ++q4) m = max(m, S.Res[2][q4][lc0 + e]);
+                const double scale = fmax(1.0, __hiloint2double((int)m, 0));
+                thr_p[e] = mag_hi(P.eps * scale);
+                thr_d[e] = mag_hi(P.eps * scale / P.rho);
+            }
 
             // ---- ADMM ---------------------------------------------------------------------------
             bool done[2] = {!live[0], !live[1]};
@@ -393,8 +407,8 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
                 ContractDispatch<NRB, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
 
-                // residuals and the magnitude of the new right-hand side (stop test is relative to it)
-                double res[2] = {0.0, 0.0}, mag[2] = {0.0, 0.0};
+                // relaxation, projection, dual update, residuals, next right-hand side
+                uint32_t rp[2] = {0u, 0u}, rd[2] = {0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     if (!done[e]) {
@@ -403,14 +417,13 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                             if (r >= nrb) continue;
                             const double v = acc[r][e];
                             const double zo = fmin(fmax(tv[r][e], lo[r][e]), hi[r][e]);
-                            const double wo = tv[r][e] - zo;
-                            const double tn = fma(P.alpha, v, fma(1.0 - P.alpha, zo, wo));
+                            // alpha v + (1 - alpha) zo + (t - zo)  =  t + alpha (v - zo)
+                            const double tn = fma(P.alpha, v - zo, tv[r][e]);
                             const double zn = fmin(fmax(tn, lo[r][e]), hi[r][e]);
-                            res[e] = fmax(res[e], fmax(fabs(v - zn), P.rho * fabs(zn - zo)));
+                            rp[e] = max(rp[e], mag_hi(v - zn));
+                            rd[e] = max(rd[e], mag_hi(zn - zo));
                             tv[r][e] = tn;
-                            const double rn = fma(P.rho, 2.0 * zn - tn, -q[r][e]);
-                            mag[e] = fmax(mag[e], fabs(rn));
-                            acc[r][e] = rn;
+                            acc[r][e] = fma(two_rho, zn, fma(-P.rho, tn, -q[r][e]));
                         }
                     }
                 }
@@ -418,15 +431,15 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                 for (int e = 0; e < 2; ++e) {
 #pragma unroll
                     for (int o = 4; o <= 16; o <<= 1) {
-                        res[e] = fmax(res[e], __shfl_xor_sync(0xffffffffu, res[e], o));
-                        mag[e] = fmax(mag[e], __shfl_xor_sync(0xffffffffu, mag[e], o));
+                        rp[e] = max(rp[e], __shfl_xor_sync(0xffffffffu, rp[e], o));
+                        rd[e] = max(rd[e], __shfl_xor_sync(0xffffffffu, rd[e], o));
                     }
                 }
                 if (g == 0) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        S.Res[rg * kGroupCols + lc0 + e] = res[e];
-                        S.Res[(kRowGroups + rg) * kGroupCols + lc0 + e] = mag[e];
+                        S.Res[0][rg][lc0 + e] = rp[e];
+                        S.Res[1][rg][lc0 + e] = rd[e];
                     }
                 }
                 group_sync(bar_id);   // every warp of the group has consumed R; partials are visible
@@ -438,17 +451,18 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                         for (int r = 0; r < NRB; ++r)
                             if (r < nrb) rOut0[e * KP + r * 8] = acc[r][e];
-                        double cr = S.Res[lc0 + e], cm = S.Res[kRowGroups * kGroupCols + lc0 + e];
+                        uint32_t cp = S.Res[0][0][lc0 + e], cd = S.Res[1][0][lc0 + e];
 #pragma unroll
                         for (int q4 = 1; q4 < kRowGroups; ++q4) {
-                            cr = fmax(cr, S.Res[q4 * kGroupCols + lc0 + e]);
-                            cm = fmax(cm, S.Res[(kRowGroups + q4) * kGroupCols + lc0 + e]);
+                            cp = max(cp, S.Res[0][q4][lc0 + e]);
+                            cd = max(cd, S.Res[1][q4][lc0 + e]);
                         }
                         ++iters[e];
-                        done[e] = (cr <= P.eps * fmax(1.0, cm));
+                        done[e] = (cp <= thr_p[e]) && (cd <= thr_d[e]);
                     }
                     all_mine = all_mine && done[e];
                 }
+                ++group_iters;
                 if (group_sync_and(bar_id, all_mine)) break;   // new R visible; partials consumed
             }
 
@@ -503,6 +517,10 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
         }
 
         // ---- per-column summaries -----------------------------------------------------------------
+        if (gtid == 0) {
+            atomicAdd(P.stats, (unsigned long long)group_iters);
+            atomicAdd(P.stats + 1, 1ull);
+        }
         if (gtid < kGroupCols) {
             const int c = col0 + gtid;
             if (c < B.ncols) {
@@ -515,17 +533,16 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
     }
 }
 
-template <int NG>
-size_t strict_smem_bytes(int NP) {
+size_t strict_smem_bytes(int NG, int NP) {
     const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
-    const size_t gbytes = (group_smem_bytes(column_pitch(NP)) + 15) & ~(size_t)15;
-    return sizeof(double) * (nfrag + (size_t)NP * 3) + 2 * sizeof(unsigned long long) + NG * gbytes;
+    return smem_fixed_bytes(NG) +
+           sizeof(double) * ((size_t)NP * 3 + (size_t)NG * kGroupCols * column_pitch(NP) + nfrag);
 }
 
-template <int NRB, int NG>
+template <int NRB, int NG, int NPC>
 int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) {
-    const size_t smem = strict_smem_bytes<NG>(plan->NP);
-    auto kernel = k_strict_rollout<NRB, NG>;
+    const size_t smem = strict_smem_bytes(NG, plan->NP);
+    auto kernel = k_strict_rollout<NRB, NG, NPC>;
     LIPM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StrictParams Q = P;
     Q.num_units = (unsigned)((P.cb.ncols + kGroupCols - 1) / kGroupCols);
@@ -533,6 +550,7 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
     const unsigned ctas = (Q.num_units + NG - 1) / NG;
     const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
+    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 2 * sizeof(unsigned long long), stream));
     kernel<<<grid, kGroupThreads * NG, smem, stream>>>(Q);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;
@@ -560,16 +578,18 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
     P.pu00 = plan->pu00;
     P.mfrag = plan->d_mfrag; P.gpx = plan->d_gpx;
     P.tile_counter = plan->d_tile_counter;
+    P.stats = plan->d_stats;
     P.num_units = 0;
     P.nfrag = (size_t)(plan->NP / 8) * (plan->NP / 4) * 32;
 
     const int nrb = (P.RBLK + kRowGroups - 1) / kRowGroups;
+    if (plan->NP == 152) return launch_variant<5, 3, 152>(plan, P, stream);   // N = 145..152 (default 150)
     switch (nrb) {
-        case 1: return launch_variant<1, 4>(plan, P, stream);
-        case 2: return launch_variant<2, 4>(plan, P, stream);
-        case 3: return launch_variant<3, 4>(plan, P, stream);
-        case 4: return launch_variant<4, 3>(plan, P, stream);
-        case 5: return launch_variant<5, 3>(plan, P, stream);
+        case 1: return launch_variant<1, 4, 0>(plan, P, stream);
+        case 2: return launch_variant<2, 4, 0>(plan, P, stream);
+        case 3: return launch_variant<3, 4, 0>(plan, P, stream);
+        case 4: return launch_variant<4, 3, 0>(plan, P, stream);
+        case 5: return launch_variant<5, 3, 0>(plan, P, stream);
         default: break;
     }
     set_error("strict mode: no kernel variant for %d row blocks", P.RBLK);

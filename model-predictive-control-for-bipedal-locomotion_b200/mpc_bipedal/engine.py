@@ -32,7 +32,7 @@ LIBRARY_PATH = os.path.join(_PKG_ROOT, "_lib", "liblipm_mpc.so")
 
 EXPORTED_SYMBOLS = (
     "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout",
-    "lipm_solve_tick", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
+    "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
 )
 
 
@@ -81,6 +81,8 @@ def load_library() -> ctypes.CDLL:
     lib.lipm_rollout.restype = i32
     lib.lipm_solve_tick.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.lipm_solve_tick.restype = i32
+    lib.lipm_plan_stats.argtypes = [vp, vp]
+    lib.lipm_plan_stats.restype = i32
     lib.lipm_last_error.restype = ctypes.c_char_p
     lib.lipm_version.restype = ctypes.c_char_p
     lib.lipm_max_strict_horizon.restype = i32
@@ -164,6 +166,12 @@ class LipmPlan:
         out = np.empty(shape, dtype=np.float64)
         _check(self._lib.lipm_plan_export(self._handle, which, out.ctypes.data, out.size))
         return out
+
+    def stats(self) -> Dict[str, int]:
+        """Work accounting of the last strict launch (synchronises)."""
+        out = np.zeros(2, dtype=np.uint64)
+        _check(self._lib.lipm_plan_stats(self._handle, out.ctypes.data))
+        return {"group_iterations": int(out[0]), "units": int(out[1])}
 
     # ------------------------------------------------------------------ walks
     def rollout(self, mode: int, x0, y0, z_min, z_max, *, n_steps=None, impulse=None, force_tick=None,

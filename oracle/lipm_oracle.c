@@ -171,30 +171,29 @@ static int admm_solve(const oracle_plan *p, const double *x, const double *lo, c
         const double z = clip(tv[j], lo[j], hi[j]);
         rhs[j] = rho * (2.0 * z - tv[j]) - q[j];          /* rho (z - w) - q,  w = t - z */
     }
+    /* stop test: primal and rho*dual residual <= eps * max(1, |q|_inf)  (relative to the linear
+     * term: a diverging "fall" has a huge q and an absolute test would sit below FP64 rounding) */
+    double qmag = 0.0;
+    for (int j = 0; j < N; ++j) qmag = fmax(qmag, fabs(q[j]));
+    const double thr = p->eps * fmax(1.0, qmag);
     *converged = 0;
     int it = 0;
     while (it < p->max_iter) {
         ++it;
-        double res = 0.0;
-        /* v = M rhs ; the update of row i only needs v_i, but rhs must stay intact until all
-         * rows are done, so stage the new right-hand side in q-space scratch afterwards */
+        double rp = 0.0, rd = 0.0;
         for (int i = 0; i < N; ++i) {
             const double *Mi = p->M + (size_t)i * N;
             double v = 0.0;
             for (int j = 0; j < N; ++j) v += Mi[j] * rhs[j];
             const double zo = clip(tv[i], lo[i], hi[i]);
-            const double wo = tv[i] - zo;
-            const double tn = alpha * v + (1.0 - alpha) * zo + wo;
+            const double tn = tv[i] + alpha * (v - zo);   /* alpha v + (1-alpha) zo + (t - zo) */
             const double zn = clip(tn, lo[i], hi[i]);
-            res = fmax(res, fmax(fabs(v - zn), rho * fabs(zn - zo)));
+            rp = fmax(rp, fabs(v - zn));
+            rd = fmax(rd, fabs(zn - zo));
             tv[i] = tn;
         }
-        double mag = 0.0;                              /* stop test is relative to the rhs magnitude */
-        for (int i = 0; i < N; ++i) {
-            rhs[i] = rho * (2.0 * clip(tv[i], lo[i], hi[i]) - tv[i]) - q[i];
-            mag = fmax(mag, fabs(rhs[i]));
-        }
-        if (res <= p->eps * fmax(1.0, mag)) { *converged = 1; break; }
+        for (int i = 0; i < N; ++i) rhs[i] = rho * (2.0 * clip(tv[i], lo[i], hi[i]) - tv[i]) - q[i];
+        if (rp <= thr && rho * rd <= thr) { *converged = 1; break; }
     }
     return it;
 }

@@ -162,9 +162,9 @@ def strict_axis_admm(p: Problem, x: np.ndarray, zmax: np.ndarray, zmin: np.ndarr
         r_prim = np.max(np.abs(v - zn))
         r_dual = rho * np.max(np.abs(zn - z))
         z = zn
-        # stop test relative to the magnitude of the next right-hand side (diverging "falls" have
-        # a huge linear term; an absolute test would sit below their FP64 rounding floor)
-        if max(r_prim, r_dual) <= eps * max(1.0, np.max(np.abs(rho * (z - w) - q))):
+        # stop test relative to the magnitude of the linear term (diverging "falls" have a huge
+        # q; an absolute test would sit below their FP64 rounding floor)
+        if max(r_prim, r_dual) <= eps * max(1.0, np.max(np.abs(q))):
             break
     jerk0 = (z[0] - p.Px[0] @ x) / p.Pu[0, 0]
     return p.A @ x + p.B * jerk0, z, w, it

@@ -72,6 +72,17 @@ int main() {
         flops = 2.0 * 32 * 8.0 * iters * 8 * w * sms;
         printf(",\n {\"kind\": \"dfma\", \"warps_per_sm\": %d, \"chains\": 8, \"tflops\": %.3f}", w, flops / ms / 1e9);
     }
+    // dependent-issue latency: one warp per SM sub-partition with 1..10 independent chains, and
+    // 2 or 3 warps per sub-partition with 5 chains each (the strict kernel's situation)
+#define CHAIN_PROBE(CH, W)                                                                          \
+    {                                                                                               \
+        float ms = time_ms([&] { k_dmma<CH><<<sms, 32 * (W)>>>(out, iters, 1.0); });              \
+        double flops = 2.0 * 256 * (double)(CH) * iters * (W) * sms;                                \
+        printf(",\n {\"kind\": \"dmma884\", \"warps_per_sm\": %d, \"chains\": %d, \"tflops\": %.3f}", (W), (CH), \
+               flops / ms / 1e9);                                                                   \
+    }
+    CHAIN_PROBE(1, 4) CHAIN_PROBE(2, 4) CHAIN_PROBE(3, 4) CHAIN_PROBE(4, 4) CHAIN_PROBE(5, 4) CHAIN_PROBE(6, 4)
+    CHAIN_PROBE(10, 4) CHAIN_PROBE(5, 8) CHAIN_PROBE(5, 12) CHAIN_PROBE(10, 8)
     printf("\n]}\n");
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 1; }
