@@ -133,8 +133,10 @@ __device__ __forceinline__ uint32_t mag_hi(double x) { return (uint32_t)__double
 // acc[r] += M[row block r of this warp] * R[:, this group's 8 columns]   (NR row blocks, all k).
 // Fragments are double buffered: the loads of k-block kb+1 are in flight while kb is multiplied.
 template <int NR, int NRB>
-__device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* __restrict__ aBase,
-                                         const int aStride, const double* __restrict__ bBase, const int KB) {
+// (No __restrict__ on bBase: R is rewritten between calls and the loads must stay behind the
+// group barrier that publishes it.)
+__device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aBase,
+                                         const int aStride, const volatile double* bBase, const int KB) {
     double a0[NR], a1[NR], b0, b1;
     b0 = bBase[0];
 #pragma unroll
@@ -157,14 +159,14 @@ __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* __
 template <int NR, int NRB>
 struct ContractDispatch {
     static __device__ __forceinline__ void run(int nrb, double (&acc)[NRB][2], const double* aBase, int aStride,
-                                               const double* bBase, int KB) {
+                                               const volatile double* bBase, int KB) {
         if (nrb == NR) contract<NR, NRB>(acc, aBase, aStride, bBase, KB);
         else ContractDispatch<NR - 1, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
     }
 };
 template <int NRB>
 struct ContractDispatch<0, NRB> {
-    static __device__ __forceinline__ void run(int, double (&)[NRB][2], const double*, int, const double*, int) {}
+    static __device__ __forceinline__ void run(int, double (&)[NRB][2], const double*, int, const volatile double*, int) {}
 };
 
 // Shared memory of one solver group, fixed-size part (compile-time offsets from the group base).

@@ -290,3 +290,32 @@ def test_reference_python_surface_on_gpu(golden):
     x_state, y_state = ctrl.generate_state_trajectory_wieber(zero, zero.copy(), z_max, z_min)
     assert x_state.shape == (420, 3, 1)
     assert rel_err(x_state, gn["nopush_x_hist"]) < REL and rel_err(y_state, gn["nopush_y_hist"]) < REL
+
+
+@pytest.mark.parametrize("N", [24, 40, 100, 128])
+def test_strict_ticks_other_horizons_and_determinism(engine, N):
+    """Every kernel variant (row blocks per warp 1..5, partial last row group, padded rows):
+    result equals the oracle's ADMM and repeated launches are bit-identical (no races)."""
+    rng = np.random.default_rng(11 + N)
+    plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    p = orc.Problem.make(N)
+    cases = 40
+    x = rng.normal(size=(cases, 3)) * np.array([0.05, 0.1, 0.5])
+    centre = rng.uniform(-0.05, 0.05, size=(cases, 1)) + np.cumsum(
+        (rng.random((cases, N)) < 0.04) * rng.uniform(-0.1, 0.1, size=(cases, N)), axis=1)
+    lo, hi = centre - 0.055, centre + 0.055
+    first = plan.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    z = first["zmp_plan"].cpu().numpy()
+    assert (first["status"].cpu().numpy() == 0).all()
+    M = orc.admm_matrix(p, 2.0)
+    for k in range(0, cases, 3):
+        _, want, _, _ = orc.strict_axis_admm(p, x[k], hi[k], lo[k], eps=1e-13, M=M)
+        assert np.max(np.abs(z[k] - want)) < 1e-10, (N, k)
+    for _ in range(3):
+        again = plan.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+        assert np.array_equal(again["zmp_plan"].cpu().numpy(), z)
+        assert np.array_equal(again["iters"].cpu().numpy(), first["iters"].cpu().numpy())
+    # a permuted batch gives each problem the same bits
+    perm = rng.permutation(cases)
+    shuffled = plan.solve_tick(engine.MODE_STRICT, x[perm], lo[perm], hi[perm], want_plan=True)
+    assert np.array_equal(shuffled["zmp_plan"].cpu().numpy(), z[perm])
