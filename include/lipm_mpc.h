@@ -63,7 +63,7 @@ typedef struct lipm_plan_desc {
     double Q, R;       /* tracking / jerk weights (zmp_controller.py:186, :174)             */
     double rho;        /* ADMM penalty          (<=0 -> default 2.0)                        */
     double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.6)                        */
-    double eps;        /* ADMM stop: primal, rho*dual residual <= eps * max(1, |q|_inf) (<=0 -> 1e-12) */
+    double eps;        /* ADMM stop: primal and rho*dual residual <= eps * max(1, |q|_inf)  (<=0 -> 1e-12) */
     int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000)                           */
     double viol_tol;   /* box-violation tolerance for LIPM_FLAG_VIOL_* (<0 -> 1e-9)         */
     int32_t device;    /* CUDA device ordinal                                               */

@@ -48,6 +48,7 @@ struct StrictParams {
     int strict_flags;       // 1: report active-set bits
     int max_iter;
     double rho, alpha, eps, viol_tol;
+    double stop_factor;     // 1 / max(1 + alpha, rho * alpha)
     double Qhalf;           // Q / 2
     double T, c2, c3, hg;   // dt, dt^2/2, dt^3/6, h/g
     double px02;            // Px[0][2] = dt^2/2 - h/g
@@ -130,6 +131,12 @@ __device__ __forceinline__ bool group_sync_and(int id, bool pred) {
 // and the maxima then run on the integer pipe instead of competing with DMMA for the FP64 pipe.
 __device__ __forceinline__ uint32_t mag_hi(double x) { return (uint32_t)__double2hiint(x) & 0x7fffffffu; }
 
+// Box projection by plain compare-select (fmin/fmax would add NaN-quieting code to every call).
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {
+    const double r = x < lo ? lo : x;
+    return r > hi ? hi : r;
+}
+
 // acc[r] += M[row block r of this warp] * R[:, this group's 8 columns]   (NR row blocks, all k).
 // Fragments are double buffered: the loads of k-block kb+1 are in flight while kb is multiplied.
 template <int NR, int NRB>
@@ -179,7 +186,7 @@ struct GroupFixed {
     double* Hist[kGroupCols];
     double* Zplan[kGroupCols];
     uint8_t* Flag[kGroupCols];
-    uint32_t Res[3][kRowGroups][kGroupCols];  // high words: primal, dual residual; |q| partials
+    uint32_t Res[2][kRowGroups][kGroupCols];  // high words: residual partials; |q| partials
     int Nser[kGroupCols], Nticks[kGroupCols], Ftick[kGroupCols], Iter[kGroupCols], NotConv[kGroupCols];
     int Unit[2];                              // [0] unit index, [1] ticks of the longest column
 };
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                         for (int e = 0; e < 2; ++e) {
                             const double shifted = sR[(lc0 + e) * KP + (j + 1 < N ? j + 1 : N - 1)];
                             // last row: keep the primal value, drop the dual
-                            tv[r][e] = (j + 1 < N) ? shifted : fmin(fmax(shifted, lo[r][e]), hi[r][e]);
+                            tv[r][e] = (j + 1 < N) ? shifted : clipd(shifted, lo[r][e], hi[r][e]);
                         }
                     }
                 }
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                     q[r][e] = qv;
                     qmag[e] = max(qmag[e], mag_hi(qv));
                     // rho (z - w) - q with z = clip(t), w = t - z  ->  rho (2z - t) - q
-                    const double zc = fmin(fmax(tv[r][e], lo[r][e]), hi[r][e]);
+                    const double zc = clipd(tv[r][e], lo[r][e], hi[r][e]);
                     if (r < nrb) rOut0[e * KP + r * 8] = fma(P.rho, 2.0 * zc - tv[r][e], -qv);
                 }
             }
@@ -384,19 +391,20 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
             for (int e = 0; e < 2; ++e) {
 #pragma unroll
                 for (int o = 4; o <= 16; o <<= 1) qmag[e] = max(qmag[e], __shfl_xor_sync(0xffffffffu, qmag[e], o));
-                if (g == 0) S.Res[2][rg][lc0 + e] = qmag[e];
+                if (g == 0) S.Res[1][rg][lc0 + e] = qmag[e];
             }
             group_sync(bar_id);
-            // stop thresholds of my two columns: eps * max(1, |q|_inf), as high words
-            uint32_t thr_p[2], thr_d[2];
+            // Stop threshold of my two columns (as a high word).  The test uses d = |v - z_old|: the
+            // primal residual |v - z_new| <= (1 + alpha) d and the dual one rho |z_new - z_old| <= rho alpha d,
+            // so d <= eps * max(1, |q|_inf) / max(1 + alpha, rho alpha) bounds both by eps * max(1, |q|_inf).
+            uint32_t thr[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                uint32_t m = S.Res[2][0][lc0 + e];
+                uint32_t m = S.Res[1][0][lc0 + e];
 #pragma unroll
-                for (int q4 = 1; q4 < kRowGroups; ++q4) m = max(m, S.Res[2][q4][lc0 + e]);
+                for (int q4 = 1; q4 < kRowGroups; ++q4) m = max(m, S.Res[1][q4][lc0 + e]);
                 const double scale = fmax(1.0, __hiloint2double((int)m, 0));
-                thr_p[e] = mag_hi(P.eps * scale);
-                thr_d[e] = mag_hi(P.eps * scale / P.rho);
+                thr[e] = mag_hi(P.eps * scale * P.stop_factor);
             }
 
             // ---- ADMM ---------------------------------------------------------------------------
@@ -409,21 +417,20 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
                 ContractDispatch<NRB, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
 
-                // relaxation, projection, dual update, residuals, next right-hand side
-                uint32_t rp[2] = {0u, 0u}, rd[2] = {0u, 0u};
+                // relaxation, projection, dual update, residual, next right-hand side
+                uint32_t rd[2] = {0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     if (!done[e]) {
 #pragma unroll
                         for (int r = 0; r < NRB; ++r) {
                             if (r >= nrb) continue;
-                            const double v = acc[r][e];
-                            const double zo = fmin(fmax(tv[r][e], lo[r][e]), hi[r][e]);
+                            const double zo = clipd(tv[r][e], lo[r][e], hi[r][e]);
+                            const double d = acc[r][e] - zo;
                             // alpha v + (1 - alpha) zo + (t - zo)  =  t + alpha (v - zo)
-                            const double tn = fma(P.alpha, v - zo, tv[r][e]);
-                            const double zn = fmin(fmax(tn, lo[r][e]), hi[r][e]);
-                            rp[e] = max(rp[e], mag_hi(v - zn));
-                            rd[e] = max(rd[e], mag_hi(zn - zo));
+                            const double tn = fma(P.alpha, d, tv[r][e]);
+                            const double zn = clipd(tn, lo[r][e], hi[r][e]);
+                            rd[e] = max(rd[e], mag_hi(d));
                             tv[r][e] = tn;
                             acc[r][e] = fma(two_rho, zn, fma(-P.rho, tn, -q[r][e]));
                         }
@@ -432,17 +439,8 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
 #pragma unroll
-                    for (int o = 4; o <= 16; o <<= 1) {
-                        rp[e] = max(rp[e], __shfl_xor_sync(0xffffffffu, rp[e], o));
-                        rd[e] = max(rd[e], __shfl_xor_sync(0xffffffffu, rd[e], o));
-                    }
-                }
-                if (g == 0) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        S.Res[0][rg][lc0 + e] = rp[e];
-                        S.Res[1][rg][lc0 + e] = rd[e];
-                    }
+                    for (int o = 4; o <= 16; o <<= 1) rd[e] = max(rd[e], __shfl_xor_sync(0xffffffffu, rd[e], o));
+                    if (g == 0) S.Res[0][rg][lc0 + e] = rd[e];
                 }
                 group_sync(bar_id);   // every warp of the group has consumed R; partials are visible
 
@@ -453,14 +451,11 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                         for (int r = 0; r < NRB; ++r)
                             if (r < nrb) rOut0[e * KP + r * 8] = acc[r][e];
-                        uint32_t cp = S.Res[0][0][lc0 + e], cd = S.Res[1][0][lc0 + e];
+                        uint32_t cd = S.Res[0][0][lc0 + e];
 #pragma unroll
-                        for (int q4 = 1; q4 < kRowGroups; ++q4) {
-                            cp = max(cp, S.Res[0][q4][lc0 + e]);
-                            cd = max(cd, S.Res[1][q4][lc0 + e]);
-                        }
+                        for (int q4 = 1; q4 < kRowGroups; ++q4) cd = max(cd, S.Res[0][q4][lc0 + e]);
                         ++iters[e];
-                        done[e] = (cp <= thr_p[e]) && (cd <= thr_d[e]);
+                        done[e] = (cd <= thr[e]);
                     }
                     all_mine = all_mine && done[e];
                 }
@@ -476,7 +471,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                     if (!live[e]) continue;
                     const double x0 = S.X[lc * 3 + 0], x1 = S.X[lc * 3 + 1], x2 = S.X[lc * 3 + 2];
                     const double l0 = lo[0][e], h0 = hi[0][e];
-                    const double z0 = fmin(fmax(tv[0][e], l0), h0);
+                    const double z0 = clipd(tv[0][e], l0, h0);
                     const double pred = fma(P.px02, x2, fma(P.T, x1, x0));
                     const double jerk = (z0 - pred) / P.pu00;
                     double n0 = fma(P.c3, jerk, fma(P.c2, x2, fma(P.T, x1, x0)));
@@ -510,7 +505,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                         for (int r = 0; r < NRB; ++r) {
                             const int j = row0 + r * 8;
-                            if (r < nrb && j < N) pz[j] = fmin(fmax(tv[r][e], lo[r][e]), hi[r][e]);
+                            if (r < nrb && j < N) pz[j] = clipd(tv[r][e], lo[r][e], hi[r][e]);
                         }
                     }
                 }
@@ -574,6 +569,7 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
     P.strict_flags = 1;
     P.max_iter = d.max_iter;
     P.rho = d.rho; P.alpha = d.alpha; P.eps = d.eps; P.viol_tol = d.viol_tol;
+    P.stop_factor = 1.0 / std::fmax(1.0 + d.alpha, d.rho * d.alpha);
     P.Qhalf = 0.5 * d.Q;
     P.T = plan->T; P.c2 = std::pow(d.dt, 2) / 2.0; P.c3 = std::pow(d.dt, 3) / 6.0; P.hg = plan->hg;
     P.px02 = P.c2 - P.hg;

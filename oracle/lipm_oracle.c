@@ -171,29 +171,29 @@ static int admm_solve(const oracle_plan *p, const double *x, const double *lo, c
         const double z = clip(tv[j], lo[j], hi[j]);
         rhs[j] = rho * (2.0 * z - tv[j]) - q[j];          /* rho (z - w) - q,  w = t - z */
     }
-    /* stop test: primal and rho*dual residual <= eps * max(1, |q|_inf)  (relative to the linear
-     * term: a diverging "fall" has a huge q and an absolute test would sit below FP64 rounding) */
+    /* stop test on d = |v - z_old|: primal residual |v - z_new| <= (1+alpha) d and dual residual
+     * rho |z_new - z_old| <= rho alpha d, so d <= thr bounds both by eps * max(1, |q|_inf)
+     * (relative to the linear term: a diverging "fall" has a huge q and an absolute test would
+     * sit below FP64 rounding) */
     double qmag = 0.0;
     for (int j = 0; j < N; ++j) qmag = fmax(qmag, fabs(q[j]));
-    const double thr = p->eps * fmax(1.0, qmag);
+    const double thr = p->eps * fmax(1.0, qmag) / fmax(1.0 + alpha, rho * alpha);
     *converged = 0;
     int it = 0;
     while (it < p->max_iter) {
         ++it;
-        double rp = 0.0, rd = 0.0;
+        double dmax = 0.0;
         for (int i = 0; i < N; ++i) {
             const double *Mi = p->M + (size_t)i * N;
             double v = 0.0;
             for (int j = 0; j < N; ++j) v += Mi[j] * rhs[j];
             const double zo = clip(tv[i], lo[i], hi[i]);
-            const double tn = tv[i] + alpha * (v - zo);   /* alpha v + (1-alpha) zo + (t - zo) */
-            const double zn = clip(tn, lo[i], hi[i]);
-            rp = fmax(rp, fabs(v - zn));
-            rd = fmax(rd, fabs(zn - zo));
-            tv[i] = tn;
+            const double d = v - zo;
+            dmax = fmax(dmax, fabs(d));
+            tv[i] = tv[i] + alpha * d;                    /* alpha v + (1-alpha) zo + (t - zo) */
         }
         for (int i = 0; i < N; ++i) rhs[i] = rho * (2.0 * clip(tv[i], lo[i], hi[i]) - tv[i]) - q[i];
-        if (rp <= thr && rho * rd <= thr) { *converged = 1; break; }
+        if (dmax <= thr) { *converged = 1; break; }
     }
     return it;
 }

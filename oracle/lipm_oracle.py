@@ -153,18 +153,17 @@ def strict_axis_admm(p: Problem, x: np.ndarray, zmax: np.ndarray, zmin: np.ndarr
     z = np.clip(np.zeros(p.N) if z0 is None else z0, zmin, zmax)
     w = np.zeros(p.N) if w0 is None else w0.copy()
     it = 0
+    # Stop test on d = |v - z_old|: primal residual <= (1+alpha) d, dual residual <= rho alpha d; the
+    # threshold is relative to the linear term (diverging "falls" have a huge q and an absolute
+    # test would sit below their FP64 rounding floor).
+    thr = eps * max(1.0, np.max(np.abs(q))) / max(1.0 + alpha, rho * alpha)
     for it in range(1, max_iter + 1):
         v = M @ (rho * (z - w) - q)
-        xh = alpha * v + (1.0 - alpha) * z
-        t = xh + w
-        zn = np.minimum(np.maximum(t, zmin), zmax)
-        w = t - zn
-        r_prim = np.max(np.abs(v - zn))
-        r_dual = rho * np.max(np.abs(zn - z))
-        z = zn
-        # stop test relative to the magnitude of the linear term (diverging "falls" have a huge
-        # q; an absolute test would sit below their FP64 rounding floor)
-        if max(r_prim, r_dual) <= eps * max(1.0, np.max(np.abs(q))):
+        d = np.max(np.abs(v - z))
+        t = alpha * v + (1.0 - alpha) * z + w
+        z = np.minimum(np.maximum(t, zmin), zmax)
+        w = t - z
+        if d <= thr:
             break
     jerk0 = (z[0] - p.Px[0] @ x) / p.Pu[0, 0]
     return p.A @ x + p.B * jerk0, z, w, it
