@@ -129,7 +129,9 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
 /*
  * Work accounting of the last strict launch on this plan (blocking read-back):
  *   host_out[0] = ADMM iterations executed by 8-column solver groups (each occupies 8 column
- *                 slots of the tensor pipe, converged or not); host_out[1] = 8-column units walked.
+ *                 slots of the tensor pipe, converged or not); host_out[1] = 8-column units walked;
+ *   host_out[2], host_out[3] = debug cycle counters (zero unless LIPM_STRICT_SKIP has bit 16).
+ *   host_out must hold 4 values.
  * Useful-work fraction = sum(iters) / (8 * host_out[0]).
  */
 int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out);

@@ -139,7 +139,7 @@ int lipm_plan_export(const lipm_plan_t* plan, int which, double* host_out, size_
 int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out) {
     if (!plan || !host_out) { set_error("lipm_plan_stats: null argument"); return LIPM_E_INVALID; }
     DeviceGuard guard(plan->desc.device);
-    LIPM_CUDA_TRY(cudaMemcpy(host_out, plan->d_stats, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    LIPM_CUDA_TRY(cudaMemcpy(host_out, plan->d_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return LIPM_OK;
 }
 

@@ -233,8 +233,8 @@ int build_plan_matrices(lipm_plan* plan) {
     LIPM_CUDA_TRY(cudaMalloc(&plan->d_tile_counter, sizeof(unsigned int)));
     LIPM_CUDA_TRY(cudaMemset(plan->d_info, 0, sizeof(int) * 4));
     LIPM_CUDA_TRY(cudaMemset(plan->d_tile_counter, 0, sizeof(unsigned int)));
-    LIPM_CUDA_TRY(cudaMalloc(&plan->d_stats, 2 * sizeof(unsigned long long)));
-    LIPM_CUDA_TRY(cudaMemset(plan->d_stats, 0, 2 * sizeof(unsigned long long)));
+    LIPM_CUDA_TRY(cudaMalloc(&plan->d_stats, 4 * sizeof(unsigned long long)));
+    LIPM_CUDA_TRY(cudaMemset(plan->d_stats, 0, 4 * sizeof(unsigned long long)));
 
     k_model<<<(N + 127) / 128, 128>>>(s, N, plan->d_px, plan->d_pu, plan->d_abc);
     k_toeplitz_inverse<<<1, 256, sizeof(double) * 2 * N>>>(N, plan->d_pu, plan->d_tinv);

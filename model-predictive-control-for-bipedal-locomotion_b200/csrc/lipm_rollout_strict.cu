@@ -38,6 +38,8 @@
 // order, so a scenario's result is bit-identical whatever batch, unit or GPU it lands in.
 #include "lipm_internal.cuh"
 
+#include <cstdlib>
+
 namespace lipm {
 
 namespace {
@@ -58,6 +60,8 @@ struct StrictParams {
     unsigned int* tile_counter;
     unsigned long long* stats;   // [0] group iterations executed (8 column slots each), [1] units
     unsigned int num_units;   // 8-column work units
+    int active_groups;        // debug: solver groups per CTA that take work (LIPM_STRICT_GROUPS)
+    int debug_skip;           // debug (LIPM_STRICT_SKIP): 1 skip contraction, 2 skip epilogue math, 4 skip barrier, 8 never converge
     size_t nfrag;           // doubles in mfrag
 };
 
@@ -139,40 +143,50 @@ __device__ __forceinline__ double clipd(double x, double lo, double hi) {
 
 // acc[r] += M[row block r of this warp] * R[:, this group's 8 columns]   (NR row blocks, all k).
 // Fragments are double buffered: the loads of k-block kb+1 are in flight while kb is multiplied.
-template <int NR, int NRB>
 // (No __restrict__ on bBase: R is rewritten between calls and the loads must stay behind the
 // group barrier that publishes it.)
+// KBC > 0: compile-time trip count, fully unrolled (straight-line code keeps ptxas' warp
+// convergence check -- YIELD / WARPSYNC.ALL -- out of the inner loop); KBC == 0: run-time count.
+template <int NR, int NRB, int KBC>
 __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aBase,
-                                         const int aStride, const volatile double* bBase, const int KB) {
+                                         const int aStride, const volatile double* bBase, const int KB_rt) {
+    const int KB = KBC > 0 ? KBC : KB_rt;
     double a0[NR], a1[NR], b0, b1;
     b0 = bBase[0];
 #pragma unroll
     for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride];
-#pragma unroll 1
-    for (int kb = 0; kb < KB; kb += 2) {     // KB = NP/4 is even because NP is a multiple of 8
+    auto trip = [&](int kb) {
         b1 = bBase[(kb + 1) * 4];
 #pragma unroll
         for (int r = 0; r < NR; ++r) a1[r] = aBase[r * aStride + (kb + 1) * 32];
 #pragma unroll
         for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a0[r], b0);
-        const int kn = (kb + 2 < KB) ? kb + 2 : kb;   // last trip reloads a valid block, unused
-        b0 = bBase[kn * 4];
+        if (kb + 2 < KB) {
+            b0 = bBase[(kb + 2) * 4];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride + kn * 32];
+            for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride + (kb + 2) * 32];
+        }
 #pragma unroll
         for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a1[r], b1);
+    };
+    if (KBC > 0) {
+#pragma unroll
+        for (int kb = 0; kb < KBC; kb += 2) trip(kb);
+    } else {
+#pragma unroll 1
+        for (int kb = 0; kb < KB; kb += 2) trip(kb);     // KB = NP/4 is even: NP is a multiple of 8
     }
 }
-template <int NR, int NRB>
+template <int NR, int NRB, int KBC>
 struct ContractDispatch {
     static __device__ __forceinline__ void run(int nrb, double (&acc)[NRB][2], const double* aBase, int aStride,
                                                const volatile double* bBase, int KB) {
-        if (nrb == NR) contract<NR, NRB>(acc, aBase, aStride, bBase, KB);
-        else ContractDispatch<NR - 1, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
+        if (nrb == NR) contract<NR, NRB, KBC>(acc, aBase, aStride, bBase, KB);
+        else ContractDispatch<NR - 1, NRB, KBC>::run(nrb, acc, aBase, aStride, bBase, KB);
     }
 };
-template <int NRB>
-struct ContractDispatch<0, NRB> {
+template <int NRB, int KBC>
+struct ContractDispatch<0, NRB, KBC> {
     static __device__ __forceinline__ void run(int, double (&)[NRB][2], const double*, int, const volatile double*, int) {}
 };
 
@@ -254,6 +268,8 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
     // ADMM state of this thread's elements: tv = relaxed iterate + dual (z = clip(tv), w = tv - z)
     double tv[NRB][2], lo[NRB][2], hi[NRB][2], q[NRB][2];
+
+    if (grp >= P.active_groups) return;   // measurement knob; all groups by default
 
     for (;;) {
         // ---- fetch an 8-column unit (y-axis units, which iterate longer, are handed out first) --
@@ -415,13 +431,23 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                 for (int r = 0; r < NRB; ++r) acc[r][0] = acc[r][1] = 0.0;
 
-                ContractDispatch<NRB, NRB>::run(nrb, acc, aBase, aStride, bBase, KB);
+                long long tc0 = 0;
+                if (P.debug_skip & 16) tc0 = clock64();
+                if (!(P.debug_skip & 1)) ContractDispatch<NRB, NRB, NPC / 4>::run(nrb, acc, aBase, aStride, bBase, KB);
+                if ((P.debug_skip & 16) && tid == 0) {
+                    // wait for the accumulators, then charge the elapsed cycles to the contraction
+                    double sink = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NRB; ++r) sink += acc[r][0];
+                    if (sink == 1.2345e300) S.Viol[0] = sink;
+                    atomicAdd(P.stats + 2, (unsigned long long)(clock64() - tc0));
+                }
 
                 // relaxation, projection, dual update, residual, next right-hand side
                 uint32_t rd[2] = {0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    if (!done[e]) {
+                    if (!done[e] && !(P.debug_skip & 2)) {
 #pragma unroll
                         for (int r = 0; r < NRB; ++r) {
                             if (r >= nrb) continue;
@@ -442,7 +468,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                     for (int o = 4; o <= 16; o <<= 1) rd[e] = max(rd[e], __shfl_xor_sync(0xffffffffu, rd[e], o));
                     if (g == 0) S.Res[0][rg][lc0 + e] = rd[e];
                 }
-                group_sync(bar_id);   // every warp of the group has consumed R; partials are visible
+                if (!(P.debug_skip & 4)) group_sync(bar_id);   // every warp of the group has consumed R; partials are visible
 
                 bool all_mine = true;
 #pragma unroll
@@ -455,12 +481,14 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                         for (int q4 = 1; q4 < kRowGroups; ++q4) cd = max(cd, S.Res[0][q4][lc0 + e]);
                         ++iters[e];
-                        done[e] = (cd <= thr[e]);
+                        done[e] = (cd <= thr[e]) && !(P.debug_skip & 8);
                     }
                     all_mine = all_mine && done[e];
                 }
                 ++group_iters;
-                if (group_sync_and(bar_id, all_mine)) break;   // new R visible; partials consumed
+                const bool stop = group_sync_and(bar_id, all_mine);   // new R visible; partials consumed
+                if ((P.debug_skip & 16) && tid == 0) atomicAdd(P.stats + 3, (unsigned long long)(clock64() - tc0));
+                if (stop) break;
             }
 
             // ---- apply the first sample: state update, push, outputs --------------------------
@@ -542,12 +570,19 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
     auto kernel = k_strict_rollout<NRB, NG, NPC>;
     LIPM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StrictParams Q = P;
+    Q.active_groups = NG;
+    Q.debug_skip = 0;
+    if (const char* env = std::getenv("LIPM_STRICT_SKIP")) Q.debug_skip = std::atoi(env);
+    if (const char* env = std::getenv("LIPM_STRICT_GROUPS")) {
+        const int v = std::atoi(env);
+        if (v >= 1 && v < NG) Q.active_groups = v;
+    }
     Q.num_units = (unsigned)((P.cb.ncols + kGroupCols - 1) / kGroupCols);
     if (Q.num_units == 0) return LIPM_OK;
     const unsigned ctas = (Q.num_units + NG - 1) / NG;
     const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 2 * sizeof(unsigned long long), stream));
+    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), stream));
     kernel<<<grid, kGroupThreads * NG, smem, stream>>>(Q);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;

@@ -169,9 +169,10 @@ class LipmPlan:
 
     def stats(self) -> Dict[str, int]:
         """Work accounting of the last strict launch (synchronises)."""
-        out = np.zeros(2, dtype=np.uint64)
+        out = np.zeros(4, dtype=np.uint64)
         _check(self._lib.lipm_plan_stats(self._handle, out.ctypes.data))
-        return {"group_iterations": int(out[0]), "units": int(out[1])}
+        return {"group_iterations": int(out[0]), "units": int(out[1]),
+                "debug_cycles_contraction": int(out[2]), "debug_cycles_iteration": int(out[3])}
 
     # ------------------------------------------------------------------ walks
     def rollout(self, mode: int, x0, y0, z_min, z_max, *, n_steps=None, impulse=None, force_tick=None,
