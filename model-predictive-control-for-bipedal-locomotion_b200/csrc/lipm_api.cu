@@ -181,8 +181,17 @@ int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n
     cb.status = status;
     cb.iters = iters;
     cb.zmp_plan = nullptr;
-    return mode == LIPM_MODE_STRICT ? launch_strict_rollout(plan, cb, (cudaStream_t)stream)
-                                    : launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream);
+    if (mode != LIPM_MODE_STRICT) return launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream);
+    // strict walks: group scenarios that will need similar iteration counts (lipm_order.cu)
+    int* order = nullptr;
+    if (B > 8 && (n_steps || (impulse && force_tick))) {
+        const int rc = build_processing_order(B, n_max, n_steps, impulse, force_tick, &order, (cudaStream_t)stream);
+        if (rc != LIPM_OK) return rc;
+    }
+    cb.order = order;
+    const int rc = launch_strict_rollout(plan, cb, (cudaStream_t)stream);
+    if (order) cudaFreeAsync(order, (cudaStream_t)stream);
+    return rc;
 }
 
 int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, const double* z_min,

@@ -70,7 +70,8 @@ int build_plan_matrices(lipm_plan* plan);
 // One "column" = one axis of one scenario.  The rollout kernels receive this flat description.
 struct ColumnBatch {
     int ncols;              // number of columns (2B for walks, B for single ticks)
-    int B;                  // scenarios; column c -> scenario c % B, axis c / B
+    int B;                  // scenarios; column c -> slot c % B, axis c / B
+    const int* order;       // [B] scenario processed in each slot (nullptr: identity)
     int bounds_batch;       // 1 (shared) or B
     long long bound_scn_stride;   // doubles between consecutive scenarios' bound series
     int bound_stride;       // doubles between consecutive samples of one axis (2 walks, 1 ticks)
@@ -96,6 +97,8 @@ struct ColumnBatch {
     double* zmp_plan;       // [ncols,N] or nullptr: final previewed ZMP of the last tick
 };
 
+int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
+                           const int32_t* force_tick, int** perm_out, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_jerk_from_zmp(lipm_plan* plan, int ncols, const double* state, const double* zmp_plan,

@@ -1,0 +1,58 @@
+// Processing order of the scenarios of a batch.
+//
+// A solver group iterates its 8 columns until the slowest one has converged, so columns that
+// need similar iteration counts should share a group.  What drives the count is known before
+// the walk starts: the walk length and the push (when, how hard).  Scenarios are therefore
+// processed in the order of the key (n_steps, force_tick, impulse); results are written to
+// the scenario's own slots, so the order is invisible to the caller and -- every column being
+// solved independently and deterministically -- does not change a single bit of the output.
+#include "lipm_internal.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace lipm {
+
+namespace {
+
+__global__ void k_order_keys(int B, int n_uniform, const int32_t* __restrict__ n_steps,
+                             const double* __restrict__ impulse, const int32_t* __restrict__ force_tick,
+                             unsigned long long* __restrict__ keys, int* __restrict__ ids) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const unsigned long long n = (unsigned long long)min(max(n_steps ? n_steps[b] : n_uniform, 0), (1 << 20) - 1);
+    long long tick = (impulse && force_tick) ? (long long)force_tick[b] + 1 : 0;   // 0 = no push
+    tick = tick < 0 ? 0 : (tick > (1 << 20) - 1 ? (1 << 20) - 1 : tick);
+    const float f = impulse ? fabsf((float)impulse[b]) : 0.0f;
+    const unsigned long long mag = (unsigned long long)(__float_as_uint(f) >> 8);   // 24 bits, order preserving
+    keys[b] = (n << 44) | ((unsigned long long)tick << 24) | mag;
+    ids[b] = b;
+}
+
+}  // namespace
+
+// perm[slot] = scenario processed in that slot.  Buffers come from the stream-ordered allocator;
+// `*perm_out` must be released with cudaFreeAsync on the same stream after the rollout launch.
+int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
+                           const int32_t* force_tick, int** perm_out, cudaStream_t stream) {
+    *perm_out = nullptr;
+    unsigned long long *keys_in = nullptr, *keys_out = nullptr;
+    int *ids_in = nullptr, *ids_out = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, ids_in, ids_out, B, 0, 64, stream));
+    LIPM_CUDA_TRY(cudaMallocAsync(&keys_in, sizeof(unsigned long long) * 2 * (size_t)B, stream));
+    keys_out = keys_in + B;
+    LIPM_CUDA_TRY(cudaMallocAsync(&ids_in, sizeof(int) * (size_t)B, stream));
+    LIPM_CUDA_TRY(cudaMallocAsync(&ids_out, sizeof(int) * (size_t)B, stream));
+    LIPM_CUDA_TRY(cudaMallocAsync(&temp, temp_bytes ? temp_bytes : 16, stream));
+    k_order_keys<<<(B + 255) / 256, 256, 0, stream>>>(B, n_uniform, n_steps, impulse, force_tick, keys_in, ids_in);
+    LIPM_CUDA_TRY(cudaGetLastError());
+    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, ids_in, ids_out, B, 0, 64, stream));
+    LIPM_CUDA_TRY(cudaFreeAsync(temp, stream));
+    LIPM_CUDA_TRY(cudaFreeAsync(keys_in, stream));
+    LIPM_CUDA_TRY(cudaFreeAsync(ids_in, stream));
+    *perm_out = ids_out;
+    return LIPM_OK;
+}
+
+}  // namespace lipm

@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
             const int c = col0 + gtid;
             const bool valid = c < B.ncols;
             const int axis = valid ? c / B.B : 0;
-            const int b = valid ? c - axis * B.B : 0;
+            int b = valid ? c - axis * B.B : 0;
+            if (valid && B.order) b = B.order[b];
             int n = valid ? (B.n_steps ? B.n_steps[b] : B.n_uniform) : 0;
             n = n > B.n_max ? B.n_max : n;
             int ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
@@ -549,7 +550,9 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
         if (gtid < kGroupCols) {
             const int c = col0 + gtid;
             if (c < B.ncols) {
-                const int axis = c / B.B, b = c - axis * B.B;
+                const int axis = c / B.B;
+                const int slot = c - axis * B.B;
+                const int b = B.order ? B.order[slot] : slot;
                 if (B.max_violation) B.max_violation[b * 2 + axis] = S.Viol[gtid];
                 if (B.status) B.status[b * 2 + axis] = S.NotConv[gtid];
                 if (B.iters) B.iters[b * 2 + axis] = S.Iter[gtid];
