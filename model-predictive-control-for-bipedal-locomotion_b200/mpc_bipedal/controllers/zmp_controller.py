@@ -57,7 +57,8 @@ class ZMPController:
     # ------------------------------------------------------------------ batched entry (new, additive)
     def generate_com_trajectory_batched(self, x_init, y_init, z_max, z_min, *, F_ext=None, m=None,
                                         force_tick=None, n_steps=None, add_force: Optional[bool] = None,
-                                        strict: Optional[bool] = None, to_numpy: bool = True):
+                                        strict: Optional[bool] = None, to_numpy: bool = True,
+                                        fall_angle_deg: float = 30.0):
         """Walks of B independent scenarios in one device launch.
 
         x_init, y_init: (B,3).  z_max, z_min: (n,2) shared by all scenarios or (B,n,2).
@@ -65,7 +66,12 @@ class ZMPController:
         velocity after tick ``force_tick`` (default ``n_steps // 2`` as the reference, :90).
         n_steps: (B,) int, bound samples per scenario (default: all n).
         Returns dict(com (B,n,2), x_hist, y_hist (B,n,3), zmp (B,n,2), flags (B,n,2) uint8,
-        max_violation (B,), status (B,), iters (B,2)).
+        max_violation (B,), fell (B,) bool, status (B,), iters (B,2)).
+
+        ``fell`` is a definition of this build (the reference computes no outcome): the walk counts
+        as a fall when the CoM gets further from the ZMP than ``h * tan(fall_angle_deg)``, i.e. the
+        pendulum leans more than that angle -- in strict mode the ZMP cannot leave the sole, so an
+        unrecoverable push shows up as the CoM running away from it.
         """
         import torch
         from .. import engine
@@ -91,12 +97,16 @@ class ZMPController:
         out = plan.rollout(mode, x_init, y_init, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick)
         x_hist, y_hist = out["x_hist"], out["y_hist"]
         c = torch.as_tensor(self.C, device=x_hist.device)
+        com = torch.stack([x_hist[..., 0], y_hist[..., 0]], dim=-1)
+        zmp = torch.stack([x_hist @ c, y_hist @ c], dim=-1)                  # reference run_mpc.py:294
+        lean = (com - zmp).abs().amax(dim=(1, 2))
         res = {
-            "com": torch.stack([x_hist[..., 0], y_hist[..., 0]], dim=-1),
+            "com": com,
             "x_hist": x_hist, "y_hist": y_hist,
-            "zmp": torch.stack([x_hist @ c, y_hist @ c], dim=-1),            # reference run_mpc.py:294
+            "zmp": zmp,
             "flags": out["flags"],
             "max_violation": out["max_violation"].amax(dim=1),
+            "fell": lean > cfg.h * float(np.tan(np.radians(fall_angle_deg))),
             "status": out["status"].sum(dim=1),
             "iters": out["iters"],
         }
