@@ -187,7 +187,8 @@ def run_ours(args, rank, world, local_rank):
     cfg, z_max, z_min, F, tick = sweep_inputs(B, seed=rank)
     n = len(z_min)
     solves_per_step = B * 2 * (n - 1)
-    plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R)
+    precision = engine.PRECISION_F16X3 if args.precision == "f16x3" else engine.PRECISION_FP64
+    plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R, precision=precision)
     mode = engine.MODE_STRICT if args.mode == "strict" else engine.MODE_UNCONSTRAINED
 
     # device-resident inputs for `value`
@@ -230,6 +231,7 @@ def run_ours(args, rank, world, local_rank):
     total_s = total_ms.item() * 1e-3
     value = world * solves_per_step * args.steps / total_s
 
+    slots = 128 if precision == engine.PRECISION_F16X3 else 8      # columns a solver unit iterates together
     iters = out["iters"].sum().item() if mode == engine.MODE_STRICT else 0
     stats = plan.stats() if mode == engine.MODE_STRICT else {"group_iterations": 0, "units": 0}
     status_bad = int((out["status"] != 0).sum().item())
@@ -238,6 +240,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the public API with host buffers ---------------------------------------
     ctrl = ZMPController(cfg)
     ctrl.config.strict = (args.mode == "strict")
+    ctrl.solver_options = {"precision": precision}
     hx0 = np.zeros((B, 3)); hy0 = np.zeros((B, 3))
     e2e_steps = max(1, min(args.steps, 3))
     ctrl.generate_com_trajectory_batched(hx0, hy0, z_max, z_min, F_ext=F, force_tick=tick)   # warm
@@ -268,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "admm": {"rho": 2.0, "alpha": 1.6, "eps": 1e-12,
                                 "mean_iters_per_solve": iters / max(solves_per_step, 1),
-                                "useful_column_slot_fraction": iters / max(8 * stats["group_iterations"], 1)}},
+                                "useful_column_slot_fraction": iters / max(slots * stats["group_iterations"], 1)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "api": "ZMPController.generate_com_trajectory_batched (NumPy in, NumPy out)"},
             "gpu_launches": args.steps,
@@ -300,6 +303,7 @@ def main():
     ap.add_argument("--batch", type=int, default=SCENARIOS_PER_GPU, help="scenarios per GPU")
     ap.add_argument("--mode", choices=["strict", "unconstrained"], default="strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", choices=["fp64", "f16x3"], default="fp64")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

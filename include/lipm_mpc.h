@@ -41,6 +41,12 @@ typedef struct lipm_plan lipm_plan_t;
 #define LIPM_MODE_UNCONSTRAINED 0 /* closed form, zmp_controller.py:196-198                 */
 #define LIPM_MODE_STRICT 1        /* box-constrained QP, zmp_controller.py:173-195          */
 
+/* arithmetic of the strict mode -- north_star: "FP64 DMMA for the exactness path, and a
+ * reduced-precision path with FP32 accumulate for throughput" */
+#define LIPM_PRECISION_FP64 0   /* FP64 tensor pipe (DMMA); trajectories <= 1e-9 relative          */
+#define LIPM_PRECISION_F16X3 1  /* tcgen05 FP16 operands split hi+lo (3 products), FP32 accumulate,
+                                   FP32 ADMM state, FP64 walk state; trajectories <= 1e-4 m; N <= 152 */
+
 /* per-sample flag bits written by rollouts: flags[b][t][axis] */
 #define LIPM_FLAG_ACTIVE_LO 1u     /* applied ZMP sample sits on its lower bound (strict)   */
 #define LIPM_FLAG_ACTIVE_HI 2u     /* ... on its upper bound                                */
@@ -63,10 +69,12 @@ typedef struct lipm_plan_desc {
     double Q, R;       /* tracking / jerk weights (zmp_controller.py:186, :174)             */
     double rho;        /* ADMM penalty          (<=0 -> default 2.0)                        */
     double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.6)                        */
-    double eps;        /* ADMM stop: primal and rho*dual residual <= eps * max(1, |q|_inf)  (<=0 -> 1e-12) */
+    double eps;        /* ADMM stop: primal and rho*dual residual <= eps * max(1, |q|_inf)  (<=0 -> 1e-12;
+                          F16X3: <=0 -> 1e-5, floor 5e-7)                                   */
     int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000)                           */
     double viol_tol;   /* box-violation tolerance for LIPM_FLAG_VIOL_* (<0 -> 1e-9)         */
     int32_t device;    /* CUDA device ordinal                                               */
+    int32_t precision; /* LIPM_PRECISION_* of the strict mode (eps default 1e-5 for F16X3)          */
 } lipm_plan_desc_t;
 
 /*
@@ -139,7 +147,10 @@ int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out);
 /* Library / build information. */
 const char* lipm_last_error(void);
 const char* lipm_version(void);
-/* Largest horizon the resident-matrix strict kernel of this build serves. */
+/* Largest horizon of the reduced-precision strict kernel (LIPM_PRECISION_F16X3). */
+int lipm_max_reduced_horizon(void);
+/* Largest horizon the strict kernels of this build serve (the matrix is resident in shared
+ * memory up to N = 160 and streamed from L2 beyond that). */
 int lipm_max_strict_horizon(void);
 
 #ifdef __cplusplus

@@ -34,7 +34,7 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_gain, p->d_info, p->d_tile_counter, p->d_stats};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_gain, p->d_info, p->d_tile_counter, p->d_stats, p->d_bf16};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }
@@ -48,7 +48,9 @@ extern "C" {
 
 const char* lipm_last_error(void) { return g_error; }
 
-const char* lipm_version(void) { return "lipm_mpc 0.1 (sm_100a; fp64 DMMA ADMM, gain-row unconstrained)"; }
+const char* lipm_version(void) { return "lipm_mpc 0.2 (sm_100a; fp64 DMMA ADMM, tcgen05 f16x3 ADMM, gain-row unconstrained)"; }
+
+int lipm_max_reduced_horizon(void) { return kMaxReducedHorizon; }
 
 int lipm_max_strict_horizon(void) { return kMaxStrictHorizon; }
 
@@ -65,6 +67,18 @@ int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
     if (!(d.rho > 0)) d.rho = 2.0;
     if (!(d.alpha > 0)) d.alpha = 1.6;
     if (d.alpha >= 2.0) { set_error("alpha must be in (0, 2), got %g", d.alpha); return LIPM_E_INVALID; }
+    if (d.precision != LIPM_PRECISION_FP64 && d.precision != LIPM_PRECISION_F16X3) {
+        set_error("unknown precision %d", d.precision);
+        return LIPM_E_INVALID;
+    }
+    if (d.precision == LIPM_PRECISION_F16X3) {
+        if (d.horizon > kMaxReducedHorizon) {
+            set_error("precision F16X3: horizon %d exceeds the reduced-precision kernel's limit %d", d.horizon, kMaxReducedHorizon);
+            return LIPM_E_UNSUPPORTED;
+        }
+        if (!(d.eps > 0)) d.eps = 1e-5;
+        if (d.eps < 5e-7) d.eps = 5e-7;     // FP32 iterates: below this the stop test sits in the rounding noise
+    }
     if (!(d.eps > 0)) d.eps = 1e-12;
     if (d.max_iter <= 0) d.max_iter = 2000;
     if (d.viol_tol < 0 || !std::isfinite(d.viol_tol)) d.viol_tol = 1e-9;
@@ -189,7 +203,8 @@ int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n
         if (rc != LIPM_OK) return rc;
     }
     cb.order = order;
-    const int rc = launch_strict_rollout(plan, cb, (cudaStream_t)stream);
+    const int rc = plan->desc.precision == LIPM_PRECISION_F16X3 ? launch_strict_rollout_f16(plan, cb, (cudaStream_t)stream)
+                                                                : launch_strict_rollout(plan, cb, (cudaStream_t)stream);
     if (order) cudaFreeAsync(order, (cudaStream_t)stream);
     return rc;
 }
@@ -238,8 +253,9 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
         cb.status = stage;
         cb.iters = stage + 2 * (size_t)B;
     }
-    int rc = mode == LIPM_MODE_STRICT ? launch_strict_rollout(plan, cb, (cudaStream_t)stream)
-                                      : launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream);
+    int rc = mode != LIPM_MODE_STRICT ? launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream)
+             : plan->desc.precision == LIPM_PRECISION_F16X3 ? launch_strict_rollout_f16(plan, cb, (cudaStream_t)stream)
+                                                            : launch_strict_rollout(plan, cb, (cudaStream_t)stream);
     if (rc == LIPM_OK && stage) {
         if (status) LIPM_CUDA_TRY(cudaMemcpy2DAsync(status, sizeof(int32_t), stage, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         if (iters) LIPM_CUDA_TRY(cudaMemcpy2DAsync(iters, sizeof(int32_t), stage + 2 * (size_t)B, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

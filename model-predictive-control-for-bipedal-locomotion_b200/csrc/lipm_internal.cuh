@@ -32,7 +32,22 @@ __host__ __device__ inline int column_pitch(int np) { return np + 4; }
 
 constexpr int kRowGroups = 4;       // warps along the row dimension of the iteration matrix
 constexpr int kMaxRowBlocksPerWarp = 5;
-constexpr int kMaxStrictHorizon = 8 * kRowGroups * kMaxRowBlocksPerWarp;  // 160
+constexpr int kMaxResidentHorizon = 8 * kRowGroups * kMaxRowBlocksPerWarp;  // 160: matrix resident in shared memory
+constexpr int kMaxStrictHorizon = 8 * 16 * kMaxRowBlocksPerWarp;             // 640: matrix streamed from L2 beyond that
+
+// Reduced-precision strict kernel (tcgen05): fixed 128 x 160 x 160 tile.  Rows 0..151 carry the
+// horizon, contraction slots 152..154 carry the axis state (the G Px x term rides in the K padding).
+constexpr int kF16Tile = 160;                 // padded horizon = MMA N = MMA K
+constexpr int kF16Cols = 128;                 // columns (scenario axes) per CTA = MMA M = TMEM lanes
+constexpr int kF16StateSlot = 152;            // first contraction slot of the state
+constexpr int kMaxReducedHorizon = 152;
+constexpr int kF16OperandBytesB = (kF16Tile / 8) * (kF16Tile / 8) * 128;   // 51200: one FP16 image of B
+constexpr int kF16OperandBytesA = (kF16Tile / 8) * (kF16Cols / 8) * 128;   // 40960: one FP16 image of A
+// Byte offset of element (row, k) of a K-major operand without swizzle: 8 x 16-byte core matrices,
+// 128 B between 8-row groups (SBO), rows/8 * 128 B between 8-element K chunks (LBO).
+__host__ __device__ inline int f16_operand_offset(int row, int k, int rows) {
+    return (k >> 3) * ((rows >> 3) * 128) + (row >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
 
 // ------------------------------------------------------------------ the plan
 }  // namespace lipm
@@ -57,6 +72,7 @@ struct lipm_plan {
     double* d_minv;       // [N,N] (Q I + G + rho I)^-1
     double* d_mfrag;      // [(NP/8) x (NP/4) x 32] ADMM matrix in DMMA A-fragment order
     double* d_gain;       // [N+3] kz, kx
+    unsigned char* d_bf16; // [2 x kF16OperandBytesB] FP16 hi / lo images of [M | M G Px] (F16X3 plans only)
     int* d_info;          // [4] factorisation status words
     unsigned int* d_tile_counter;  // dynamic work-unit scheduler of the strict kernel
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch
@@ -100,6 +116,7 @@ struct ColumnBatch {
 int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
                            const int32_t* force_tick, int** perm_out, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_jerk_from_zmp(lipm_plan* plan, int ncols, const double* state, const double* zmp_plan,
                          double* jerk_plan, cudaStream_t stream);

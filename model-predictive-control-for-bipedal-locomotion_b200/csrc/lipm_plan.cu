@@ -13,6 +13,8 @@
 
 #include <cmath>
 
+#include <cuda_fp16.h>
+
 namespace lipm {
 
 namespace {
@@ -190,6 +192,28 @@ __global__ void k_gain(int N, double Q, double pu00, const double* __restrict__ 
     }
 }
 
+// B operand of the reduced-precision kernel: row n (output row), contraction index k:
+//   k < N            -> M[n][k]
+//   k = 152 + c      -> (M G Px)[n][c]   (multiplies the axis state carried in the K padding)
+// split into FP16 hi + lo (hi = rn(v), lo = rn(v - hi)) and laid out as the tensor core reads it.
+__global__ void k_pack_f16(int N, const double* __restrict__ M, const double* __restrict__ gpx,
+                           unsigned char* __restrict__ img) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kF16Tile * kF16Tile) return;
+    const int n = idx / kF16Tile, k = idx % kF16Tile;
+    double v = 0.0;
+    if (n < N && k < N) v = M[(size_t)n * N + k];
+    else if (n < N && k >= kF16StateSlot && k < kF16StateSlot + 3) {
+        const int c = k - kF16StateSlot;
+        for (int j = 0; j < N; ++j) v = fma(M[(size_t)n * N + j], gpx[j * 3 + c], v);
+    }
+    const __half hi = __double2half(v);
+    const __half lo = __double2half(v - (double)__half2float(hi));
+    const int off = f16_operand_offset(n, k, kF16Tile);
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + kF16OperandBytesB + off) = lo;
+}
+
 int invert_shifted(lipm_plan* plan, double diag, double* d_out) {
     const int N = plan->N;
     const size_t nn = (size_t)N * N;
@@ -250,6 +274,10 @@ int build_plan_matrices(lipm_plan* plan) {
     const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
     k_pack_fragments<<<(unsigned)((nfrag + 255) / 256), 256>>>(N, NP, plan->d_minv, plan->d_mfrag);
     k_gain<<<1, 256>>>(N, d.Q, plan->pu00, plan->d_hinv, plan->d_gpx, plan->d_px, plan->d_gain);
+    if (d.precision == LIPM_PRECISION_F16X3) {
+        LIPM_CUDA_TRY(cudaMalloc(&plan->d_bf16, 2 * kF16OperandBytesB));
+        k_pack_f16<<<(kF16Tile * kF16Tile + 255) / 256, 256>>>(N, plan->d_minv, plan->d_gpx, plan->d_bf16);
+    }
     LIPM_CUDA_TRY(cudaGetLastError());
     LIPM_CUDA_TRY(cudaDeviceSynchronize());
 

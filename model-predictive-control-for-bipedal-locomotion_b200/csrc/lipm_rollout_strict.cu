@@ -109,13 +109,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "memory");
 }
 
-constexpr int kGroupThreads = 32 * kRowGroups;   // 128: one warp per row group
 constexpr int kGroupCols = 8;                    // one DMMA column block
 
-// Named barriers: id 0 is __syncthreads; group g uses id 1 + g.
+// Named barriers: id 0 is __syncthreads; group g uses id 1 + g.  GT = threads of a solver group.
+template <int GT>
 __device__ __forceinline__ void group_sync(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroupThreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GT) : "memory");
 }
+template <int GT>
 __device__ __forceinline__ bool group_sync_and(int id, bool pred) {
     uint32_t out;
     asm volatile(
@@ -126,7 +127,7 @@ __device__ __forceinline__ bool group_sync_and(int id, bool pred) {
         "selp.u32 %0, 1, 0, q;\n"
         "}\n"
         : "=r"(out)
-        : "r"(id), "r"((uint32_t)pred), "n"(kGroupThreads)
+        : "r"(id), "r"((uint32_t)pred), "n"(GT)
         : "memory");
     return out != 0;
 }
@@ -147,24 +148,28 @@ __device__ __forceinline__ double clipd(double x, double lo, double hi) {
 // group barrier that publishes it.)
 // KBC > 0: compile-time trip count, fully unrolled (straight-line code keeps ptxas' warp
 // convergence check -- YIELD / WARPSYNC.ALL -- out of the inner loop); KBC == 0: run-time count.
-template <int NR, int NRB, int KBC>
+// STREAM: the matrix is not resident in shared memory (horizons beyond the resident limit); its
+// fragments are read straight from global memory (they stay in L2: one coalesced 256-byte line
+// per warp and fragment, read-only path).
+template <int NR, int NRB, int KBC, bool STREAM>
 __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aBase,
                                          const int aStride, const volatile double* bBase, const int KB_rt) {
     const int KB = KBC > 0 ? KBC : KB_rt;
     double a0[NR], a1[NR], b0, b1;
+    auto lda = [&](int off) -> double { return STREAM ? __ldg(aBase + off) : aBase[off]; };
     b0 = bBase[0];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride];
+    for (int r = 0; r < NR; ++r) a0[r] = lda(r * aStride);
     auto trip = [&](int kb) {
         b1 = bBase[(kb + 1) * 4];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a1[r] = aBase[r * aStride + (kb + 1) * 32];
+        for (int r = 0; r < NR; ++r) a1[r] = lda(r * aStride + (kb + 1) * 32);
 #pragma unroll
         for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a0[r], b0);
         if (kb + 2 < KB) {
             b0 = bBase[(kb + 2) * 4];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) a0[r] = aBase[r * aStride + (kb + 2) * 32];
+            for (int r = 0; r < NR; ++r) a0[r] = lda(r * aStride + (kb + 2) * 32);
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a1[r], b1);
@@ -177,20 +182,22 @@ __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aB
         for (int kb = 0; kb < KB; kb += 2) trip(kb);     // KB = NP/4 is even: NP is a multiple of 8
     }
 }
-template <int NR, int NRB, int KBC>
+template <int NR, int NRB, int KBC, bool STREAM>
 struct ContractDispatch {
     static __device__ __forceinline__ void run(int nrb, double (&acc)[NRB][2], const double* aBase, int aStride,
                                                const volatile double* bBase, int KB) {
-        if (nrb == NR) contract<NR, NRB, KBC>(acc, aBase, aStride, bBase, KB);
-        else ContractDispatch<NR - 1, NRB, KBC>::run(nrb, acc, aBase, aStride, bBase, KB);
+        if (nrb == NR) contract<NR, NRB, KBC, STREAM>(acc, aBase, aStride, bBase, KB);
+        else ContractDispatch<NR - 1, NRB, KBC, STREAM>::run(nrb, acc, aBase, aStride, bBase, KB);
     }
 };
-template <int NRB, int KBC>
-struct ContractDispatch<0, NRB, KBC> {
+template <int NRB, int KBC, bool STREAM>
+struct ContractDispatch<0, NRB, KBC, STREAM> {
     static __device__ __forceinline__ void run(int, double (&)[NRB][2], const double*, int, const volatile double*, int) {}
 };
 
 // Shared memory of one solver group, fixed-size part (compile-time offsets from the group base).
+// RG = warps of the group (each owns a contiguous range of row blocks).
+template <int RG>
 struct GroupFixed {
     double X[kGroupCols * 3];                 // current axis state
     double Imp[kGroupCols];                   // dt*F/m of the push
@@ -200,18 +207,22 @@ struct GroupFixed {
     double* Hist[kGroupCols];
     double* Zplan[kGroupCols];
     uint8_t* Flag[kGroupCols];
-    uint32_t Res[2][kRowGroups][kGroupCols];  // high words: residual partials; |q| partials
+    uint32_t Res[2][RG][kGroupCols];  // high words: residual partials; |q| partials
     int Nser[kGroupCols], Nticks[kGroupCols], Ftick[kGroupCols], Iter[kGroupCols], NotConv[kGroupCols];
     int Unit[2];                              // [0] unit index, [1] ticks of the longest column
 };
 
-// Layout: [ mbarrier | NG x GroupFixed | G Px | NG x R[8][KP] | M fragments ]
+// Layout: [ mbarrier | NG x GroupFixed | G Px | NG x R[8][KP] | M fragments (resident variants) ]
+template <int RG>
 __host__ __device__ inline size_t smem_fixed_bytes(int NG) {
-    return 16 + (size_t)NG * ((sizeof(GroupFixed) + 15) & ~(size_t)15);
+    return 16 + (size_t)NG * ((sizeof(GroupFixed<RG>) + 15) & ~(size_t)15);
 }
 
-template <int NRB, int NG, int NPC>
-__global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const StrictParams P) {
+// NRB row blocks per warp, NG solver groups per CTA, NPC compile-time padded horizon (0: run time),
+// RG warps per group, STREAM: matrix read from L2 instead of shared memory.
+template <int NRB, int NG, int NPC, int RG, bool STREAM>
+__global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const StrictParams P) {
+    constexpr int kGroupThreads = 32 * RG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     // Geometry: compile-time for the specialised horizons (NPC > 0), run-time otherwise.
@@ -222,19 +233,19 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int grp = warp >> 2;                    // solver group
+    const int grp = warp / RG;                    // solver group
     const int gtid = tid & (kGroupThreads - 1);   // thread index inside the group
-    const int rg = (warp + grp) & 3;              // row group (rotated per group)
+    const int rg = (warp + grp) & (RG - 1);       // row group (rotated per group)
     const int g = lane >> 2, t = lane & 3;
     const ColumnBatch& B = P.cb;
     const int bar_id = 1 + grp;
 
     unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem_raw);
-    constexpr size_t kFixedStride = (sizeof(GroupFixed) + 15) & ~(size_t)15;
-    GroupFixed& S = *reinterpret_cast<GroupFixed*>(smem_raw + 16 + grp * kFixedStride);
+    constexpr size_t kFixedStride = (sizeof(GroupFixed<RG>) + 15) & ~(size_t)15;
+    GroupFixed<RG>& S = *reinterpret_cast<GroupFixed<RG>*>(smem_raw + 16 + grp * kFixedStride);
     double* sGPx = reinterpret_cast<double*>(smem_raw + 16 + NG * kFixedStride);
     double* sR = sGPx + NP * 3 + grp * (kGroupCols * KP);     // this group's right-hand sides
-    double* sM = sGPx + NP * 3 + NG * (kGroupCols * KP);
+    const double* sM = STREAM ? P.mfrag : sGPx + NP * 3 + NG * (kGroupCols * KP);
 
     // ---- stationary operands: iteration matrix and G Px, bulk copies issued by one thread -------
     if (tid == 0) mbar_init(sBar, 1);
@@ -242,12 +253,14 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
     if (tid == 0) {
         const uint32_t m_bytes = (uint32_t)((size_t)RBLK * KB * 32 * sizeof(double));
         const uint32_t g_bytes = (uint32_t)(NP * 3 * sizeof(double));
-        mbar_expect_tx(sBar, m_bytes + g_bytes);
-        const uint32_t chunk = 32768;
-        for (uint32_t off = 0; off < m_bytes; off += chunk) {
-            const uint32_t n = (m_bytes - off < chunk) ? (m_bytes - off) : chunk;
-            bulk_load(reinterpret_cast<unsigned char*>(sM) + off,
-                      reinterpret_cast<const unsigned char*>(P.mfrag) + off, n, sBar);
+        mbar_expect_tx(sBar, (STREAM ? 0u : m_bytes) + g_bytes);
+        if (!STREAM) {
+            unsigned char* dstM = reinterpret_cast<unsigned char*>(sGPx + NP * 3 + NG * (kGroupCols * KP));
+            const uint32_t chunk = 32768;
+            for (uint32_t off = 0; off < m_bytes; off += chunk) {
+                const uint32_t n = (m_bytes - off < chunk) ? (m_bytes - off) : chunk;
+                bulk_load(dstM + off, reinterpret_cast<const unsigned char*>(P.mfrag) + off, n, sBar);
+            }
         }
         bulk_load(sGPx, P.gpx, g_bytes, sBar);
     }
@@ -273,12 +286,12 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
     for (;;) {
         // ---- fetch an 8-column unit (y-axis units, which iterate longer, are handed out first) --
-        group_sync(bar_id);
+        group_sync<kGroupThreads>(bar_id);
         if (gtid == 0) {
             S.Unit[0] = (int)atomicAdd(P.tile_counter, 1u);
             S.Unit[1] = 0;
         }
-        group_sync(bar_id);
+        group_sync<kGroupThreads>(bar_id);
         const unsigned int unit = (unsigned int)S.Unit[0];
         if (unit >= P.num_units) break;
         const int col0 = (int)(P.num_units - 1u - unit) * kGroupCols;
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
             S.Viol[gtid] = viol; S.Iter[gtid] = 0; S.NotConv[gtid] = 0;
             atomicMax(&S.Unit[1], ticks);
         }
-        group_sync(bar_id);
+        group_sync<kGroupThreads>(bar_id);
         const int max_ticks = S.Unit[1];
         unsigned int group_iters = 0;
 
@@ -366,7 +379,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 #pragma unroll
                         for (int e = 0; e < 2; ++e) rOut0[e * KP + r * 8] = tv[r][e];
                     }
-                group_sync(bar_id);
+                group_sync<kGroupThreads>(bar_id);
 #pragma unroll
                 for (int r = 0; r < NRB; ++r) {
                     const int j = row0 + r * 8;
@@ -379,7 +392,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                         }
                     }
                 }
-                group_sync(bar_id);
+                group_sync<kGroupThreads>(bar_id);
             }
 
             // ---- linear term, its magnitude (scale of the stop test) and first right-hand side ----
@@ -410,7 +423,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                 for (int o = 4; o <= 16; o <<= 1) qmag[e] = max(qmag[e], __shfl_xor_sync(0xffffffffu, qmag[e], o));
                 if (g == 0) S.Res[1][rg][lc0 + e] = qmag[e];
             }
-            group_sync(bar_id);
+            group_sync<kGroupThreads>(bar_id);
             // Stop threshold of my two columns (as a high word).  The test uses d = |v - z_old|: the
             // primal residual |v - z_new| <= (1 + alpha) d and the dual one rho |z_new - z_old| <= rho alpha d,
             // so d <= eps * max(1, |q|_inf) / max(1 + alpha, rho alpha) bounds both by eps * max(1, |q|_inf).
@@ -419,7 +432,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
             for (int e = 0; e < 2; ++e) {
                 uint32_t m = S.Res[1][0][lc0 + e];
 #pragma unroll
-                for (int q4 = 1; q4 < kRowGroups; ++q4) m = max(m, S.Res[1][q4][lc0 + e]);
+                for (int q4 = 1; q4 < RG; ++q4) m = max(m, S.Res[1][q4][lc0 + e]);
                 const double scale = fmax(1.0, __hiloint2double((int)m, 0));
                 thr[e] = mag_hi(P.eps * scale * P.stop_factor);
             }
@@ -434,7 +447,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
 
                 long long tc0 = 0;
                 if (P.debug_skip & 16) tc0 = clock64();
-                if (!(P.debug_skip & 1)) ContractDispatch<NRB, NRB, NPC / 4>::run(nrb, acc, aBase, aStride, bBase, KB);
+                if (!(P.debug_skip & 1)) ContractDispatch<NRB, NRB, NPC / 4, STREAM>::run(nrb, acc, aBase, aStride, bBase, KB);
                 if ((P.debug_skip & 16) && tid == 0) {
                     // wait for the accumulators, then charge the elapsed cycles to the contraction
                     double sink = 0.0;
@@ -469,7 +482,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                     for (int o = 4; o <= 16; o <<= 1) rd[e] = max(rd[e], __shfl_xor_sync(0xffffffffu, rd[e], o));
                     if (g == 0) S.Res[0][rg][lc0 + e] = rd[e];
                 }
-                if (!(P.debug_skip & 4)) group_sync(bar_id);   // every warp of the group has consumed R; partials are visible
+                if (!(P.debug_skip & 4)) group_sync<kGroupThreads>(bar_id);   // every warp of the group has consumed R; partials are visible
 
                 bool all_mine = true;
 #pragma unroll
@@ -480,14 +493,14 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                             if (r < nrb) rOut0[e * KP + r * 8] = acc[r][e];
                         uint32_t cd = S.Res[0][0][lc0 + e];
 #pragma unroll
-                        for (int q4 = 1; q4 < kRowGroups; ++q4) cd = max(cd, S.Res[0][q4][lc0 + e]);
+                        for (int q4 = 1; q4 < RG; ++q4) cd = max(cd, S.Res[0][q4][lc0 + e]);
                         ++iters[e];
                         done[e] = (cd <= thr[e]) && !(P.debug_skip & 8);
                     }
                     all_mine = all_mine && done[e];
                 }
                 ++group_iters;
-                const bool stop = group_sync_and(bar_id, all_mine);   // new R visible; partials consumed
+                const bool stop = group_sync_and<kGroupThreads>(bar_id, all_mine);   // new R visible; partials consumed
                 if ((P.debug_skip & 16) && tid == 0) atomicAdd(P.stats + 3, (unsigned long long)(clock64() - tc0));
                 if (stop) break;
             }
@@ -539,7 +552,7 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
                     }
                 }
             }
-            group_sync(bar_id);
+            group_sync<kGroupThreads>(bar_id);
         }
 
         // ---- per-column summaries -----------------------------------------------------------------
@@ -561,16 +574,17 @@ __global__ void __launch_bounds__(kGroupThreads * NG, 1) k_strict_rollout(const 
     }
 }
 
+template <int RG, bool STREAM>
 size_t strict_smem_bytes(int NG, int NP) {
-    const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
-    return smem_fixed_bytes(NG) +
+    const size_t nfrag = STREAM ? 0 : (size_t)(NP / 8) * (NP / 4) * 32;
+    return smem_fixed_bytes<RG>(NG) +
            sizeof(double) * ((size_t)NP * 3 + (size_t)NG * kGroupCols * column_pitch(NP) + nfrag);
 }
 
-template <int NRB, int NG, int NPC>
+template <int NRB, int NG, int NPC, int RG = kRowGroups, bool STREAM = false>
 int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) {
-    const size_t smem = strict_smem_bytes(NG, plan->NP);
-    auto kernel = k_strict_rollout<NRB, NG, NPC>;
+    const size_t smem = strict_smem_bytes<RG, STREAM>(NG, plan->NP);
+    auto kernel = k_strict_rollout<NRB, NG, NPC, RG, STREAM>;
     LIPM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StrictParams Q = P;
     Q.active_groups = NG;
@@ -586,7 +600,7 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
     const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), stream));
-    kernel<<<grid, kGroupThreads * NG, smem, stream>>>(Q);
+    kernel<<<grid, 32 * RG * NG, smem, stream>>>(Q);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;
 }
@@ -596,7 +610,7 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
     const lipm_plan_desc_t& d = plan->desc;
     if (plan->N > kMaxStrictHorizon) {
-        set_error("strict mode: horizon %d exceeds the resident-matrix kernel's limit %d in this build",
+        set_error("strict mode: horizon %d exceeds this build's limit %d",
                   plan->N, kMaxStrictHorizon);
         return LIPM_E_UNSUPPORTED;
     }
@@ -618,15 +632,33 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
     P.num_units = 0;
     P.nfrag = (size_t)(plan->NP / 8) * (plan->NP / 4) * 32;
 
-    const int nrb = (P.RBLK + kRowGroups - 1) / kRowGroups;
     if (plan->NP == 152) return launch_variant<5, 3, 152>(plan, P, stream);   // N = 145..152 (default 150)
-    switch (nrb) {
-        case 1: return launch_variant<1, 4, 0>(plan, P, stream);
-        case 2: return launch_variant<2, 4, 0>(plan, P, stream);
-        case 3: return launch_variant<3, 4, 0>(plan, P, stream);
-        case 4: return launch_variant<4, 3, 0>(plan, P, stream);
-        case 5: return launch_variant<5, 3, 0>(plan, P, stream);
-        default: break;
+    if (plan->N <= kMaxResidentHorizon) {
+        // resident matrix, 4 warps per solver group
+        switch ((P.RBLK + kRowGroups - 1) / kRowGroups) {
+            case 1: return launch_variant<1, 4, 0>(plan, P, stream);
+            case 2: return launch_variant<2, 4, 0>(plan, P, stream);
+            case 3: return launch_variant<3, 4, 0>(plan, P, stream);
+            case 4: return launch_variant<4, 3, 0>(plan, P, stream);
+            case 5: return launch_variant<5, 3, 0>(plan, P, stream);
+            default: break;
+        }
+    } else if (P.RBLK <= 8 * 5) {
+        // N = 161..320: matrix streamed from L2, 8 warps per group
+        switch ((P.RBLK + 7) / 8) {
+            case 3: return launch_variant<3, 2, 0, 8, true>(plan, P, stream);
+            case 4: return launch_variant<4, 1, 0, 8, true>(plan, P, stream);
+            case 5: return launch_variant<5, 1, 0, 8, true>(plan, P, stream);
+            default: break;
+        }
+    } else {
+        // N = 321..640: matrix streamed from L2, 16 warps per group
+        switch ((P.RBLK + 15) / 16) {
+            case 3: return launch_variant<3, 1, 0, 16, true>(plan, P, stream);
+            case 4: return launch_variant<4, 1, 0, 16, true>(plan, P, stream);
+            case 5: return launch_variant<5, 1, 0, 16, true>(plan, P, stream);
+            default: break;
+        }
     }
     set_error("strict mode: no kernel variant for %d row blocks", P.RBLK);
     return LIPM_E_UNSUPPORTED;

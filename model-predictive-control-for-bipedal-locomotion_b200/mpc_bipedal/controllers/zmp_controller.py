@@ -111,7 +111,7 @@ class ZMPController:
             "iters": out["iters"],
         }
         if to_numpy:
-            res = {k: v.cpu().numpy() for k, v in res.items()}
+            res = engine.to_host(res)
         return res
 
     # ------------------------------------------------------------------ single walk (reference :59-147)
