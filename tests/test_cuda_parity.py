@@ -449,3 +449,37 @@ def test_reduced_ragged_and_limits(engine, plan150_f16):
     # the unconstrained mode of a reduced-precision plan is the same FP64 gain-row kernel
     a = plan150_f16.rollout(engine.MODE_UNCONSTRAINED, zero, zero, z_min[:70], z_max[:70])
     assert np.isfinite(a["y_hist"].cpu().numpy()).all()
+
+
+# ----------------------------------------------------------------------------- parameter sweep (BASELINE config 5)
+def test_param_sweep_matches_individual_walks(engine, default_config):
+    """Each scenario of a (h, m, step_length, foot_spread, F_ext) sweep equals the same walk run alone
+    through the mirrored reference API with that scenario's own MPCConfig."""
+    from dataclasses import replace
+
+    import torch
+
+    from mpc_bipedal import parallel, sweeps
+    from mpc_bipedal.controllers import ZMPController
+    from mpc_bipedal.generators import CoPGenerator
+
+    cfg = replace(default_config, distance=0.9, standing_duration=0.4)
+    table = sweeps.make_sweep(96, seed=5, h_values=(0.62, 0.8), step_lengths=(0.25, 0.35), foot_spreads=(0.09,))
+    parts = [sweeps.run_shard(cfg, table, rank, 3) for rank in range(3)]          # three shards on one GPU
+    record = torch.cat([p["record"] for p in parts], dim=0)
+    whole = sweeps.run_shard(cfg, table, 0, 1)
+    assert torch.equal(record, whole["record"])                                   # sharding does not change a bit
+    assert sum(p["solves"] for p in parts) == whole["solves"]
+    out = parallel.unpack_outcomes(whole["record"].cpu())
+    assert (out["status"] == 0).all() and out["max_violation"].max().item() < 1e-9
+    bounds = sweeps.variant_bounds(cfg, table.variants)
+    for k in (0, 40, 95):
+        step_length, foot_spread = table.variants[table.variant[k]]
+        one = replace(cfg, h=float(table.h_values[table.h_index[k]]), m=float(table.mass[k]), F_ext=float(table.F_ext[k]),
+                      step_length=step_length, foot_spread=foot_spread, add_force=True, strict=True)
+        z_max, z_min, _ = CoPGenerator(one).generate_cop_trajectory(save_footsteps=False)
+        tick = sweeps.push_ticks(table, bounds, k, k + 1, int(table.variant[k]))
+        res = ZMPController(one).generate_com_trajectory_batched(np.zeros((1, 3)), np.zeros((1, 3)), z_max, z_min,
+                                                                 F_ext=[one.F_ext], m=[one.m], force_tick=tick)
+        assert int(res["iters"].sum()) == int(out["iters"][k])                    # same solves, iteration for iteration
+        assert bool(res["fell"][0]) == bool(out["fell"][k])

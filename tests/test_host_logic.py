@@ -109,3 +109,34 @@ def test_classic_speed_reference(golden):
     cfg.speed_generation = "bogus"
     with pytest.raises(ValueError, match="Unknown speed_generation"):
         SpeedTrajectoryGenerator(cfg).generate_speed_and_state(save_footsteps=False)
+
+
+# ----------------------------------------------------------------------------- parameter sweeps (config 5)
+def test_sweep_table_groups_and_shards(default_config):
+    from mpc_bipedal import sweeps
+    from mpc_bipedal.parallel import shard_range
+
+    table = sweeps.make_sweep(1000, seed=3)
+    assert len(table) == 1000 and len(table.variants) == 15 and len(table.h_values) == 8
+    key = table.h_index.astype(np.int64) * 100 + table.variant
+    assert (np.diff(key) >= 0).all()                                  # sorted by (h, variant)
+    assert sorted(table.scenario_id.tolist()) == list(range(1000))    # a permutation of the caller's order
+    for world in (1, 2, 8):
+        covered = []
+        for rank in range(world):
+            lo, hi = shard_range(1000, rank, world)
+            runs = sweeps.groups_of_shard(table, rank, world)
+            assert runs[0][2] == lo and runs[-1][3] == hi
+            for (h_idx, var, a, b), nxt in zip(runs, runs[1:] + [None]):
+                assert a < b and (table.h_index[a:b] == h_idx).all() and (table.variant[a:b] == var).all()
+                if nxt is not None:
+                    assert nxt[2] == b and (nxt[0], nxt[1]) != (h_idx, var)
+            covered.extend(range(lo, hi))
+            # "few plans per rank": a contiguous shard of the sorted table touches at most ceil(8/world)+1 heights
+            assert len({r[0] for r in runs}) <= -(-8 // world) + 1
+        assert covered == list(range(1000))
+    bounds = sweeps.variant_bounds(default_config, table.variants[:3])
+    for var, (z_max, z_min, first, last, n) in enumerate(bounds):
+        assert z_max.shape == (n, 2) and (z_max >= z_min).all() and 0 < first < last < n
+        tick = sweeps.push_ticks(table, bounds, 0, 50, var)
+        assert tick.dtype == np.int32 and (tick >= first).all() and (tick <= last).all()

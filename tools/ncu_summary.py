@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Summarise one kernel of an .ncu-rep (raw page) into the handful of metrics the design cites.
-Usage: python tools/ncu_summary.py REPORT.ncu-rep [kernel-substring] > profiles/xxx.json"""
+Usage: python tools/ncu_summary.py REPORT.ncu-rep [kernel-substring [scenarios-per-gpu]] > profiles/xxx.json"""
 import csv, json, subprocess, sys
 rep = sys.argv[1]
 want = sys.argv[2] if len(sys.argv) > 2 else ""
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -23,11 +24,15 @@ for r in rows[2:]:
     if want not in d.get("Kernel Name", ""):
         continue
     rec = {"kernel": d["Kernel Name"][:120]}
+    if batch is not None:
+        rec["scenarios_per_gpu"] = batch
     for k, u in zip(hdr, units):
         if k in KEYS or k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio") or "tensor" in k and "pct" in k and ".avg." in k:
             try:
-                rec[k + (f" [{u}]" if u else "")] = float(d[k].replace(",", ""))
+                value = float(d[k].replace(",", ""))
+                rec[k + (f" [{u}]" if u else "")] = value if value == value else None
             except ValueError:
                 rec[k] = d[k]
-    out.append(rec)
+    if rec.get("gpu__time_duration.sum [ms]") is not None and not any(v is None for v in rec.values()):
+        out.append(rec)
 json.dump(out, sys.stdout, indent=1)
