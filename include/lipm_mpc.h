@@ -71,7 +71,7 @@ typedef struct lipm_plan_desc {
     double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.6)                        */
     double eps;        /* ADMM stop: primal and rho*dual residual <= eps * max(1, |q|_inf)  (<=0 -> 1e-12;
                           F16X3: <=0 -> 1e-5, floor 5e-7)                                   */
-    int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000)                           */
+    int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000; F16X3: 500)                */
     double viol_tol;   /* box-violation tolerance for LIPM_FLAG_VIOL_* (<0 -> 1e-9)         */
     int32_t device;    /* CUDA device ordinal                                               */
     int32_t precision; /* LIPM_PRECISION_* of the strict mode (eps default 1e-5 for F16X3)          */
@@ -109,7 +109,10 @@ int lipm_plan_export(const lipm_plan_t* plan, int which, double* host_out, size_
  *   x_hist,y_hist dev [B,n_max,3] state histories; sample 0 is the initial state
  *   flags        dev uint8 [B,n_max,2]
  *   max_violation dev [B,2]      per axis: max over samples of max(z_min - zmp, zmp - z_max, 0)
- *   status       dev int32 [B,2] per axis: number of ticks whose QP hit max_iter (0 = all converged)
+ *   status       dev int32 [B,2] per axis: 1 if a QP hit max_iter (0 = all converged).  Like the reference,
+ *                                which raises at the first QP without a solution (:193-194), the walk of
+ *                                that axis stops at that sample (flagged NOT_CONVERGED); later samples
+ *                                are left untouched
  *   iters        dev int32 [B,2] per axis: ADMM iterations executed, summed over ticks
  */
 int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n_steps,
@@ -117,6 +120,18 @@ int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n
                  int bounds_batch, const double* impulse, const int32_t* force_tick,
                  double* x_hist, double* y_hist, uint8_t* flags, double* max_violation,
                  int32_t* status, int32_t* iters, void* stream);
+
+/*
+ * Same as lipm_rollout, with a TABLE of bound series and one index per scenario: z_min / z_max are
+ * dev [V, n_max, 2] (V = bounds_batch series) and bounds_index is dev int32 [B] with values in [0, V).
+ * Parameter sweeps use it to run scenarios with different footstep plans (step length, foot spread --
+ * generators/footstep_generator.py:19-49) in one launch; n_steps gives each scenario its series' length.
+ */
+int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n_steps,
+                         const double* x0, const double* y0, const double* z_min, const double* z_max,
+                         int bounds_batch, const int32_t* bounds_index, const double* impulse,
+                         const int32_t* force_tick, double* x_hist, double* y_hist, uint8_t* flags,
+                         double* max_violation, int32_t* status, int32_t* iters, void* stream);
 
 /*
  * One control tick for a batch of independent axis problems: replaces

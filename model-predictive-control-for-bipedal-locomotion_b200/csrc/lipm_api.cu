@@ -77,6 +77,7 @@ int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
             return LIPM_E_UNSUPPORTED;
         }
         if (!(d.eps > 0)) d.eps = 1e-5;
+        if (d.max_iter <= 0) d.max_iter = 500;   // ~8 iterations per solve on average; a column that needs more has diverged
         if (d.eps < 5e-7) d.eps = 5e-7;     // FP32 iterates: below this the stop test sits in the rounding noise
     }
     if (!(d.eps > 0)) d.eps = 1e-12;
@@ -161,12 +162,22 @@ int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n
                  const double* y0, const double* z_min, const double* z_max, int bounds_batch,
                  const double* impulse, const int32_t* force_tick, double* x_hist, double* y_hist,
                  uint8_t* flags, double* max_violation, int32_t* status, int32_t* iters, void* stream) {
+    return lipm_rollout_indexed(plan, mode, B, n_max, n_steps, x0, y0, z_min, z_max, bounds_batch, nullptr, impulse,
+                                force_tick, x_hist, y_hist, flags, max_violation, status, iters, stream);
+}
+
+int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n_steps, const double* x0,
+                         const double* y0, const double* z_min, const double* z_max, int bounds_batch,
+                         const int32_t* bounds_index, const double* impulse, const int32_t* force_tick,
+                         double* x_hist, double* y_hist, uint8_t* flags, double* max_violation, int32_t* status,
+                         int32_t* iters, void* stream) {
     if (!plan) { set_error("lipm_rollout: null plan"); return LIPM_E_INVALID; }
     if (mode != LIPM_MODE_STRICT && mode != LIPM_MODE_UNCONSTRAINED) { set_error("lipm_rollout: bad mode %d", mode); return LIPM_E_INVALID; }
     if (B < 0 || n_max < 2) { set_error("lipm_rollout: need B >= 0 and n_max >= 2 (got %d, %d)", B, n_max); return LIPM_E_INVALID; }
     if (B == 0) return LIPM_OK;
     if (!x0 || !y0 || !z_min || !z_max) { set_error("lipm_rollout: x0, y0, z_min, z_max are required"); return LIPM_E_INVALID; }
-    if (bounds_batch != 1 && bounds_batch != B) { set_error("lipm_rollout: bounds_batch must be 1 or B (got %d, B=%d)", bounds_batch, B); return LIPM_E_INVALID; }
+    if (!bounds_index && bounds_batch != 1 && bounds_batch != B) { set_error("lipm_rollout: bounds_batch must be 1 or B (got %d, B=%d)", bounds_batch, B); return LIPM_E_INVALID; }
+    if (bounds_index && bounds_batch < 1) { set_error("lipm_rollout_indexed: bounds_batch must be the number of series (got %d)", bounds_batch); return LIPM_E_INVALID; }
     if ((long long)B * 2 > 0x7fffffffLL / 8) { set_error("lipm_rollout: batch too large"); return LIPM_E_INVALID; }
     DeviceGuard guard(plan->desc.device);
 
@@ -175,6 +186,7 @@ int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n
     cb.ncols = 2 * B;
     cb.B = B;
     cb.bounds_batch = bounds_batch;
+    cb.bounds_index = bounds_index;
     cb.bound_scn_stride = (long long)n_max * 2;
     cb.bound_stride = 2;
     cb.bound_axis_offset = 1;

@@ -88,7 +88,8 @@ struct ColumnBatch {
     int ncols;              // number of columns (2B for walks, B for single ticks)
     int B;                  // scenarios; column c -> slot c % B, axis c / B
     const int* order;       // [B] scenario processed in each slot (nullptr: identity)
-    int bounds_batch;       // 1 (shared) or B
+    int bounds_batch;       // 1 (shared), B (one series per scenario) or V (with bounds_index)
+    const int32_t* bounds_index;  // [B] series used by each scenario, or nullptr
     long long bound_scn_stride;   // doubles between consecutive scenarios' bound series
     int bound_stride;       // doubles between consecutive samples of one axis (2 walks, 1 ticks)
     int bound_axis_offset;  // doubles between the x and the y series (1 for walks)

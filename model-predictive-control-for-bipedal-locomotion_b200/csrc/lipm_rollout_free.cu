@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
     n = n > B.n_max ? B.n_max : n;
     int ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
     if (n < 1 || ticks < 0) ticks = 0;
-    const long long bz = (B.bounds_batch == 1) ? 0 : b;
+    const long long bz = B.bounds_index ? B.bounds_index[b] : ((B.bounds_batch == 1) ? 0 : b);
     const double* plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
     const double* phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
     double* hist = axis ? B.hist[1] : B.hist[0];

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
             n = n > B.n_max ? B.n_max : n;
             int ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
             if (!valid || n < 1 || ticks < 0) ticks = 0;
-            const long long bz = (B.bounds_batch == 1) ? 0 : b;
+            const long long bz = B.bounds_index ? B.bounds_index[b] : ((B.bounds_batch == 1) ? 0 : b);
             const double* plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
             const double* phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
             double* ph = axis ? B.hist[1] : B.hist[0];
@@ -526,7 +526,13 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                                  (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u);
                     if (P.strict_flags)
                         f |= (z0 == l0 ? LIPM_FLAG_ACTIVE_LO : 0u) | (z0 == h0 ? LIPM_FLAG_ACTIVE_HI : 0u);
-                    if (!done[e]) { f |= LIPM_FLAG_NOT_CONVERGED; S.NotConv[lc] += 1; }
+                    if (!done[e]) {
+                        // the reference raises at the first QP without a solution (zmp_controller.py:193-194):
+                        // the walk of this column ends here
+                        f |= LIPM_FLAG_NOT_CONVERGED;
+                        S.NotConv[lc] += 1;
+                        S.Nticks[lc] = i + 1;
+                    }
                     if (i == S.Ftick[lc]) n1 -= S.Imp[lc];
                     const long long sample = i + 1;
                     double* ph = S.Hist[lc];

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
         int nticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
         if (!valid || n < 1 || nticks < 0) nticks = 0;
         const int last = n - 1;
-        const long long bz = (B.bounds_batch == 1) ? 0 : b;
+        const long long bz = B.bounds_index ? B.bounds_index[b] : ((B.bounds_batch == 1) ? 0 : b);
         const double* plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
         const double* phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
         double* ph = nullptr;
@@ -508,6 +508,9 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                 S.X[s][0] = n0; S.X[s][1] = n1; S.X[s][2] = n2;
                 iter_sum += iters;
             }
+            // the reference raises at the first QP without a solution (zmp_controller.py:193-194): the walk of
+            // this column ends here (every part of the column reaches the same verdict from the same residuals)
+            if (live && !done) nticks = i + 1;
             tc_fence_before();
             __syncthreads();              // the new state is visible to every part
             tc_fence_after();

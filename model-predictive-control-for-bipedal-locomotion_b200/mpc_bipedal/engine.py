@@ -34,7 +34,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBRARY_PATH = os.path.join(_PKG_ROOT, "_lib", "liblipm_mpc.so")
 
 EXPORTED_SYMBOLS = (
-    "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout",
+    "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout", "lipm_rollout_indexed",
     "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
     "lipm_max_reduced_horizon",
 )
@@ -84,6 +84,8 @@ def load_library() -> ctypes.CDLL:
     lib.lipm_plan_export.restype = i32
     lib.lipm_rollout.argtypes = [vp, i32, i32, i32] + [vp] * 5 + [i32] + [vp] * 9
     lib.lipm_rollout.restype = i32
+    lib.lipm_rollout_indexed.argtypes = [vp, i32, i32, i32] + [vp] * 5 + [i32] + [vp] * 10
+    lib.lipm_rollout_indexed.restype = i32
     lib.lipm_solve_tick.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.lipm_solve_tick.restype = i32
     lib.lipm_plan_stats.argtypes = [vp, vp]
@@ -185,12 +187,14 @@ class LipmPlan:
 
     # ------------------------------------------------------------------ walks
     def rollout(self, mode: int, x0, y0, z_min, z_max, *, n_steps=None, impulse=None, force_tick=None,
-                want_flags: bool = True, want_iters: bool = True,
+                bounds_index=None, want_flags: bool = True, want_iters: bool = True, want_hist: bool = True,
                 out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Batched walks (``lipm_rollout``).  Inputs may be host or device arrays.
 
         x0, y0: (B,3); z_min, z_max: (n,2) shared or (B,n,2); n_steps: (B,) int32 or None;
         impulse: (B,) = dt*F_ext/m or None; force_tick: (B,) int32 or None.
+        bounds_index: (B,) int32 -> z_min, z_max are a table (V,n,2) of series and scenario b uses
+        series bounds_index[b] (``lipm_rollout_indexed``).
         Returns device tensors x_hist, y_hist (B,n,3), flags (B,n,2) uint8,
         max_violation (B,2), status (B,2) int32, iters (B,2) int32.
         """
@@ -205,7 +209,12 @@ class LipmPlan:
         if z_min.shape != z_max.shape or z_min.shape[-1] != 2 or z_min.ndim not in (2, 3):
             raise ValueError("z_min and z_max must both have shape (n, 2) or (B, n, 2)")
         bounds_batch = 1 if z_min.ndim == 2 else z_min.shape[0]
-        if bounds_batch not in (1, B):
+        index_t = None
+        if bounds_index is not None:
+            if z_min.ndim != 3:
+                raise ValueError("bounds_index needs a (V, n, 2) table of bound series")
+            index_t = _dev_tensor(bounds_index, torch.int32, dev, (B,))
+        elif bounds_batch not in (1, B):
             raise ValueError("bounds batch must be 1 or B")
         n_max = z_min.shape[-2]
         n_steps_t = None if n_steps is None else _dev_tensor(n_steps, torch.int32, dev, (B,))
@@ -219,19 +228,19 @@ class LipmPlan:
                 t = torch.zeros(shape, dtype=dtype, device=dev)
                 out[name] = t
             return t
-        x_hist = buf("x_hist", (B, n_max, 3), torch.float64)
-        y_hist = buf("y_hist", (B, n_max, 3), torch.float64)
+        x_hist = buf("x_hist", (B, n_max, 3), torch.float64) if want_hist else None
+        y_hist = buf("y_hist", (B, n_max, 3), torch.float64) if want_hist else None
         flags = buf("flags", (B, n_max, 2), torch.uint8) if want_flags else None
         viol = buf("max_violation", (B, 2), torch.float64)
         status = buf("status", (B, 2), torch.int32)
         iters = buf("iters", (B, 2), torch.int32) if want_iters else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _check(self._lib.lipm_rollout(
+        _check(self._lib.lipm_rollout_indexed(
             self._handle, mode, B, n_max, _ptr(n_steps_t), _ptr(x0), _ptr(y0), _ptr(z_min), _ptr(z_max),
-            bounds_batch, _ptr(impulse_t), _ptr(force_t), _ptr(x_hist), _ptr(y_hist), _ptr(flags),
+            bounds_batch, _ptr(index_t), _ptr(impulse_t), _ptr(force_t), _ptr(x_hist), _ptr(y_hist), _ptr(flags),
             _ptr(viol), _ptr(status), _ptr(iters), stream))
         # keep inputs alive until the stream has consumed them
-        out["_keepalive"] = (x0, y0, z_min, z_max, n_steps_t, impulse_t, force_t)
+        out["_keepalive"] = (x0, y0, z_min, z_max, n_steps_t, impulse_t, force_t, index_t)
         return out
 
     # ------------------------------------------------------------------ single ticks

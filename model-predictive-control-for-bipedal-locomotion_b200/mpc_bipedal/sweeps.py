@@ -10,7 +10,8 @@ as a Python loop over `MPCConfig`s is organised here for the batched engine:
 * m and F_ext enter only through the impulse dt * F_ext / m (`:106`).
 
 Scenarios are sorted by (h, bounds variant), split into contiguous balanced shards (one per GPU), and
-each shard is run group by group -- one `lipm_rollout` per (h, variant) group with shared bounds.
+each shard is run bucket by bucket -- one `lipm_rollout_indexed` per CoM height, the bound series picked
+per scenario from the table of variants.
 The only thing that leaves a rank is the packed per-scenario outcome record.
 """
 
@@ -73,27 +74,41 @@ def variant_bounds(config: MPCConfig, variants: Sequence[Tuple[float, float]]):
     return out
 
 
-def groups_of_shard(table: SweepTable, rank: int, world: int) -> List[Tuple[int, int, int, int]]:
-    """(h_index, variant, lo, hi) runs of identical (h, variant) inside this rank's contiguous shard."""
+def groups_of_shard(table: SweepTable, rank: int, world: int) -> List[Tuple[int, int, int]]:
+    """(h_index, lo, hi) runs of identical h inside this rank's contiguous shard: one plan and one launch
+    each (the bound series of a run's scenarios are selected per scenario from the table of variants)."""
     lo, hi = shard_range(len(table), rank, world)
     runs = []
     start = lo
     while start < hi:
-        key = (int(table.h_index[start]), int(table.variant[start]))
+        key = int(table.h_index[start])
         stop = start + 1
-        while stop < hi and (int(table.h_index[stop]), int(table.variant[stop])) == key:
+        while stop < hi and int(table.h_index[stop]) == key:
             stop += 1
-        runs.append((key[0], key[1], start, stop))
+        runs.append((key, start, stop))
         start = stop
     return runs
 
 
-def push_ticks(table: SweepTable, bounds, lo: int, hi: int, variant: int) -> np.ndarray:
-    """Push tick inside the walking phase of the variant's timeline."""
-    _, _, first, last, n = bounds[variant]
-    span = max(last - first, 1)
-    tick = first + np.floor(table.tick_fraction[lo:hi] * span).astype(np.int32)
+def push_ticks(table: SweepTable, bounds, lo: int, hi: int) -> np.ndarray:
+    """Push tick inside the walking phase of each scenario's own timeline."""
+    first = np.array([bd[2] for bd in bounds])[table.variant[lo:hi]]
+    last = np.array([bd[3] for bd in bounds])[table.variant[lo:hi]]
+    n = np.array([bd[4] for bd in bounds])[table.variant[lo:hi]]
+    span = np.maximum(last - first, 1)
+    tick = first + np.floor(table.tick_fraction[lo:hi] * span).astype(np.int64)
     return np.clip(tick, 0, n - 2).astype(np.int32)
+
+
+def bounds_table(bounds) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Stack the variants' series into (V, n_max, 2) tables (rows past a series' end are never read:
+    the engine repeats the LAST VALID row of each series, `zmp_controller.py:81-88`) + lengths (V,)."""
+    n_max = max(bd[4] for bd in bounds)
+    z_max = np.zeros((len(bounds), n_max, 2))
+    z_min = np.zeros((len(bounds), n_max, 2))
+    for v, (hi_series, lo_series, _, _, n) in enumerate(bounds):
+        z_max[v, :n], z_min[v, :n] = hi_series, lo_series
+    return z_max, z_min, np.array([bd[4] for bd in bounds], np.int32)
 
 
 def run_shard(config: MPCConfig, table: SweepTable, rank: int = 0, world: int = 1, *, strict: bool = True,
@@ -106,28 +121,25 @@ def run_shard(config: MPCConfig, table: SweepTable, rank: int = 0, world: int = 
     from .parallel import pack_outcomes
 
     bounds = variant_bounds(config, table.variants)
+    z_max_t, z_min_t, lengths = bounds_table(bounds)
     lo_all, hi_all = shard_range(len(table), rank, world)
     device = torch.device("cuda", torch.cuda.current_device())
+    z_max_d, z_min_d = torch.as_tensor(z_max_t).to(device), torch.as_tensor(z_min_t).to(device)
     record = torch.zeros((hi_all - lo_all, 4), dtype=torch.float64, device=device)
     solves = 0
     mode = engine.MODE_STRICT if strict else engine.MODE_UNCONSTRAINED
-    dev_bounds = {}
-    for h_idx, var, lo, hi in groups_of_shard(table, rank, world):
+    for h_idx, lo, hi in groups_of_shard(table, rank, world):
         h = float(table.h_values[h_idx])
         plan = engine.get_plan(config.horizon, h, config.g, config.dt, config.Q, config.R, precision=precision)
-        if var not in dev_bounds:
-            z_max, z_min, _, _, _ = bounds[var]
-            dev_bounds[var] = (torch.as_tensor(z_min).to(device), torch.as_tensor(z_max).to(device))
-        z_min_d, z_max_d = dev_bounds[var]
-        n = z_min_d.shape[0]
         count = hi - lo
         zero = torch.zeros((count, 3), dtype=torch.float64, device=device)
         impulse = config.dt * table.F_ext[lo:hi] / table.mass[lo:hi]
-        out = plan.rollout(mode, zero, zero, z_min_d, z_max_d, impulse=impulse,
-                           force_tick=push_ticks(table, bounds, lo, hi, var), want_flags=False)
+        n_steps = lengths[table.variant[lo:hi]]
+        out = plan.rollout(mode, zero, zero, z_min_d, z_max_d, n_steps=n_steps, bounds_index=table.variant[lo:hi],
+                           impulse=impulse, force_tick=push_ticks(table, bounds, lo, hi), want_flags=False)
         lean = (h / config.g) * out["y_hist"][..., 2].abs().amax(dim=1)     # |CoM - ZMP| = (h/g) |acceleration|
         lean = torch.maximum(lean, (h / config.g) * out["x_hist"][..., 2].abs().amax(dim=1))
         fell = lean > h * float(np.tan(np.radians(fall_angle_deg)))
         record[lo - lo_all:hi - lo_all] = pack_outcomes(out["max_violation"], out["status"], out["iters"], fell)
-        solves += count * 2 * (n - 1)
+        solves += int((2 * (n_steps.astype(np.int64) - 1)).sum())
     return {"record": record, "solves": solves, "range": (lo_all, hi_all)}

@@ -478,7 +478,7 @@ def test_param_sweep_matches_individual_walks(engine, default_config):
         one = replace(cfg, h=float(table.h_values[table.h_index[k]]), m=float(table.mass[k]), F_ext=float(table.F_ext[k]),
                       step_length=step_length, foot_spread=foot_spread, add_force=True, strict=True)
         z_max, z_min, _ = CoPGenerator(one).generate_cop_trajectory(save_footsteps=False)
-        tick = sweeps.push_ticks(table, bounds, k, k + 1, int(table.variant[k]))
+        tick = sweeps.push_ticks(table, bounds, k, k + 1)
         res = ZMPController(one).generate_com_trajectory_batched(np.zeros((1, 3)), np.zeros((1, 3)), z_max, z_min,
                                                                  F_ext=[one.F_ext], m=[one.m], force_tick=tick)
         assert int(res["iters"].sum()) == int(out["iters"][k])                    # same solves, iteration for iteration

@@ -126,17 +126,21 @@ def test_sweep_table_groups_and_shards(default_config):
         for rank in range(world):
             lo, hi = shard_range(1000, rank, world)
             runs = sweeps.groups_of_shard(table, rank, world)
-            assert runs[0][2] == lo and runs[-1][3] == hi
-            for (h_idx, var, a, b), nxt in zip(runs, runs[1:] + [None]):
-                assert a < b and (table.h_index[a:b] == h_idx).all() and (table.variant[a:b] == var).all()
+            assert runs[0][1] == lo and runs[-1][2] == hi
+            for (h_idx, a, b), nxt in zip(runs, runs[1:] + [None]):
+                assert a < b and (table.h_index[a:b] == h_idx).all()
                 if nxt is not None:
-                    assert nxt[2] == b and (nxt[0], nxt[1]) != (h_idx, var)
+                    assert nxt[1] == b and nxt[0] != h_idx
             covered.extend(range(lo, hi))
             # "few plans per rank": a contiguous shard of the sorted table touches at most ceil(8/world)+1 heights
-            assert len({r[0] for r in runs}) <= -(-8 // world) + 1
+            assert len(runs) <= -(-8 // world) + 1
         assert covered == list(range(1000))
-    bounds = sweeps.variant_bounds(default_config, table.variants[:3])
-    for var, (z_max, z_min, first, last, n) in enumerate(bounds):
+    bounds = sweeps.variant_bounds(default_config, table.variants)
+    for z_max, z_min, first, last, n in bounds:
         assert z_max.shape == (n, 2) and (z_max >= z_min).all() and 0 < first < last < n
-        tick = sweeps.push_ticks(table, bounds, 0, 50, var)
-        assert tick.dtype == np.int32 and (tick >= first).all() and (tick <= last).all()
+    tick = sweeps.push_ticks(table, bounds, 0, 50)
+    first = np.array([bd[2] for bd in bounds])[table.variant[:50]]
+    last = np.array([bd[3] for bd in bounds])[table.variant[:50]]
+    assert tick.dtype == np.int32 and (tick >= first).all() and (tick <= last).all()
+    z_max_t, z_min_t, lengths = sweeps.bounds_table(bounds)
+    assert z_max_t.shape == (15, lengths.max(), 2) and np.array_equal(z_max_t[3, :lengths[3]], bounds[3][0])
