@@ -202,6 +202,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, next to the JSON line
         dist.init_process_group("nccl", device_id=device)
 
     B = args.batch
