@@ -159,6 +159,60 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
  */
 int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Herdt free-footstep MPC (method = "herdt"): ZMPController.predict_herdt_joint (zmp_controller.py:533-826)
+ * for B scenarios that share a support timeline.  The rollout bookkeeping of
+ * generate_com_trajectory_herdt (:435-531: swing-foot interpolation, side toggle, footstep commit, push)
+ * stays with the caller, tick by tick, on device tensors.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct herdt_plan herdt_plan_t;
+typedef struct herdt_timeline herdt_timeline_t;
+
+typedef struct herdt_plan_desc {
+    int32_t horizon;                /* N (<= 152: N + footstep slots must fit the resident-matrix kernel) */
+    double h, g, dt;
+    double alpha, beta, gamma;      /* jerk / velocity / ZMP weights (config.py:42-44, zmp_controller.py:605-607) */
+    double foot_length, foot_width; /* ZMP box around the supporting foot (:661-680)                      */
+    double foot_spread;             /* standing hull (:715-750)                                           */
+    double rho, relax, eps;         /* ADMM penalty (<=0 -> 8), over-relaxation (<=0 -> 1.6), stop (<=0 -> 1e-11) */
+    int32_t max_iter;               /* <=0 -> 4000                                                        */
+    int32_t device;
+} herdt_plan_desc_t;
+
+/* Per (N, h, g, dt, alpha, beta): T = Pzu^-1, V = Pvu Pzu^-1, W = alpha T'T + beta V'V, on the device. */
+int herdt_plan_create(herdt_plan_t** out, const herdt_plan_desc_t* desc);
+void herdt_plan_destroy(herdt_plan_t* plan);
+int herdt_plan_export_w(const herdt_plan_t* plan, double* host_out, size_t capacity);
+
+/*
+ * Per support timeline: for every tick the layout of the preview window (host arrays, :581-603, :682-698):
+ *   phase_of_row [n_ticks, N] int8   -1: row supported by the current foot (U_c), k >= 0: by future footstep k (U)
+ *   row_kind     [n_ticks, N] int8    0: unconstrained, 1: ZMP box around its foot, 2: standing hull of both feet
+ *   m_per_tick   [n_ticks]   int32   future footsteps in the window (m_max = their maximum)
+ * Builds the Hessian of every tick, its shifted inverse and the DMMA fragment image, on the device.
+ */
+int herdt_timeline_create(herdt_plan_t* plan, int n_ticks, int m_max, const int8_t* phase_of_row,
+                          const int8_t* row_kind, const int32_t* m_per_tick, herdt_timeline_t** out);
+void herdt_timeline_destroy(herdt_timeline_t* timeline);
+int herdt_timeline_size(const herdt_timeline_t* timeline);   /* padded variable count per axis */
+
+/*
+ * One control tick (predict_herdt_joint) for B scenarios of the timeline:
+ *   x, y        dev [B,3]   axis states;   fc dev [B,2] current support foot;
+ *   vref        dev [vref_batch, n_ext, 2] reference velocities, already padded by the caller (:465-467);
+ *               window row j reads sample tick + 1 + j
+ *   foot_side   0 = left, 1 = right (selects the standing hull; the polygon is passed explicitly)
+ *   poly_verts  HOST [n_verts, 2] reachable polygon of the next footstep relative to fc, counter-clockwise
+ *               (config.py:57-82 through ConvexHull, zmp_controller.py:773-790)
+ * outputs: next_x, next_y dev [B,3]; f1 dev [B,2] first free footstep (NaN when the window holds none);
+ *          solution dev [2B, size] or NULL ((e, F) per axis, x and y columns of a scenario adjacent);
+ *          status, iters dev int32 [2B] or NULL.
+ */
+int herdt_tick(herdt_timeline_t* timeline, int tick, int B, const double* x, const double* y, const double* fc,
+               const double* vref, int vref_batch, int n_ext, int foot_side, const double* poly_verts, int n_verts,
+               double* next_x, double* next_y, double* f1, double* solution, int32_t* status, int32_t* iters,
+               void* stream);
+
 /* Library / build information. */
 const char* lipm_last_error(void);
 const char* lipm_version(void);

@@ -27,6 +27,7 @@ class ZMPController:
         self.external_force = True
         # ADMM settings of the strict mode (library defaults when left at 0 / -1)
         self.solver_options: Dict[str, float] = {}
+        self.herdt_options: Dict[str, float] = {}     # rho / relax / eps / max_iter of the Herdt ADMM
 
     # ------------------------------------------------------------------ engine access
     def _plan(self, horizon: Optional[int] = None):
@@ -231,12 +232,77 @@ class ZMPController:
             raise ValueError(f"Polytope half-space conversion failed: max violation = {worst}")
         return A, b
 
-    # ------------------------------------------------------------------ Herdt (next scope row)
-    def generate_com_trajectory_herdt(self, x_init, y_init, v_ref, state_ref):
-        raise NotImplementedError(
-            "Herdt free-footstep MPC is not part of this build yet (SURVEY.md section 8(f), rank 1); "
-            "the Wieber path (method='wieber') is the implemented hot path")
+    # ------------------------------------------------------------------ Herdt (reference :435-826)
+    def generate_com_trajectory_herdt_batched(self, x_init, y_init, v_ref, state_ref, *, F_ext=None, m=None,
+                                              add_force: Optional[bool] = None, to_numpy: bool = True):
+        """Herdt walks of B scenarios that share ``state_ref`` (one launch per tick for the whole batch).
 
-    def predict_herdt_joint(self, *args, **kwargs):
-        raise NotImplementedError(
-            "Herdt free-footstep MPC is not part of this build yet (SURVEY.md section 8(f), rank 1)")
+        x_init, y_init (B,3); v_ref (n,2) shared or (B,n,2); state_ref (n,) of ``State``.  Returns dict(com
+        (B,n,2), x_hist, y_hist (B,n,3), foot_hist (B,n,2), status (B,), iters (B,))."""
+        import torch
+        from .. import engine
+        from ..herdt import HerdtBatch, state_codes
+
+        codes = state_codes(state_ref)
+        padded = np.concatenate([np.asarray(state_ref, dtype=object),
+                                 np.repeat(np.asarray(state_ref, dtype=object)[-1:], self.config.horizon)])
+        key = (codes.tobytes(), self.config.horizon, self.config.h, self.config.alpha, self.config.beta, self.config.gamma)
+        cache = getattr(self, "_herdt_cache", None)
+        if cache is None or cache[0] != key:
+            batch = HerdtBatch(self.config, state_ref, self.find_nb_steps(padded), solver_options=self.herdt_options)
+            self._herdt_cache = (key, batch)
+        batch = self._herdt_cache[1]
+        out = batch.rollout(x_init, y_init, v_ref, F_ext=F_ext, mass=m, add_force=add_force)
+        out["com"] = torch.stack([out["x_hist"][..., 0], out["y_hist"][..., 0]], dim=-1)
+        return engine.to_host(out) if to_numpy else out
+
+    def generate_com_trajectory_herdt(self, x_init, y_init, v_ref, state_ref):
+        """One Herdt walk: ``(com (n,2), y_hist (n,3,1), foot_hist (n,2))`` -- reference :435-531."""
+        res = self.generate_com_trajectory_herdt_batched(
+            np.asarray(x_init, dtype=np.float64).reshape(1, 3), np.asarray(y_init, dtype=np.float64).reshape(1, 3),
+            np.asarray(v_ref, dtype=np.float64), state_ref)
+        if int(res["status"][0]) != 0:
+            print("Joint QP solver failed on at least one tick")               # reference :797 prints and falls back
+        return res["com"][0], res["y_hist"][0][:, :, None], res["foot_hist"][0]
+
+    def predict_herdt_joint(self, x_init, y_init, v_ref, x_fc, y_fc, current_state, state_ref, nb_steps,
+                            nb_steps_to_next_state, x_airc, y_airc, foot_side, idx=0):
+        """One tick of the joint QP -- reference :533-826 (13 arguments, same order).  Returns
+        ``(x_next (3,1), y_next (3,1), first_x_footstep | None, first_y_footstep | None)``."""
+        import torch
+        from .. import engine
+        from ..herdt import STANDING, polygon_vertices, state_codes, support_runs
+
+        cfg = self.config
+        N = int(nb_steps)
+        window = state_codes(state_ref)[:N]
+        cur = int(state_codes([current_state])[0])
+        runs = support_runs(cur, window)
+        phase = np.full((1, N), -2, np.int8)
+        phase[0, : runs[0]] = -1
+        start = runs[0]
+        for k, length in enumerate(runs[1:]):
+            phase[0, start: start + length] = k
+            start += length
+        kind = np.zeros((1, N), np.int8)
+        walking = window != STANDING
+        kind[0][walking] = 1
+        if (cur == STANDING or not walking.any()) and (~walking).any():
+            kind[0][~walking] = 2
+        plan = engine.HerdtPlan(N, cfg.h, cfg.g, cfg.dt, cfg.alpha, cfg.beta, cfg.gamma, cfg.foot_length,
+                                cfg.foot_width, cfg.foot_spread, **self.herdt_options)
+        timeline = plan.timeline(phase, kind, np.array([len(runs) - 1], np.int32))
+        dev = plan.device
+        to_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        v = np.asarray(v_ref, dtype=np.float64).reshape(-1, 2)[:N]
+        vref = to_dev(np.vstack([v[:1], v]))                                      # the tick reads samples 1 .. N
+        side = 0 if foot_side == "left" else 1
+        poly = polygon_vertices(cfg.left_foot_polytope if side == 0 else cfg.right_foot_polytope)
+        fc = to_dev([[float(np.asarray(x_fc).reshape(-1)[0]), float(np.asarray(y_fc).reshape(-1)[0])]])
+        out = timeline.tick(0, to_dev(np.asarray(x_init).reshape(1, 3)), to_dev(np.asarray(y_init).reshape(1, 3)), fc,
+                            vref, side, poly if len(runs) > 1 else None)
+        res = engine.to_host({k: out[k] for k in ("next_x", "next_y", "f1", "status")})
+        plan.close()
+        has_step = len(runs) > 1
+        return (res["next_x"].reshape(3, 1), res["next_y"].reshape(3, 1),
+                float(res["f1"][0, 0]) if has_step else None, float(res["f1"][0, 1]) if has_step else None)

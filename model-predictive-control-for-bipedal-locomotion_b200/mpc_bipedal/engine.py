@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = (
     "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout", "lipm_rollout_indexed",
     "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
     "lipm_max_reduced_horizon",
+    "herdt_plan_create", "herdt_plan_destroy", "herdt_plan_export_w", "herdt_timeline_create",
+    "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick",
 )
 
 
@@ -314,3 +316,135 @@ def to_host(tensors: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
 
 def library_version() -> str:
     return load_library().lipm_version().decode()
+
+
+# ====================================================================================== Herdt (free footsteps)
+class _HerdtDesc(ctypes.Structure):
+    _fields_ = [
+        ("horizon", ctypes.c_int32),
+        ("h", ctypes.c_double), ("g", ctypes.c_double), ("dt", ctypes.c_double),
+        ("alpha", ctypes.c_double), ("beta", ctypes.c_double), ("gamma", ctypes.c_double),
+        ("foot_length", ctypes.c_double), ("foot_width", ctypes.c_double), ("foot_spread", ctypes.c_double),
+        ("rho", ctypes.c_double), ("relax", ctypes.c_double), ("eps", ctypes.c_double),
+        ("max_iter", ctypes.c_int32), ("device", ctypes.c_int32),
+    ]
+
+
+HERDT_SYMBOLS = ("herdt_plan_create", "herdt_plan_destroy", "herdt_plan_export_w", "herdt_timeline_create",
+                 "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick")
+
+
+def _herdt_lib() -> ctypes.CDLL:
+    lib = load_library()
+    if not getattr(lib, "_herdt_ready", False):
+        vp, i32 = ctypes.c_void_p, ctypes.c_int
+        lib.herdt_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_HerdtDesc)]
+        lib.herdt_plan_create.restype = i32
+        lib.herdt_plan_destroy.argtypes = [vp]
+        lib.herdt_plan_destroy.restype = None
+        lib.herdt_plan_export_w.argtypes = [vp, vp, ctypes.c_size_t]
+        lib.herdt_plan_export_w.restype = i32
+        lib.herdt_timeline_create.argtypes = [vp, i32, i32, vp, vp, vp, ctypes.POINTER(vp)]
+        lib.herdt_timeline_create.restype = i32
+        lib.herdt_timeline_destroy.argtypes = [vp]
+        lib.herdt_timeline_destroy.restype = None
+        lib.herdt_timeline_size.argtypes = [vp]
+        lib.herdt_timeline_size.restype = i32
+        lib.herdt_tick.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.herdt_tick.restype = i32
+        lib._herdt_ready = True
+    return lib
+
+
+class HerdtPlan:
+    """Device-resident matrices of the Herdt QP for one ``(N, h, g, dt, alpha, beta, gamma, foot)``."""
+
+    def __init__(self, horizon, h, g, dt, alpha, beta, gamma, foot_length, foot_width, foot_spread, *,
+                 rho=0.0, relax=0.0, eps=0.0, max_iter=0, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("liblipm_mpc needs a CUDA device (B200 / sm_100a); there is no CPU path")
+        self._lib = _herdt_lib()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        with torch.cuda.device(self.device_index):
+            torch.zeros(1, device=self.device)
+        self.horizon = int(horizon)
+        desc = _HerdtDesc(self.horizon, h, g, dt, alpha, beta, gamma, foot_length, foot_width, foot_spread,
+                          rho, relax, eps, max_iter, self.device_index)
+        handle = ctypes.c_void_p()
+        _check(self._lib.herdt_plan_create(ctypes.byref(handle), ctypes.byref(desc)))
+        self._handle = handle
+        self._timelines = []
+
+    def export_w(self) -> np.ndarray:
+        N = self.horizon
+        out = np.empty((N, N))
+        _check(self._lib.herdt_plan_export_w(self._handle, out.ctypes.data, out.size))
+        return out
+
+    def timeline(self, phase_of_row: np.ndarray, row_kind: np.ndarray, m_per_tick: np.ndarray) -> "HerdtTimeline":
+        return HerdtTimeline(self, phase_of_row, row_kind, m_per_tick)
+
+    def close(self) -> None:
+        for t in self._timelines:
+            t.close()
+        self._timelines = []
+        if getattr(self, "_handle", None):
+            self._lib.herdt_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HerdtTimeline:
+    """Per-tick Hessians (inverted, in DMMA fragment order) of one support timeline."""
+
+    def __init__(self, plan: HerdtPlan, phase_of_row, row_kind, m_per_tick):
+        self.plan = plan
+        self._lib = plan._lib
+        phase = np.ascontiguousarray(phase_of_row, dtype=np.int8)
+        kind = np.ascontiguousarray(row_kind, dtype=np.int8)
+        m = np.ascontiguousarray(m_per_tick, dtype=np.int32)
+        if phase.shape != kind.shape or phase.ndim != 2 or phase.shape[1] != plan.horizon or len(m) != len(phase):
+            raise ValueError("phase_of_row / row_kind must be (n_ticks, N) and m_per_tick (n_ticks,)")
+        self.n_ticks = len(m)
+        self.m = m
+        handle = ctypes.c_void_p()
+        _check(self._lib.herdt_timeline_create(plan._handle, self.n_ticks, int(m.max()), phase.ctypes.data,
+                                               kind.ctypes.data, m.ctypes.data, ctypes.byref(handle)))
+        self._handle = handle
+        self.size = int(self._lib.herdt_timeline_size(handle))
+        plan._timelines.append(self)
+
+    def tick(self, i: int, x: torch.Tensor, y: torch.Tensor, fc: torch.Tensor, vref: torch.Tensor, foot_side: int,
+             poly_verts: Optional[np.ndarray], *, want_solution: bool = False) -> Dict[str, torch.Tensor]:
+        """``predict_herdt_joint`` for B scenarios (device tensors in, device tensors out)."""
+        dev = self.plan.device
+        B = x.shape[0]
+        vref_batch = 1 if vref.ndim == 2 else vref.shape[0]
+        n_ext = vref.shape[-2]
+        nx = torch.empty((B, 3), dtype=torch.float64, device=dev)
+        ny = torch.empty((B, 3), dtype=torch.float64, device=dev)
+        f1 = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        status = torch.zeros((2 * B,), dtype=torch.int32, device=dev)
+        iters = torch.zeros((2 * B,), dtype=torch.int32, device=dev)
+        sol = torch.empty((2 * B, self.size), dtype=torch.float64, device=dev) if want_solution else None
+        verts = None if poly_verts is None else np.ascontiguousarray(poly_verts, dtype=np.float64)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(self._lib.herdt_tick(self._handle, int(i), B, x.data_ptr(), y.data_ptr(), fc.data_ptr(), vref.data_ptr(),
+                                    vref_batch, n_ext, int(foot_side), None if verts is None else verts.ctypes.data,
+                                    0 if verts is None else len(verts), nx.data_ptr(), ny.data_ptr(), f1.data_ptr(),
+                                    _ptr(sol), status.data_ptr(), iters.data_ptr(), stream))
+        out = {"next_x": nx, "next_y": ny, "f1": f1, "status": status, "iters": iters}
+        if want_solution:
+            out["solution"] = sol
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.herdt_timeline_destroy(self._handle)
+            self._handle = None

@@ -1,0 +1,166 @@
+"""Herdt free-footstep MPC on the batched engine (reference ``zmp_controller.py:435-826``).
+
+Host side of the method: the support-phase layout of every tick's preview window (what the reference
+recomputes inside ``predict_herdt_joint``, ``:581-603`` and ``:682-698``) and the rollout bookkeeping of
+``generate_com_trajectory_herdt`` (``:450-531``: swing-foot interpolation, side toggle and footstep commit
+on leaving SINGLE_SUPPORT, push, current-state tracking).  The joint QP of every tick is solved on the GPU
+for all scenarios that share the timeline (``engine.HerdtTimeline.tick`` -> ``herdt_tick``).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .generators.cop_generator import State
+
+STANDING, DOUBLE_SUPPORT, SINGLE_SUPPORT = 0, 1, 2
+
+
+def state_codes(state_ref) -> np.ndarray:
+    """``State`` members (or ints) -> int8 codes 0 STANDING / 1 DOUBLE_SUPPORT / 2 SINGLE_SUPPORT."""
+    table = {State.STANDING: STANDING, State.DOUBLE_SUPPORT: DOUBLE_SUPPORT, State.SINGLE_SUPPORT: SINGLE_SUPPORT}
+    return np.array([table.get(s, s) for s in state_ref], dtype=np.int8)
+
+
+def support_runs(current_state: int, window: Sequence[int]) -> List[int]:
+    """Run lengths of the support phases seen from the current tick (reference ``:581-594``): a run ends when
+    the state changes, except DOUBLE_SUPPORT -> SINGLE_SUPPORT which is one footstep.  The current tick is
+    counted in the first run, so the lengths sum to N + 1."""
+    runs, count, s = [], 1, current_state
+    for state in window:
+        if state == s or (s == DOUBLE_SUPPORT and state == SINGLE_SUPPORT):
+            count += 1
+        else:
+            runs.append(count)
+            count = 1
+        s = state
+    runs.append(count)
+    return runs
+
+
+@dataclass
+class TimelineLayout:
+    """Everything about a walk that depends on the state timeline only (shared by a batch)."""
+
+    codes: np.ndarray            # (n + N,) padded state codes (reference :468-470)
+    current: np.ndarray          # (n-1,) state the controller is in at each tick
+    foot_side: np.ndarray        # (n-1,) 0 left / 1 right at each tick
+    commit: np.ndarray           # (n-1,) bool: the tick leaves SINGLE_SUPPORT (footstep is committed, side toggles)
+    phase_of_row: np.ndarray     # (n-1, N) int8
+    row_kind: np.ndarray         # (n-1, N) int8
+    m: np.ndarray                # (n-1,) int32
+
+
+def timeline_layout(state_ref, horizon: int) -> TimelineLayout:
+    codes = state_codes(state_ref)
+    n, N = len(codes), horizon
+    ext = np.concatenate([codes, np.repeat(codes[-1:], N)])
+    ticks = n - 1
+    current = np.zeros(ticks, np.int8)
+    side = np.zeros(ticks, np.int8)
+    commit = np.zeros(ticks, bool)
+    phase = np.zeros((ticks, N), np.int8)
+    kind = np.zeros((ticks, N), np.int8)
+    m = np.zeros(ticks, np.int32)
+    cur, foot = int(ext[0]), 0                       # reference :459, :457 ("left")
+    for i in range(ticks):
+        window = ext[i + 1: i + 1 + N]
+        runs = support_runs(cur, window)
+        current[i], side[i], m[i] = cur, foot, len(runs) - 1
+        row = np.full(N, -2, np.int8)
+        row[: runs[0]] = -1                          # U_c, :597-598
+        start = runs[0]
+        for k, length in enumerate(runs[1:]):        # U, :599-603 (clipped at N like the numpy slices)
+            row[start: start + length] = k
+            start += length
+        phase[i] = row
+        walking = window != STANDING
+        kind[i][walking] = 1                         # ZMP box around the supporting foot, rows kept by :682-698
+        if (cur == STANDING or not walking.any()) and (~walking).any():
+            kind[i][~walking] = 2                    # standing hull, :715-771
+        nxt = int(ext[i + 1])
+        if nxt != cur and cur == SINGLE_SUPPORT:     # :501-503
+            commit[i] = True
+            foot = 1 - foot
+        if nxt != cur:                               # :524-525
+            cur = nxt
+    return TimelineLayout(ext, current, side, commit, phase, kind, m)
+
+
+def polygon_vertices(polytope) -> np.ndarray:
+    """Counter-clockwise hull vertices of a footstep polytope (what ``_polytope_halfspace`` turns into facets)."""
+    from scipy.spatial import ConvexHull
+
+    verts = np.asarray(polytope, dtype=float)
+    return np.ascontiguousarray(verts[ConvexHull(verts).vertices])
+
+
+class HerdtBatch:
+    """Batched ``generate_com_trajectory_herdt`` for scenarios sharing one state timeline."""
+
+    def __init__(self, config, state_ref, nb_steps, *, solver_options: Optional[dict] = None):
+        from . import engine
+
+        self.config = config
+        self.layout = timeline_layout(state_ref, config.horizon)
+        self.nb_steps = nb_steps          # find_nb_steps of the PADDED timeline (reference :471)
+        opts = solver_options or {}
+        self.plan = engine.HerdtPlan(config.horizon, config.h, config.g, config.dt, config.alpha, config.beta,
+                                     config.gamma, config.foot_length, config.foot_width, config.foot_spread, **opts)
+        self.timeline = self.plan.timeline(self.layout.phase_of_row, self.layout.row_kind, self.layout.m)
+        self.polygons = (polygon_vertices(config.left_foot_polytope), polygon_vertices(config.right_foot_polytope))
+
+    def rollout(self, x_init, y_init, v_ref, *, F_ext=None, mass=None, add_force: Optional[bool] = None,
+                n_ticks: Optional[int] = None) -> Dict[str, "torch.Tensor"]:
+        """x_init, y_init (B,3); v_ref (n,2) shared or (B,n,2).  Returns device tensors x_hist, y_hist (B,n,3),
+        foot_hist (B,n,2), status (B,) = ticks whose QP did not converge, iters (B,)."""
+        import torch
+
+        cfg, lay = self.config, self.layout
+        dev = self.plan.device
+        N = cfg.horizon
+        x = torch.as_tensor(np.asarray(x_init, float).reshape(-1, 3)).to(dev).contiguous()
+        y = torch.as_tensor(np.asarray(y_init, float).reshape(-1, 3)).to(dev).contiguous()
+        B = x.shape[0]
+        v = np.asarray(v_ref, float)
+        n = v.shape[-2]
+        if n != len(lay.codes) - N:
+            raise ValueError("v_ref and state_ref must have the same length")
+        pad = np.repeat(v[..., -1:, :], N, axis=-2)                              # reference :465-467
+        vref = torch.as_tensor(np.concatenate([v, pad], axis=-2)).to(dev).contiguous()
+        fc = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+        fc[:, 1] = cfg.foot_spread                                                # :455-456
+        air = fc.clone()
+        push = cfg.add_force if add_force is None else add_force
+        impulse = None
+        if push:
+            F = np.broadcast_to(np.asarray(cfg.F_ext if F_ext is None else F_ext, float), (B,))
+            m_ = np.broadcast_to(np.asarray(cfg.m if mass is None else mass, float), (B,))
+            impulse = torch.as_tensor(cfg.dt * F / m_).to(dev)
+        ticks = n - 1 if n_ticks is None else n_ticks
+        x_hist = torch.zeros((B, n, 3), dtype=torch.float64, device=dev)
+        y_hist = torch.zeros((B, n, 3), dtype=torch.float64, device=dev)
+        foot_hist = torch.zeros((B, n, 2), dtype=torch.float64, device=dev)
+        x_hist[:, 0], y_hist[:, 0], foot_hist[:, 0] = x, y, fc
+        status = torch.zeros((B,), dtype=torch.int32, device=dev)
+        iters = torch.zeros((B,), dtype=torch.int64, device=dev)
+        for i in range(ticks):
+            side = int(lay.foot_side[i])
+            has_step = lay.m[i] > 0
+            out = self.timeline.tick(i, x, y, fc, vref, side, self.polygons[side] if has_step else None)
+            x, y = out["next_x"], out["next_y"]
+            if has_step:
+                air = air + (1.0 / self.nb_steps[i][0]) * (out["f1"] - air)      # :495-498
+            if lay.commit[i]:                                                     # :501-517
+                fc = out["f1"].clone() if has_step else air.clone()
+                air = fc.clone()
+            if push and i == n // 2:                                              # :522-523
+                y = y.clone()
+                y[:, 1] -= impulse
+            x_hist[:, i + 1], y_hist[:, i + 1], foot_hist[:, i + 1] = x, y, fc
+            status += out["status"].view(B, 2).amax(dim=1)
+            iters += out["iters"].view(B, 2).amax(dim=1)
+        return {"x_hist": x_hist, "y_hist": y_hist, "foot_hist": foot_hist, "status": status, "iters": iters}

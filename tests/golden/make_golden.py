@@ -207,5 +207,35 @@ def main():
         TARGETS[name](path)
 
 
+# ----------------------------------------------------------------------------- Herdt (oracle, not reference)
+def make_oracle_herdt_walk():
+    """ORACLE Herdt walk (KKT-certified QP solves) on the class-default config the reference's
+    run_herdt_method.py uses (:53), timeline / nb_steps / polytope facets taken from the REFERENCE outputs
+    recorded in ref_herdt_helpers.npz.  ~5 minutes of CPU."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "model-predictive-control-for-bipedal-locomotion_b200"))
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.models.lipm_model import discrete_model
+    from oracle import herdt_oracle as ho
+
+    g = np.load(os.path.join(HERE, "ref_herdt_helpers.npz"))
+    cfg = MPCConfig()
+    cfg.add_force = True
+    A, B, _ = discrete_model(cfg.dt, cfg.h, cfg.g)
+    states = g["class_defaults/states"]
+    v_ref = np.stack([g["class_defaults/vx"], g["class_defaults/vy"]], 1)
+    polys = {s: (g[f"polytope/{s}/A"], g[f"polytope/{s}/b"]) for s in ("left", "right")}
+    res = ho.rollout_herdt(cfg, A, B, np.zeros(3), np.zeros(3), v_ref, states, g["class_defaults/nb_steps"], polys)
+    assert all(c["ok"] for c in res["kkt"]), "a QP solve failed its KKT certificate"
+    worst = {k: max(c[k] for c in res["kkt"]) for k in ("stationarity", "primal", "dual", "complementarity")}
+    np.savez_compressed(os.path.join(HERE, "oracle_herdt_walk.npz"), x_hist=res["x_hist"], y_hist=res["y_hist"],
+                        foot_hist=res["foot_hist"], states=states, v_ref=v_ref, F_ext=cfg.F_ext, m=cfg.m,
+                        kkt_worst=np.array([worst[k] for k in ("stationarity", "primal", "dual", "complementarity")]))
+    print("oracle_herdt_walk.npz written; worst KKT residuals:", worst)
+
+
 if __name__ == "__main__":
-    main()
+    if "--herdt" in sys.argv:
+        make_oracle_herdt_walk()
+    else:
+        main()

