@@ -174,8 +174,8 @@ typedef struct herdt_plan_desc {
     double alpha, beta, gamma;      /* jerk / velocity / ZMP weights (config.py:42-44, zmp_controller.py:605-607) */
     double foot_length, foot_width; /* ZMP box around the supporting foot (:661-680)                      */
     double foot_spread;             /* standing hull (:715-750)                                           */
-    double rho, relax, eps;         /* ADMM penalty (<=0 -> 8), over-relaxation (<=0 -> 1.6), stop (<=0 -> 1e-11) */
-    int32_t max_iter;               /* <=0 -> 4000                                                        */
+    double rho, relax, eps;         /* ADMM penalty (<=0 -> 8), over-relaxation (<=0 -> 1.6), stop (<=0 -> 1e-12) */
+    int32_t max_iter;               /* <=0 -> 600 (a healthy tick needs 60..150 from a cold start)         */
     int32_t device;
 } herdt_plan_desc_t;
 
@@ -199,6 +199,9 @@ int herdt_timeline_size(const herdt_timeline_t* timeline);   /* padded variable 
 /*
  * One control tick (predict_herdt_joint) for B scenarios of the timeline:
  *   x, y        dev [B,3]   axis states;   fc dev [B,2] current support foot;
+ *   air         dev [B,2]   swing-foot interpolation (x_airc, y_airc) or NULL: a scenario whose QP does not
+ *               converge falls back like the reference (:796-804): zero jerk, footstep := air
+ *   spread      dev [B]     per-scenario foot_spread of the standing hull, or NULL (-> plan value)
  *   vref        dev [vref_batch, n_ext, 2] reference velocities, already padded by the caller (:465-467);
  *               window row j reads sample tick + 1 + j
  *   foot_side   0 = left, 1 = right (selects the standing hull; the polygon is passed explicitly)
@@ -209,9 +212,9 @@ int herdt_timeline_size(const herdt_timeline_t* timeline);   /* padded variable 
  *          status, iters dev int32 [2B] or NULL.
  */
 int herdt_tick(herdt_timeline_t* timeline, int tick, int B, const double* x, const double* y, const double* fc,
-               const double* vref, int vref_batch, int n_ext, int foot_side, const double* poly_verts, int n_verts,
-               double* next_x, double* next_y, double* f1, double* solution, int32_t* status, int32_t* iters,
-               void* stream);
+               const double* air, const double* spread, const double* vref, int vref_batch, int n_ext, int foot_side,
+               const double* poly_verts, int n_verts, double* next_x, double* next_y, double* f1, double* solution,
+               int32_t* status, int32_t* iters, void* stream);
 
 /* Library / build information. */
 const char* lipm_last_error(void);

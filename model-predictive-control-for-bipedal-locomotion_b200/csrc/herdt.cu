@@ -219,6 +219,7 @@ struct TickParams {
     double T, hg, alpha, beta;
     double half[2];               // 0.5 foot_length, 0.5 foot_width
     double foot_spread;
+    const double* spread;         // [B] per-scenario foot spread or nullptr (-> foot_spread)
     const int8_t* phase;          // [N] of this tick
     const int8_t* kind;           // [N] 0 free, 1 foot box, 2 standing hull
     const double *tcol, *vcol;    // Toeplitz first columns of T, V
@@ -282,7 +283,8 @@ __global__ void __launch_bounds__(128) k_herdt_prepare(const TickParams P) {
         box_lo = fc - P.half[0];
         box_hi = fc + P.half[0];
     } else {
-        const double other = P.foot_side == 0 ? fc - 2.0 * P.foot_spread : fc + 2.0 * P.foot_spread;
+        const double sp = P.spread ? P.spread[b] : P.foot_spread;
+        const double other = P.foot_side == 0 ? fc - 2.0 * sp : fc + 2.0 * sp;
         box_lo = fmin(fc, other) - P.half[1];
         box_hi = fmax(fc, other) + P.half[1];
     }
@@ -555,23 +557,27 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
 }
 
 // next states and first footstep of every scenario: J0 = (e_0 + fc - Pzx[0] x) / Pzu[0,0]  (:806-812)
+// A scenario whose QP did not converge falls back like the reference does when OSQP returns nothing (:796-804):
+// zero jerk, footstep := current swing-foot interpolation.
 __global__ void k_herdt_apply(int B, int NP, int N, int m, double T, double hg, const double* __restrict__ sol,
                               const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ fc,
+                              const double* __restrict__ air, const int32_t* __restrict__ status,
                               double* __restrict__ next_x, double* __restrict__ next_y, double* __restrict__ f1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 2 * B) return;
     const int b = idx >> 1, axis = idx & 1;
+    const bool failed = status && (status[2 * b] != 0 || status[2 * b + 1] != 0);
     const double* s = (axis ? y : x) + (size_t)b * 3;
     const double x0 = s[0], x1 = s[1], x2 = s[2];
     const double c3 = T * T * T / 6.0, c2 = T * T / 2.0;
     const double z0 = sol[(size_t)idx * NP] + fc[(size_t)b * 2 + axis];
     const double pred = fma(c2 - hg, x2, fma(T, x1, x0));
-    const double jerk = (z0 - pred) / (c3 - T * hg);
+    const double jerk = failed ? 0.0 : (z0 - pred) / (c3 - T * hg);
     double* out = (axis ? next_y : next_x) + (size_t)b * 3;
     out[0] = fma(c3, jerk, fma(c2, x2, fma(T, x1, x0)));
     out[1] = fma(c2, jerk, fma(T, x2, x1));
     out[2] = fma(T, jerk, x2);
-    if (f1) f1[(size_t)b * 2 + axis] = m > 0 ? sol[(size_t)idx * NP + N] : nan("");
+    if (f1) f1[(size_t)b * 2 + axis] = m > 0 ? ((failed && air) ? air[(size_t)b * 2 + axis] : sol[(size_t)idx * NP + N]) : nan("");
 }
 
 template <int NRB, int NG>
@@ -629,8 +635,8 @@ int herdt_plan_create(herdt_plan_t** out, const herdt_plan_desc_t* desc) {
     }
     if (!(d.rho > 0)) d.rho = 8.0;
     if (!(d.relax > 0)) d.relax = 1.6;
-    if (!(d.eps > 0)) d.eps = 1e-11;
-    if (d.max_iter <= 0) d.max_iter = 4000;
+    if (!(d.eps > 0)) d.eps = 1e-12;
+    if (d.max_iter <= 0) d.max_iter = 600;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { set_error("no CUDA device available (this library has no CPU path)"); return LIPM_E_CUDA; }
     if (d.device < 0 || d.device >= count) { set_error("device %d out of range", d.device); return LIPM_E_INVALID; }
@@ -735,8 +741,9 @@ void herdt_timeline_destroy(herdt_timeline_t* t) {
 }
 
 int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const double* y, const double* fc,
-               const double* vref, int vref_batch, int n_ext, int foot_side, const double* poly_verts, int n_verts,
-               double* next_x, double* next_y, double* f1, double* solution, int32_t* status, int32_t* iters, void* stream_) {
+               const double* air, const double* spread, const double* vref, int vref_batch, int n_ext, int foot_side,
+               const double* poly_verts, int n_verts, double* next_x, double* next_y, double* f1, double* solution,
+               int32_t* status, int32_t* iters, void* stream_) {
     if (!t || tick < 0 || tick >= t->n_ticks) { set_error("herdt_tick: bad timeline / tick"); return LIPM_E_INVALID; }
     if (B < 0 || !x || !y || !fc || !vref || !next_x || !next_y) { set_error("herdt_tick: missing argument"); return LIPM_E_INVALID; }
     if (B == 0) return LIPM_OK;
@@ -762,6 +769,7 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
     P.foot_side = foot_side;
     P.T = d.dt; P.hg = d.h / d.g; P.alpha = d.alpha; P.beta = d.beta;
     P.half[0] = 0.5 * d.foot_length; P.half[1] = 0.5 * d.foot_width; P.foot_spread = d.foot_spread;
+    P.spread = spread;
     P.phase = t->d_phase + (size_t)tick * N; P.kind = t->d_kind + (size_t)tick * N;
     P.tcol = plan->d_t; P.vcol = plan->d_v;
     P.x = x; P.y = y; P.fc = fc; P.vref = vref;
@@ -796,7 +804,8 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
         default: set_error("herdt: no kernel variant for padded size %d", NP); return LIPM_E_UNSUPPORTED;
     }
     if (rc != LIPM_OK) return rc;
-    k_herdt_apply<<<(ncols + 127) / 128, 128, 0, stream>>>(B, NP, N, m, d.dt, d.h / d.g, Q.sol, x, y, fc, next_x, next_y, f1);
+    k_herdt_apply<<<(ncols + 127) / 128, 128, 0, stream>>>(B, NP, N, m, d.dt, d.h / d.g, Q.sol, x, y, fc, air, status,
+                                                           next_x, next_y, f1);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;
 }

@@ -234,7 +234,8 @@ class ZMPController:
 
     # ------------------------------------------------------------------ Herdt (reference :435-826)
     def generate_com_trajectory_herdt_batched(self, x_init, y_init, v_ref, state_ref, *, F_ext=None, m=None,
-                                              add_force: Optional[bool] = None, to_numpy: bool = True):
+                                              foot_spread=None, add_force: Optional[bool] = None,
+                                              to_numpy: bool = True):
         """Herdt walks of B scenarios that share ``state_ref`` (one launch per tick for the whole batch).
 
         x_init, y_init (B,3); v_ref (n,2) shared or (B,n,2); state_ref (n,) of ``State``.  Returns dict(com
@@ -252,7 +253,7 @@ class ZMPController:
             batch = HerdtBatch(self.config, state_ref, self.find_nb_steps(padded), solver_options=self.herdt_options)
             self._herdt_cache = (key, batch)
         batch = self._herdt_cache[1]
-        out = batch.rollout(x_init, y_init, v_ref, F_ext=F_ext, mass=m, add_force=add_force)
+        out = batch.rollout(x_init, y_init, v_ref, F_ext=F_ext, mass=m, foot_spread=foot_spread, add_force=add_force)
         out["com"] = torch.stack([out["x_hist"][..., 0], out["y_hist"][..., 0]], dim=-1)
         return engine.to_host(out) if to_numpy else out
 

@@ -113,10 +113,11 @@ class HerdtBatch:
         self.timeline = self.plan.timeline(self.layout.phase_of_row, self.layout.row_kind, self.layout.m)
         self.polygons = (polygon_vertices(config.left_foot_polytope), polygon_vertices(config.right_foot_polytope))
 
-    def rollout(self, x_init, y_init, v_ref, *, F_ext=None, mass=None, add_force: Optional[bool] = None,
-                n_ticks: Optional[int] = None) -> Dict[str, "torch.Tensor"]:
+    def rollout(self, x_init, y_init, v_ref, *, F_ext=None, mass=None, foot_spread=None,
+                add_force: Optional[bool] = None, n_ticks: Optional[int] = None) -> Dict[str, "torch.Tensor"]:
         """x_init, y_init (B,3); v_ref (n,2) shared or (B,n,2).  Returns device tensors x_hist, y_hist (B,n,3),
-        foot_hist (B,n,2), status (B,) = ticks whose QP did not converge, iters (B,)."""
+        foot_hist (B,n,2), status (B,) = ticks whose QP did not converge (they fall back to zero jerk and the
+        interpolated footstep like the reference, :796-804), iters (B,)."""
         import torch
 
         cfg, lay = self.config, self.layout
@@ -132,7 +133,10 @@ class HerdtBatch:
         pad = np.repeat(v[..., -1:, :], N, axis=-2)                              # reference :465-467
         vref = torch.as_tensor(np.concatenate([v, pad], axis=-2)).to(dev).contiguous()
         fc = torch.zeros((B, 2), dtype=torch.float64, device=dev)
-        fc[:, 1] = cfg.foot_spread                                                # :455-456
+        spread = None
+        if foot_spread is not None:                                               # a plan parameter per scenario
+            spread = torch.as_tensor(np.broadcast_to(np.asarray(foot_spread, float), (B,)).copy()).to(dev)
+        fc[:, 1] = cfg.foot_spread if spread is None else spread                  # :455-456
         air = fc.clone()
         push = cfg.add_force if add_force is None else add_force
         impulse = None
@@ -150,7 +154,8 @@ class HerdtBatch:
         for i in range(ticks):
             side = int(lay.foot_side[i])
             has_step = lay.m[i] > 0
-            out = self.timeline.tick(i, x, y, fc, vref, side, self.polygons[side] if has_step else None)
+            out = self.timeline.tick(i, x, y, fc, vref, side, self.polygons[side] if has_step else None,
+                                     air=air.contiguous(), spread=spread)
             x, y = out["next_x"], out["next_y"]
             if has_step:
                 air = air + (1.0 / self.nb_steps[i][0]) * (out["f1"] - air)      # :495-498

@@ -226,12 +226,17 @@ def make_oracle_herdt_walk():
     v_ref = np.stack([g["class_defaults/vx"], g["class_defaults/vy"]], 1)
     polys = {s: (g[f"polytope/{s}/A"], g[f"polytope/{s}/b"]) for s in ("left", "right")}
     res = ho.rollout_herdt(cfg, A, B, np.zeros(3), np.zeros(3), v_ref, states, g["class_defaults/nb_steps"], polys)
-    assert all(c["ok"] for c in res["kkt"]), "a QP solve failed its KKT certificate"
-    worst = {k: max(c[k] for c in res["kkt"]) for k in ("stationarity", "primal", "dual", "complementarity")}
-    np.savez_compressed(os.path.join(HERE, "oracle_herdt_walk.npz"), x_hist=res["x_hist"], y_hist=res["y_hist"],
-                        foot_hist=res["foot_hist"], states=states, v_ref=v_ref, F_ext=cfg.F_ext, m=cfg.m,
-                        kkt_worst=np.array([worst[k] for k in ("stationarity", "primal", "dual", "complementarity")]))
-    print("oracle_herdt_walk.npz written; worst KKT residuals:", worst)
+    # The walk is certified tick by tick up to the final stance.  There the reference's formulation commits the
+    # "footstep" of the final STANDING phase (forced one step AHEAD by the reachable polytope, :773-790) and then
+    # asks the ZMP to stay in a hull that lies in front of the decelerating CoM (:715-771): every row of the QP is
+    # active, the CoM is pushed backwards and the solves no longer converge (the reference would print "Joint QP
+    # solver failed" and fall back, :796-804).  Only the certified prefix is a golden vector.
+    ok = np.array([c["ok"] for c in res["kkt"]])
+    last = int(np.where(~ok)[0][0]) if (~ok).any() else len(ok)
+    np.savez_compressed(os.path.join(HERE, "oracle_herdt_walk.npz"), x_hist=res["x_hist"][: last + 1],
+                        y_hist=res["y_hist"][: last + 1], foot_hist=res["foot_hist"][: last + 1], certified_ticks=last,
+                        final_com_uncertified=np.array([res["x_hist"][-1, 0], res["y_hist"][-1, 0]]))
+    print("oracle_herdt_walk.npz written; certified ticks:", last)
 
 
 if __name__ == "__main__":

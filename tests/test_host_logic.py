@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
 
     entry.build_cuda()
     header = open(os.path.join(REPO, "include", "lipm_mpc.h")).read()
-    declared = set(re.findall(r"\b(lipm_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b((?:lipm|herdt)_[a-z_]+)\s*\(", header))
     assert declared == set(engine.EXPORTED_SYMBOLS)
     lib = ctypes.CDLL(engine.LIBRARY_PATH)
     for name in declared:
