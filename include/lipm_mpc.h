@@ -67,7 +67,7 @@ typedef struct lipm_plan_desc {
     int32_t horizon;   /* N  = MPCConfig.horizon                                            */
     double h, g, dt;   /* CoM height, gravity, sample time (dt = 1.5/N unless overridden)   */
     double Q, R;       /* tracking / jerk weights (zmp_controller.py:186, :174)             */
-    double rho;        /* ADMM penalty          (<=0 -> default 2.0)                        */
+    double rho;        /* ADMM penalty (<=0 -> 2.0 for N <= 160, sqrt(Q (Q + lambda_max(G))) beyond) */
     double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.6)                        */
     double eps;        /* ADMM stop: primal and rho*dual residual <= eps * max(1, |q|_inf)  (<=0 -> 1e-12;
                           F16X3: <=0 -> 1e-5, floor 5e-7)                                   */
@@ -207,14 +207,18 @@ int herdt_timeline_size(const herdt_timeline_t* timeline);   /* padded variable 
  *   foot_side   0 = left, 1 = right (selects the standing hull; the polygon is passed explicitly)
  *   poly_verts  HOST [n_verts, 2] reachable polygon of the next footstep relative to fc, counter-clockwise
  *               (config.py:57-82 through ConvexHull, zmp_controller.py:773-790)
+ *   warm        0: cold start (as the reference: a fresh OSQP problem per tick);  1: start from the previous
+ *               tick's ADMM iterate kept in the timeline (only honoured when the previous call was tick - 1
+ *               with the same B);  2: same, and the previous tick's first future footstep has just become
+ *               the current phase (footstep variables move down by one)
  * outputs: next_x, next_y dev [B,3]; f1 dev [B,2] first free footstep (NaN when the window holds none);
  *          solution dev [2B, size] or NULL ((e, F) per axis, x and y columns of a scenario adjacent);
  *          status, iters dev int32 [2B] or NULL.
  */
 int herdt_tick(herdt_timeline_t* timeline, int tick, int B, const double* x, const double* y, const double* fc,
                const double* air, const double* spread, const double* vref, int vref_batch, int n_ext, int foot_side,
-               const double* poly_verts, int n_verts, double* next_x, double* next_y, double* f1, double* solution,
-               int32_t* status, int32_t* iters, void* stream);
+               const double* poly_verts, int n_verts, int warm, double* next_x, double* next_y, double* f1,
+               double* solution, int32_t* status, int32_t* iters, void* stream);
 
 /* Library / build information. */
 const char* lipm_last_error(void);

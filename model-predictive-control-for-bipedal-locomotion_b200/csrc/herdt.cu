@@ -227,6 +227,9 @@ struct TickParams {
     const double* fc;             // [B,2]
     const double* vref;           // [vref_batch, n_ext, 2]
     double *q, *lo, *hi, *t0;     // [2B, NP]
+    const double* t_prev;         // [2B, NP] final ADMM iterate t of the previous tick, or nullptr (cold start)
+    int shift_f;                  // the previous tick's first future footstep became the current phase
+    int m_prev;                   // footsteps of the previous tick
 };
 
 // linear term, bounds and start point of every column (one CTA per column)
@@ -297,6 +300,9 @@ __global__ void __launch_bounds__(128) k_herdt_prepare(const TickParams P) {
             else if (kind == 2) { const double ref = P.phase[j] == -1 ? fc : 0.0; lo = box_lo - ref; hi = box_hi - ref; }
             else { lo = -kFree; hi = kFree; }
             t0 = fmin(fmax(0.0, lo), hi);
+            // warm start: the window slid by one sample and e is relative to the supporting foot, so the previous
+            // iterate (primal + scaled dual) of row j+1 is the natural start of row j; hull rows start cold
+            if (P.t_prev && kind != 2) t0 = j + 1 < N ? P.t_prev[base + j + 1] : fmin(fmax(P.t_prev[base + j], lo), hi);
         } else if (j < N + P.m) {
             const int k = j - N;
             double s = 0.0;
@@ -305,6 +311,11 @@ __global__ void __launch_bounds__(128) k_herdt_prepare(const TickParams P) {
             q = s;
             lo = -kFree; hi = kFree;
             t0 = fc;
+            if (P.t_prev && P.m_prev > 0) {
+                int kp = k + P.shift_f;
+                kp = kp > P.m_prev - 1 ? P.m_prev - 1 : kp;      // a footstep that just entered the window starts at the last known one
+                t0 = P.t_prev[base + N + kp];
+            }
         }
         P.q[base + j] = q; P.lo[base + j] = lo; P.hi[base + j] = hi; P.t0[base + j] = t0;
     }
@@ -319,6 +330,7 @@ struct QpParams {
     const double* mfrag;
     const double *q, *lo, *hi, *t0;   // [ncols, NP]
     double* sol;                  // [ncols, NP] projected solution
+    double* t_out;                // [ncols, NP] final iterate (warm start of the next tick) or nullptr
     int32_t *status, *iters;      // [ncols]
     const double* poly_shift;     // [ncols/2, 2]: the polygon is given relative to this point (current foot)
     int n_verts;
@@ -547,6 +559,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
                 double z = clipd(tv[r][e], lo[r][e], hi[r][e]);
                 if (r == f1_r) z = zf[e];
                 P.sol[(size_t)c * NP + row0 + r * 8] = z;
+                if (P.t_out) P.t_out[(size_t)c * NP + row0 + r * 8] = tv[r][e];
             }
             if (rg == 0 && g == 0) {
                 if (P.iters) P.iters[c] = iters[e];
@@ -616,7 +629,8 @@ struct herdt_timeline {
     size_t nfrag;
     // per-tick scratch, grown on demand
     int cap_cols;
-    double *d_q, *d_lo, *d_hi, *d_t0, *d_sol;
+    double *d_q, *d_lo, *d_hi, *d_t0, *d_sol, *d_tprev;
+    int prev_tick, prev_cols;   // what d_tprev holds (-1: nothing)
 };
 
 extern "C" {
@@ -697,6 +711,7 @@ int herdt_timeline_create(herdt_plan_t* plan, int n_ticks, int m_max, const int8
     if (!t) { set_error("out of host memory"); return LIPM_E_INVALID; }
     std::memset(t, 0, sizeof(*t));
     t->plan = plan; t->n_ticks = n_ticks; t->m_pad = m_pad; t->n = n; t->NP = NP;
+    t->prev_tick = -1;
     t->nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
     t->h_m = new int32_t[n_ticks];
     std::memcpy(t->h_m, m_per_tick, sizeof(int32_t) * n_ticks);
@@ -734,7 +749,7 @@ int herdt_timeline_create(herdt_plan_t* plan, int n_ticks, int m_max, const int8
 
 void herdt_timeline_destroy(herdt_timeline_t* t) {
     if (!t) return;
-    void* ptrs[] = {t->d_phase, t->d_kind, t->d_frag, t->d_q, t->d_lo, t->d_hi, t->d_t0, t->d_sol};
+    void* ptrs[] = {t->d_phase, t->d_kind, t->d_frag, t->d_q, t->d_lo, t->d_hi, t->d_t0, t->d_sol, t->d_tprev};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete[] t->h_m;
     delete t;
@@ -742,8 +757,8 @@ void herdt_timeline_destroy(herdt_timeline_t* t) {
 
 int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const double* y, const double* fc,
                const double* air, const double* spread, const double* vref, int vref_batch, int n_ext, int foot_side,
-               const double* poly_verts, int n_verts, double* next_x, double* next_y, double* f1, double* solution,
-               int32_t* status, int32_t* iters, void* stream_) {
+               const double* poly_verts, int n_verts, int warm, double* next_x, double* next_y, double* f1,
+               double* solution, int32_t* status, int32_t* iters, void* stream_) {
     if (!t || tick < 0 || tick >= t->n_ticks) { set_error("herdt_tick: bad timeline / tick"); return LIPM_E_INVALID; }
     if (B < 0 || !x || !y || !fc || !vref || !next_x || !next_y) { set_error("herdt_tick: missing argument"); return LIPM_E_INVALID; }
     if (B == 0) return LIPM_OK;
@@ -756,14 +771,17 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
     const herdt_plan_desc_t& d = plan->desc;
     const int N = plan->N, NP = t->NP, ncols = 2 * B;
     if (ncols > t->cap_cols) {
-        void* ptrs[] = {t->d_q, t->d_lo, t->d_hi, t->d_t0, t->d_sol};
+        void* ptrs[] = {t->d_q, t->d_lo, t->d_hi, t->d_t0, t->d_sol, t->d_tprev};
         for (void* q : ptrs) if (q) cudaFree(q);
         const size_t bytes = sizeof(double) * (size_t)ncols * NP;
         LIPM_CUDA_TRY(cudaMalloc(&t->d_q, bytes)); LIPM_CUDA_TRY(cudaMalloc(&t->d_lo, bytes));
         LIPM_CUDA_TRY(cudaMalloc(&t->d_hi, bytes)); LIPM_CUDA_TRY(cudaMalloc(&t->d_t0, bytes));
-        LIPM_CUDA_TRY(cudaMalloc(&t->d_sol, bytes));
+        LIPM_CUDA_TRY(cudaMalloc(&t->d_sol, bytes)); LIPM_CUDA_TRY(cudaMalloc(&t->d_tprev, bytes));
         t->cap_cols = ncols;
+        t->prev_tick = -1;
     }
+    // warm start only from the tick just before, for the same batch
+    const bool use_prev = warm != 0 && tick > 0 && t->prev_tick == tick - 1 && t->prev_cols == ncols;
     TickParams P;
     P.N = N; P.m_pad = t->m_pad; P.NP = NP; P.m = m; P.B = B; P.tick = tick; P.n_ext = n_ext; P.vref_batch = vref_batch;
     P.foot_side = foot_side;
@@ -774,6 +792,9 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
     P.tcol = plan->d_t; P.vcol = plan->d_v;
     P.x = x; P.y = y; P.fc = fc; P.vref = vref;
     P.q = t->d_q; P.lo = t->d_lo; P.hi = t->d_hi; P.t0 = t->d_t0;
+    P.t_prev = use_prev ? t->d_tprev : nullptr;
+    P.shift_f = warm == 2 ? 1 : 0;
+    P.m_prev = use_prev ? t->h_m[tick - 1] : 0;
     k_herdt_prepare<<<ncols, 128, sizeof(double) * 6 * N, stream>>>(P);
     LIPM_CUDA_TRY(cudaGetLastError());
 
@@ -784,6 +805,8 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
     Q.mfrag = t->d_frag + (size_t)tick * t->nfrag;
     Q.q = t->d_q; Q.lo = t->d_lo; Q.hi = t->d_hi; Q.t0 = t->d_t0; Q.sol = solution ? solution : t->d_sol;
     Q.status = status; Q.iters = iters;
+    Q.t_out = t->d_tprev;        // prepare has consumed the previous iterate (stream order)
+    t->prev_tick = tick; t->prev_cols = ncols;
     Q.poly_shift = fc;
     Q.n_verts = m > 0 ? n_verts : 0;
     for (int i = 0; i < kMaxPolyVerts; ++i) {

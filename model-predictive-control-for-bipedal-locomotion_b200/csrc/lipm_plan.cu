@@ -214,6 +214,40 @@ __global__ void k_pack_f16(int N, const double* __restrict__ M, const double* __
     *reinterpret_cast<__half*>(img + kF16OperandBytesB + off) = lo;
 }
 
+// Largest eigenvalue of the symmetric positive definite G by power iteration (one CTA; N <= 4096).
+__global__ void k_power_iteration(int N, const double* __restrict__ G, int iterations, double* __restrict__ scratch,
+                                  double* __restrict__ lambda_out) {
+    __shared__ double red[32];
+    __shared__ double norm;
+    double* x = scratch;
+    double* y = scratch + N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) x[i] = 1.0 + 1e-3 * (i % 7);
+    __syncthreads();
+    double lambda = 0.0;
+    for (int it = 0; it < iterations; ++it) {
+        double part = 0.0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            double acc = 0.0;
+            for (int j = 0; j < N; ++j) acc = fma(G[(size_t)i * N + j], x[j], acc);
+            y[i] = acc;
+            part = fma(acc, acc, part);
+        }
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+            norm = sqrt(s);
+        }
+        __syncthreads();
+        lambda = norm;                                 // |G x| with |x| = 1 (after the first pass)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) x[i] = y[i] / norm;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *lambda_out = lambda;
+}
+
 int invert_shifted(lipm_plan* plan, double diag, double* d_out) {
     const int N = plan->N;
     const size_t nn = (size_t)N * N;
@@ -266,9 +300,22 @@ int build_plan_matrices(lipm_plan* plan) {
     k_gpx<<<(NP + 127) / 128, 128>>>(N, NP, plan->d_g, plan->d_px, plan->d_gpx);
     LIPM_CUDA_TRY(cudaGetLastError());
 
+    if (!(plan->desc.rho > 0)) {
+        // ADMM penalty from the spectrum of H = Q I + G: rho = sqrt(lambda_min lambda_max) = sqrt(Q (Q + lambda_max(G))).
+        // For N <= 160 this is 2.9 and the tuned 2.0 is kept (lipm_api.cu); cond(H) grows to 28 (N=300) and 110
+        // (N=600), where rho = 2 needs 1.6x / 3x the iterations of this rule.
+        double* d_scratch = nullptr;
+        LIPM_CUDA_TRY(cudaMalloc(&d_scratch, sizeof(double) * (2 * (size_t)N + 1)));
+        k_power_iteration<<<1, 1024>>>(N, plan->d_g, 60, d_scratch, d_scratch + 2 * N);
+        double lambda_max = 0.0;
+        LIPM_CUDA_TRY(cudaMemcpy(&lambda_max, d_scratch + 2 * N, sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(d_scratch);
+        if (!(lambda_max > 0.0) || !std::isfinite(lambda_max)) { set_error("power iteration on G failed"); return LIPM_E_NUMERIC; }
+        plan->desc.rho = std::sqrt(d.Q * (d.Q + lambda_max));
+    }
     int rc = invert_shifted(plan, d.Q, plan->d_hinv);
     if (rc != LIPM_OK) return rc;
-    rc = invert_shifted(plan, d.Q + d.rho, plan->d_minv);
+    rc = invert_shifted(plan, d.Q + plan->desc.rho, plan->d_minv);
     if (rc != LIPM_OK) return rc;
 
     const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;

@@ -350,7 +350,7 @@ def _herdt_lib() -> ctypes.CDLL:
         lib.herdt_timeline_destroy.restype = None
         lib.herdt_timeline_size.argtypes = [vp]
         lib.herdt_timeline_size.restype = i32
-        lib.herdt_tick.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.herdt_tick.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.herdt_tick.restype = i32
         lib._herdt_ready = True
     return lib
@@ -422,7 +422,8 @@ class HerdtTimeline:
 
     def tick(self, i: int, x: torch.Tensor, y: torch.Tensor, fc: torch.Tensor, vref: torch.Tensor, foot_side: int,
              poly_verts: Optional[np.ndarray], *, air: Optional[torch.Tensor] = None,
-             spread: Optional[torch.Tensor] = None, want_solution: bool = False) -> Dict[str, torch.Tensor]:
+             spread: Optional[torch.Tensor] = None, warm: int = 0,
+             want_solution: bool = False) -> Dict[str, torch.Tensor]:
         """``predict_herdt_joint`` for B scenarios (device tensors in, device tensors out)."""
         dev = self.plan.device
         B = x.shape[0]
@@ -438,7 +439,7 @@ class HerdtTimeline:
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(self._lib.herdt_tick(self._handle, int(i), B, x.data_ptr(), y.data_ptr(), fc.data_ptr(), _ptr(air),
                                     _ptr(spread), vref.data_ptr(), vref_batch, n_ext, int(foot_side), None if verts is None else verts.ctypes.data,
-                                    0 if verts is None else len(verts), nx.data_ptr(), ny.data_ptr(), f1.data_ptr(),
+                                    0 if verts is None else len(verts), int(warm), nx.data_ptr(), ny.data_ptr(), f1.data_ptr(),
                                     _ptr(sol), status.data_ptr(), iters.data_ptr(), stream))
         out = {"next_x": nx, "next_y": ny, "f1": f1, "status": status, "iters": iters}
         if want_solution:

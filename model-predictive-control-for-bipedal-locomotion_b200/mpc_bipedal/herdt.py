@@ -49,6 +49,7 @@ class TimelineLayout:
     current: np.ndarray          # (n-1,) state the controller is in at each tick
     foot_side: np.ndarray        # (n-1,) 0 left / 1 right at each tick
     commit: np.ndarray           # (n-1,) bool: the tick leaves SINGLE_SUPPORT (footstep is committed, side toggles)
+    new_run: np.ndarray          # (n-1,) bool: the current support run started at this tick
     phase_of_row: np.ndarray     # (n-1, N) int8
     row_kind: np.ndarray         # (n-1, N) int8
     m: np.ndarray                # (n-1,) int32
@@ -65,6 +66,7 @@ def timeline_layout(state_ref, horizon: int) -> TimelineLayout:
     phase = np.zeros((ticks, N), np.int8)
     kind = np.zeros((ticks, N), np.int8)
     m = np.zeros(ticks, np.int32)
+    new_run = np.zeros(ticks, bool)
     cur, foot = int(ext[0]), 0                       # reference :459, :457 ("left")
     for i in range(ticks):
         window = ext[i + 1: i + 1 + N]
@@ -86,8 +88,10 @@ def timeline_layout(state_ref, horizon: int) -> TimelineLayout:
             commit[i] = True
             foot = 1 - foot
         if nxt != cur:                               # :524-525
+            if i + 1 < ticks and not (cur == DOUBLE_SUPPORT and nxt == SINGLE_SUPPORT):
+                new_run[i + 1] = True                # the first future phase becomes the current one
             cur = nxt
-    return TimelineLayout(ext, current, side, commit, phase, kind, m)
+    return TimelineLayout(ext, current, side, commit, new_run, phase, kind, m)
 
 
 def polygon_vertices(polytope) -> np.ndarray:
@@ -101,12 +105,13 @@ def polygon_vertices(polytope) -> np.ndarray:
 class HerdtBatch:
     """Batched ``generate_com_trajectory_herdt`` for scenarios sharing one state timeline."""
 
-    def __init__(self, config, state_ref, nb_steps, *, solver_options: Optional[dict] = None):
+    def __init__(self, config, state_ref, nb_steps, *, solver_options: Optional[dict] = None, warm_start: bool = True):
         from . import engine
 
         self.config = config
         self.layout = timeline_layout(state_ref, config.horizon)
         self.nb_steps = nb_steps          # find_nb_steps of the PADDED timeline (reference :471)
+        self.warm_start = warm_start      # the reference cold-starts every tick; the optimum is the same
         opts = solver_options or {}
         self.plan = engine.HerdtPlan(config.horizon, config.h, config.g, config.dt, config.alpha, config.beta,
                                      config.gamma, config.foot_length, config.foot_width, config.foot_spread, **opts)
@@ -155,7 +160,8 @@ class HerdtBatch:
             side = int(lay.foot_side[i])
             has_step = lay.m[i] > 0
             out = self.timeline.tick(i, x, y, fc, vref, side, self.polygons[side] if has_step else None,
-                                     air=air.contiguous(), spread=spread)
+                                     air=air.contiguous(), spread=spread,
+                                     warm=0 if (i == 0 or not self.warm_start) else (2 if lay.new_run[i] else 1))
             x, y = out["next_x"], out["next_y"]
             if has_step:
                 air = air + (1.0 / self.nb_steps[i][0]) * (out["f1"] - air)      # :495-498
