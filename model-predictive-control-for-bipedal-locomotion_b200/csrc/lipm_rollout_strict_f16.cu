@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                     // tcgen05.ld / st are warp-collective: the warp runs the epilogue while any of its
                     // columns is still iterating; converged columns keep t (and republish the same r)
                     if (__any_sync(0xffffffffu, !done)) {
+                        const float relax = done ? 0.f : P.alpha;      // a converged column keeps its t (and republishes the same r)
 #pragma unroll
                         for (int ch = 0; ch < kChunks; ++ch) {
                             if (part == kParts - 1 && ch == kChunks - 1) continue;
@@ -409,9 +410,9 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                                 const float t = __uint_as_float(vt[e]), l = __uint_as_float(vl[e]), h = hi[ch * 8 + e];
                                 const float zo = clipf(t, l, h);
                                 const float dd = __uint_as_float(vd[e]) - zo;
-                                const float tn = done ? t : fmaf(P.alpha, dd, t);   // alpha v + (1 - alpha) zo + (t - zo)
+                                const float tn = fmaf(relax, dd, t);        // alpha v + (1 - alpha) zo + (t - zo)
                                 const float zn = clipf(tn, l, h);
-                                rd = max(rd, done ? 0u : __float_as_uint(fabsf(dd)));
+                                rd = max(rd, __float_as_uint(fabsf(dd)));
                                 vt[e] = __float_as_uint(tn);
                                 r[e] = fmaf(P.qhalf, l + h, fmaf(P.two_rho, zn, -P.rho * tn));
                             }
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                             publish_rhs(sAh, sAl, part * kChunks + ch, s, r);
                         }
                         tmem_wait_st();
+                        rd = done ? 0u : rd;
                     }
                     S.Res[part][s] = rd;
                     proxy_fence();

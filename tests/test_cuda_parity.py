@@ -483,3 +483,27 @@ def test_param_sweep_matches_individual_walks(engine, default_config):
                                                                  F_ext=[one.F_ext], m=[one.m], force_tick=tick)
         assert int(res["iters"].sum()) == int(out["iters"][k])                    # same solves, iteration for iteration
         assert bool(res["fell"][0]) == bool(out["fell"][k])
+
+
+@pytest.mark.parametrize("N", [24, 100, 128, 152])
+def test_reduced_other_horizons_against_fp64_path(engine, N):
+    """Every horizon the reduced-precision tile serves (zero-padded to 160): solution within 1e-4 m of the FP64
+    path of the same library, feasible after the FP64 clamp, far fewer iterations, bit-identical when repeated."""
+    rng = np.random.default_rng(21 + N)
+    fp64 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    f16 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
+    cases = 300                      # more than two 128-column units: partial last unit
+    x = rng.normal(size=(cases, 3)) * np.array([0.05, 0.1, 0.5])
+    centre = rng.uniform(-0.05, 0.05, size=(cases, 1)) + np.cumsum(
+        (rng.random((cases, N)) < 0.04) * rng.uniform(-0.1, 0.1, size=(cases, N)), axis=1)
+    lo, hi = centre - 0.055, centre + 0.055
+    want = fp64.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    got = f16.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    assert (got["status"].cpu().numpy() == 0).all()
+    z, zw = got["zmp_plan"].cpu().numpy(), want["zmp_plan"].cpu().numpy()
+    assert np.max(np.abs(z - zw)) < TOL_REDUCED_M
+    assert (z >= lo).all() and (z <= hi).all()
+    assert np.max(np.abs(got["next_state"].cpu().numpy()[:, 0] - want["next_state"].cpu().numpy()[:, 0])) < TOL_REDUCED_M
+    assert got["iters"].sum().item() < want["iters"].sum().item()
+    again = f16.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    assert np.array_equal(again["zmp_plan"].cpu().numpy(), z)

@@ -159,3 +159,30 @@ def test_herdt_walk_matches_oracle(herdt_case, golden):
     # every committed footstep lies in the reachable polygon of the previous one (reference check :814-823)
     lay_commit = np.where(np.any(np.diff(res["foot_hist"][0], axis=0) != 0, axis=1))[0]
     assert len(lay_commit) == 8
+
+
+@pytest.mark.gpu
+def test_predict_herdt_joint_reference_signature(herdt_case):
+    """The reference's 13-argument call (zmp_controller.py:533-547) on the mirrored controller."""
+    from mpc_bipedal.controllers import ZMPController
+    from mpc_bipedal.generators.cop_generator import State
+
+    c = herdt_case
+    cfg, N = c["cfg"], c["cfg"].horizon
+    ctrl = ZMPController(cfg)
+    names = np.array([State.STANDING, State.DOUBLE_SUPPORT, State.SINGLE_SUPPORT], dtype=object)
+    ext = np.concatenate([c["states"], np.repeat(c["states"][-1:], N)])
+    v_ext = np.vstack([c["v_ref"], np.repeat(c["v_ref"][-1:], N, 0)])
+    i = 60
+    x, y = np.array([[0.01], [0.2], [0.0]]), np.array([[0.03], [0.0], [-0.1]])
+    out = ctrl.predict_herdt_joint(x, y, v_ext[i + 1: i + 1 + N], np.array([[0.0]]), np.array([[0.1]]), names[ext[i]],
+                                   names[ext[i + 1: i + 1 + N]], N, tuple(c["nb"][i]), np.array([[0.0]]),
+                                   np.array([[0.1]]), "left", i)
+    xn, yn, fx1, fy1, u, lam, info = ho.predict_joint(cfg, c["A"], c["B"], x, y, v_ext[i + 1: i + 1 + N], 0.0, 0.1,
+                                                      int(ext[i]), ext[i + 1: i + 1 + N], "left", c["polys"]["left"])
+    assert info["kkt"]["ok"]
+    assert out[0].shape == (3, 1) and out[1].shape == (3, 1)
+    assert (np.abs(out[0][:, 0] - xn) < [1e-9, 1e-9, 2e-7]).all() and (np.abs(out[1][:, 0] - yn) < [1e-9, 1e-9, 2e-7]).all()
+    assert abs(out[2] - fx1) < 1e-7 and abs(out[3] - fy1) < 1e-7
+    with pytest.raises(ValueError):
+        ctrl.generate_com_trajectory(x, y)                  # herdt needs v_ref and state_ref (reference :53-54)

@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--horizons", type=int, nargs="+", default=[100, 150, 300, 600])
     ap.add_argument("--timed", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--precision", choices=["fp64", "f16x3"], default="fp64",
+                    help="strict-mode arithmetic (f16x3: tcgen05 path, horizons <= 152 only)")
     args = ap.parse_args()
 
     import torch
@@ -54,7 +56,11 @@ def main():
     dev = torch.device("cuda", 0)
     rows = []
     for N in args.horizons:
-        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+        reduced = args.precision == "f16x3"
+        if reduced and N > engine.load_library().lipm_max_reduced_horizon():
+            print(json.dumps({"horizon": N, "mode": "strict", "precision": "f16x3", "skipped": "beyond the reduced-precision kernel's horizon limit"}), flush=True)
+            continue
+        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=engine.PRECISION_F16X3 if reduced else engine.PRECISION_FP64)
         x, lo, hi = tick_inputs(N, args.batch)
         xd, lod, hid = (torch.as_tensor(a).to(dev) for a in (x, lo, hi))
         for mode, name in ((engine.MODE_UNCONSTRAINED, "unconstrained"), (engine.MODE_STRICT, "strict")):
@@ -71,12 +77,12 @@ def main():
                 times.append(e0.elapsed_time(e1))
             iters = int(res["iters"].sum().item())
             ms = float(np.median(times))
-            row = {"horizon": N, "mode": name, "batch": args.batch, "ms_per_tick_p50": ms,
+            row = {"horizon": N, "mode": name, "precision": args.precision if mode == engine.MODE_STRICT else "fp64", "batch": args.batch, "ms_per_tick_p50": ms,
                    "solves_per_s": args.batch / (ms * 1e-3), "cold_start": True,
                    "mean_iters_per_solve": iters / args.batch,
                    "not_converged": int((res["status"] != 0).sum().item())}
             if mode == engine.MODE_STRICT:
-                row["tflops_fp64"] = 2.0 * N * N * iters / (ms * 1e-3) / 1e12
+                row["algorithmic_tflops"] = 2.0 * N * N * iters / (ms * 1e-3) / 1e12
             rows.append(row)
             print(json.dumps(row), flush=True)
     if args.out:
