@@ -350,7 +350,9 @@ def run_ours(args, rank, world, local_rank):
                                 "useful_column_slot_fraction": iters / max(slots * stats["group_iterations"], 1)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "api": "ZMPController.generate_com_trajectory_batched (NumPy in, NumPy out)"},
-            "gpu_launches": args.steps,
+            # per timed step: k_order_keys + k_unit_work + the rollout kernel (the CUB sort passes between them
+            # are library kernels and not counted)
+            "gpu_launches": 3 * args.steps if mode == engine.MODE_STRICT else args.steps,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic,

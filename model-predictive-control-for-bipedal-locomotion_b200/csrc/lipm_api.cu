@@ -215,9 +215,22 @@ int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const in
         if (rc != LIPM_OK) return rc;
     }
     cb.order = order;
+    // longest-expected-first dispatch of the kernel's work units (8 columns FP64, 128 columns reduced precision)
+    int* unit_order = nullptr;
+    {
+        const int width = plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : 8;
+        const int units = (cb.ncols + width - 1) / width;
+        if (units > 1 && impulse && force_tick) {
+            const int rc_u = build_unit_order(units, width, cb.ncols, B, order, n_max, n_steps, impulse, force_tick, &unit_order,
+                                              (cudaStream_t)stream);
+            if (rc_u != LIPM_OK) return rc_u;
+        }
+    }
+    cb.unit_order = unit_order;
     const int rc = plan->desc.precision == LIPM_PRECISION_F16X3 ? launch_strict_rollout_f16(plan, cb, (cudaStream_t)stream)
                                                                 : launch_strict_rollout(plan, cb, (cudaStream_t)stream);
     if (order) cudaFreeAsync(order, (cudaStream_t)stream);
+    if (unit_order) cudaFreeAsync(unit_order, (cudaStream_t)stream);
     return rc;
 }
 

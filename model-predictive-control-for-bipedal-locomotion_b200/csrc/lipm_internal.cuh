@@ -88,6 +88,7 @@ struct ColumnBatch {
     int ncols;              // number of columns (2B for walks, B for single ticks)
     int B;                  // scenarios; column c -> slot c % B, axis c / B
     const int* order;       // [B] scenario processed in each slot (nullptr: identity)
+    const int* unit_order;  // [units] dispatch order of the kernel's work units (nullptr: last unit first)
     int bounds_batch;       // 1 (shared), B (one series per scenario) or V (with bounds_index)
     const int32_t* bounds_index;  // [B] series used by each scenario, or nullptr
     long long bound_scn_stride;   // doubles between consecutive scenarios' bound series
@@ -116,6 +117,8 @@ struct ColumnBatch {
 
 int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
                            const int32_t* force_tick, int** perm_out, cudaStream_t stream);
+int build_unit_order(int num_units, int width, int ncols, int B, const int* order, int n_uniform, const int32_t* n_steps,
+                     const double* impulse, const int32_t* force_tick, int** unit_order_out, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
         group_sync<kGroupThreads>(bar_id);
         const unsigned int unit = (unsigned int)S.Unit[0];
         if (unit >= P.num_units) break;
-        const int col0 = (int)(P.num_units - 1u - unit) * kGroupCols;
+        const int col0 = (B.unit_order ? B.unit_order[unit] : (int)(P.num_units - 1u - unit)) * kGroupCols;
 
         if (gtid < kGroupCols) {
             const int c = col0 + gtid;

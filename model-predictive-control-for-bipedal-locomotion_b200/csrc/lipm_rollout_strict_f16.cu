@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
         __syncthreads();
         const unsigned int unit = (unsigned int)S.unit;
         if (unit >= P.num_units) break;
-        const int c = (int)(P.num_units - 1u - unit) * kF16Cols + s;
+        const int c = (B.unit_order ? B.unit_order[unit] : (int)(P.num_units - 1u - unit)) * kF16Cols + s;
 
         // column description (every part of a column decodes it; part 0 owns the outputs)
         const bool valid = c < B.ncols;
