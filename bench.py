@@ -113,17 +113,22 @@ def cpu_baseline(walks_per_thread=16, steps=1):
         oracle = COracle(150, native=True)           # -march=native, built on this host
     except Exception:
         oracle = COracle(150)                        # portable prebuilt (x86-64-v3)
-    threads = oracle.max_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently turn the
+    # baseline into a single-thread run)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     n_walks = walks_per_thread * threads
     cfg, z_max, z_min, F, tick = sweep_inputs(n_walks)
     zero = np.zeros((n_walks, 3))
     impulse = cfg.dt * F / cfg.m
     oracle.rollout(True, zero[:threads], zero[:threads], z_min, z_max, impulse=impulse[:threads],
-                   force_tick=tick[:threads])        # warm-up
+                   force_tick=tick[:threads], threads=threads)        # warm-up
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        res = oracle.rollout(True, zero, zero, z_min, z_max, impulse=impulse, force_tick=tick)
+        res = oracle.rollout(True, zero, zero, z_min, z_max, impulse=impulse, force_tick=tick, threads=threads)
         times.append(time.perf_counter() - t0)
     assert (res["status"] == 0).all()
     solves = n_walks * 2 * (len(z_min) - 1)

@@ -37,7 +37,13 @@ def main(argv=None):
     config = base_config(args.config)
     table = sweeps.make_sweep(args.scenarios, seed=args.seed)
     precision = 1 if args.precision == "f16x3" else 0
+    # warm-up: CUDA context, kernel images, plans of this rank's CoM heights, the first collective
+    warm = sweeps.make_sweep(min(len(table), 64 * world), seed=args.seed)
+    parallel.gather_outcomes(sweeps.run_shard(config, warm, rank, world, strict=not args.non_strict, precision=precision)["record"],
+                             len(warm), rank, world)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     local = sweeps.run_shard(config, table, rank, world, strict=not args.non_strict, precision=precision)
     gathered = parallel.gather_outcomes(local["record"], len(table), rank, world)
