@@ -159,6 +159,19 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
  */
 int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out);
 
+/*
+ * Footstep plans and ZMP bound series of V walk variants, generated on the device (one thread per variant):
+ * generate_footsteps (generators/footstep_generator.py:19-49) + CoPGenerator.generate_cop_trajectory
+ * (generators/cop_generator.py:73-115), bit-identical to the host generators (same floating-point clock).
+ *   distance, step_length, foot_spread   dev [V]
+ *   z_min, z_max   dev [V, n_max, 2];  states dev int8 [V, n_max] or NULL (0 STANDING, 1 DOUBLE, 2 SINGLE)
+ *   n_out          dev int32 [V]  samples of each series; -needed when a series does not fit n_max
+ * The table feeds lipm_rollout_indexed (bounds_index = variant of each scenario, n_steps = n_out[variant]).
+ */
+int lipm_generate_bounds(int V, const double* distance, const double* step_length, const double* foot_spread,
+                         double ssp_duration, double dsp_duration, double standing_duration, double dt, int n_max,
+                         double* z_min, double* z_max, int8_t* states, int32_t* n_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Herdt free-footstep MPC (method = "herdt"): ZMPController.predict_herdt_joint (zmp_controller.py:533-826)
  * for B scenarios that share a support timeline.  The rollout bookkeeping of

@@ -67,7 +67,8 @@ class ZMPController:
         velocity after tick ``force_tick`` (default ``n_steps // 2`` as the reference, :90).
         n_steps: (B,) int, bound samples per scenario (default: all n).
         Returns dict(com (B,n,2), x_hist, y_hist (B,n,3), zmp (B,n,2), flags (B,n,2) uint8,
-        max_violation (B,), fell (B,) bool, status (B,), iters (B,2)).
+        max_violation (B,), fell (B,) bool, status (B,), iters (B,2)).  With ``to_numpy`` the arrays are views
+        of page-locked staging buffers that are recycled every second call: copy what must live longer.
 
         ``fell`` is a definition of this build (the reference computes no outcome): the walk counts
         as a fall when the CoM gets further from the ZMP than ``h * tan(fall_angle_deg)``, i.e. the
@@ -95,7 +96,17 @@ class ZMPController:
             else:
                 tick = np.broadcast_to(np.asarray(force_tick, dtype=np.int32), (B,)).copy()
         mode = self._mode() if strict is None else (1 if strict else 0)
-        out = plan.rollout(mode, x_init, y_init, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick)
+        # device output buffers are kept between calls of the same shape (cleared: ragged walks leave the
+        # samples past their end untouched)
+        cache = getattr(self, "_rollout_buffers", None) if to_numpy else None    # device results are the caller's
+        if cache is not None:
+            for name in ("x_hist", "y_hist", "flags"):
+                if name in cache:
+                    cache[name].zero_()
+        out = plan.rollout(mode, x_init, y_init, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick,
+                           out=cache)
+        if to_numpy:
+            self._rollout_buffers = out
         x_hist, y_hist = out["x_hist"], out["y_hist"]
         c = torch.as_tensor(self.C, device=x_hist.device)
         com = torch.stack([x_hist[..., 0], y_hist[..., 0]], dim=-1)
@@ -112,7 +123,10 @@ class ZMPController:
             "iters": out["iters"],
         }
         if to_numpy:
-            res = engine.to_host(res)
+            # page-locked staging buffers are recycled: the arrays of a call stay valid until the call after next
+            if getattr(self, "_host_pool", None) is None:
+                self._host_pool = engine.HostPool()
+            res = engine.to_host(res, self._host_pool)
         return res
 
     # ------------------------------------------------------------------ single walk (reference :59-147)
@@ -133,13 +147,13 @@ class ZMPController:
         force_time = n_steps // 2
         print(f"Time of the external force: {(force_time * self.config.dt):.2f}s")
         res = self._single_walk(x_init, y_init, z_max, z_min, push=bool(self.config.add_force))
-        return res["com"][0], res["y_hist"][0][:, :, None]
+        return res["com"][0].copy(), res["y_hist"][0][:, :, None].copy()      # own memory, like the reference
 
     def generate_state_trajectory_wieber(self, x_init: np.ndarray, y_init: np.ndarray, z_max: np.ndarray,
                                          z_min: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """Full state histories ``(x_hist, y_hist)``, each (n,3,1); never pushes (reference :110-147)."""
         res = self._single_walk(x_init, y_init, z_max, z_min, push=False)
-        return res["x_hist"][0][:, :, None], res["y_hist"][0][:, :, None]
+        return res["x_hist"][0][:, :, None].copy(), res["y_hist"][0][:, :, None].copy()
 
     # ------------------------------------------------------------------ one tick (reference :149-201)
     def predict_wieber_axis(self, x_init: np.ndarray, nb_steps: int, z_max: np.ndarray, z_min: np.ndarray) -> np.ndarray:

@@ -36,7 +36,7 @@ LIBRARY_PATH = os.path.join(_PKG_ROOT, "_lib", "liblipm_mpc.so")
 EXPORTED_SYMBOLS = (
     "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout", "lipm_rollout_indexed",
     "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
-    "lipm_max_reduced_horizon",
+    "lipm_max_reduced_horizon", "lipm_generate_bounds",
     "herdt_plan_create", "herdt_plan_destroy", "herdt_plan_export_w", "herdt_timeline_create",
     "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick",
 )
@@ -96,6 +96,8 @@ def load_library() -> ctypes.CDLL:
     lib.lipm_version.restype = ctypes.c_char_p
     lib.lipm_max_strict_horizon.restype = i32
     lib.lipm_max_reduced_horizon.restype = i32
+    lib.lipm_generate_bounds.argtypes = [i32, vp, vp, vp, dbl, dbl, dbl, dbl, i32, vp, vp, vp, vp, vp]
+    lib.lipm_generate_bounds.restype = i32
     _lib = lib
     return lib
 
@@ -295,17 +297,62 @@ def get_plan(horizon: int, h: float, g: float, dt: float, Q: float, R: float, *,
     return plan
 
 
-def to_host(tensors: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
-    """Device -> host for a dict of result tensors: asynchronous copies into page-locked buffers
-    (torch's caching host allocator recycles them once the returned arrays are dropped), one
-    synchronisation for the whole set.  Pageable ``.cpu()`` copies were 2/3 of the end-to-end time."""
+def generate_bounds(config, distance, step_length, foot_spread, n_max: int, *, device: Optional[int] = None,
+                    want_states: bool = True) -> Dict[str, torch.Tensor]:
+    """Bound series of V walk variants generated on the device (``lipm_generate_bounds``): the batched, bit-exact
+    counterpart of ``CoPGenerator(config).generate_cop_trajectory()`` for per-variant (distance, step_length,
+    foot_spread); durations and dt come from ``config``.  Returns z_max, z_min (V, n_max, 2), states (V, n_max)
+    int8, n (V,) int32 -- ready for ``LipmPlan.rollout(..., bounds_index=..., n_steps=n[bounds_index])``."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("liblipm_mpc needs a CUDA device (B200 / sm_100a); there is no CPU path")
+    lib = load_library()
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+    d = _dev_tensor(np.asarray(distance, dtype=np.float64).reshape(-1), torch.float64, dev)
+    V = d.shape[0]
+    s = _dev_tensor(np.broadcast_to(np.asarray(step_length, dtype=np.float64), (V,)).copy(), torch.float64, dev)
+    f = _dev_tensor(np.broadcast_to(np.asarray(foot_spread, dtype=np.float64), (V,)).copy(), torch.float64, dev)
+    z_min = torch.zeros((V, n_max, 2), dtype=torch.float64, device=dev)
+    z_max = torch.zeros((V, n_max, 2), dtype=torch.float64, device=dev)
+    states = torch.zeros((V, n_max), dtype=torch.int8, device=dev) if want_states else None
+    n = torch.zeros((V,), dtype=torch.int32, device=dev)
+    _check(lib.lipm_generate_bounds(V, d.data_ptr(), s.data_ptr(), f.data_ptr(), float(config.ssp_duration),
+                                    float(config.dsp_duration), float(config.standing_duration), float(config.dt),
+                                    int(n_max), z_min.data_ptr(), z_max.data_ptr(), _ptr(states), n.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream))
+    return {"z_max": z_max, "z_min": z_min, "states": states, "n": n}
+
+
+class HostPool:
+    """Page-locked staging buffers for results, reused across calls (allocating 141 MB of pinned memory per
+    call costs more than the walk kernel itself and made the end-to-end time erratic).  Two generations
+    alternate, so the arrays handed out by a call stay valid until the call after the next one."""
+
+    def __init__(self, generations: int = 2):
+        self._slots = [dict() for _ in range(generations)]
+        self._turn = 0
+
+    def next_generation(self) -> dict:
+        slot = self._slots[self._turn]
+        self._turn = (self._turn + 1) % len(self._slots)
+        return slot
+
+
+def to_host(tensors: Dict[str, torch.Tensor], pool: Optional[HostPool] = None) -> Dict[str, np.ndarray]:
+    """Device -> host for a dict of result tensors: asynchronous copies into page-locked buffers, one
+    synchronisation for the whole set.  With a ``pool`` the buffers are recycled (see ``HostPool``: the
+    returned arrays are views that stay valid for two calls); without, they are allocated per call."""
     staged = {}
     stream = None
+    slot = pool.next_generation() if pool is not None else None
     for key, t in tensors.items():
         if key.startswith("_"):
             continue
         t = t.contiguous()
-        host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        host = slot.get(key) if slot is not None else None
+        if host is None or host.shape != t.shape or host.dtype != t.dtype:
+            host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            if slot is not None:
+                slot[key] = host
         host.copy_(t, non_blocking=True)
         staged[key] = host
         stream = torch.cuda.current_stream(t.device)

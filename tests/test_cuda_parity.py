@@ -507,3 +507,45 @@ def test_reduced_other_horizons_against_fp64_path(engine, N):
     assert got["iters"].sum().item() < want["iters"].sum().item()
     again = f16.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
     assert np.array_equal(again["zmp_plan"].cpu().numpy(), z)
+
+
+# ----------------------------------------------------------------------------- device-side generators
+def test_device_bound_generation_is_bit_identical(engine, default_config):
+    """lipm_generate_bounds against the host generators (which are pinned against the reference itself):
+    same samples, same state timeline, same bits -- including the irregular 24/25-sample single supports."""
+    from dataclasses import replace
+
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.generators import CoPGenerator
+    from mpc_bipedal.herdt import state_codes
+
+    rng = np.random.default_rng(4)
+    for base in (default_config, MPCConfig(), replace(default_config, horizon=100, dt=1.5 / 100, ssp_duration=0.31, dsp_duration=0.05)):
+        V = 40
+        distance = np.concatenate([[base.distance, 2.0, 0.29, 0.3, 0.61], rng.uniform(0.2, 3.0, V - 5)])
+        step = np.concatenate([[base.step_length, 0.33, 0.3, 0.3, 0.3], rng.uniform(0.15, 0.45, V - 5)])
+        spread = np.concatenate([[base.foot_spread, 0.1, 0.1, 0.1, 0.1], rng.uniform(0.07, 0.13, V - 5)])
+        out = engine.generate_bounds(base, distance, step, spread, n_max=900)
+        n = out["n"].cpu().numpy()
+        assert (n > 0).all()
+        z_max, z_min, states = (out[k].cpu().numpy() for k in ("z_max", "z_min", "states"))
+        for v in range(V):
+            cfg = replace(base, distance=float(distance[v]), step_length=float(step[v]), foot_spread=float(spread[v]))
+            want_max, want_min, want_states = CoPGenerator(cfg).generate_cop_trajectory(save_footsteps=False)
+            assert n[v] == len(want_max), (v, n[v], len(want_max))
+            assert np.array_equal(z_max[v, : n[v]], want_max) and np.array_equal(z_min[v, : n[v]], want_min), v
+            assert np.array_equal(states[v, : n[v]], state_codes(want_states)), v
+            assert not z_max[v, n[v]:].any()
+    short = engine.generate_bounds(default_config, [2.1], [0.3], [0.1], n_max=100)
+    assert short["n"].item() == -420                    # does not fit: reports the length it needs
+    # the generated table drives a sweep directly
+    plan = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6)
+    table = engine.generate_bounds(default_config, [2.1, 1.2], [0.3, 0.25], [0.1, 0.09], n_max=450)
+    idx = np.array([0, 1, 1, 0], np.int32)
+    zero = np.zeros((4, 3))
+    res = plan.rollout(engine.MODE_STRICT, zero, zero, table["z_min"], table["z_max"], n_steps=table["n"][idx].cpu().numpy(),
+                       bounds_index=idx)
+    z_max0, z_min0, _ = CoPGenerator(default_config).generate_cop_trajectory(save_footsteps=False)
+    alone = plan.rollout(engine.MODE_STRICT, zero[:1], zero[:1], z_min0, z_max0)
+    assert np.array_equal(res["y_hist"][0, :420].cpu().numpy(), alone["y_hist"][0].cpu().numpy())
+    assert np.array_equal(res["y_hist"][3].cpu().numpy(), res["y_hist"][0].cpu().numpy())
