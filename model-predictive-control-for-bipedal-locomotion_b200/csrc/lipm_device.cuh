@@ -101,6 +101,9 @@ __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aB
     b0 = bBase[0];
 #pragma unroll
     for (int r = 0; r < NR; ++r) a0[r] = lda(r * aStride);
+    // With a single row block the two DMMAs of a trip would form one dependent chain on the same accumulator;
+    // odd K blocks then go to a second accumulator (summed at the end).
+    double odd0 = 0.0, odd1 = 0.0;
     auto trip = [&](int kb) {
         b1 = bBase[(kb + 1) * 4];
 #pragma unroll
@@ -112,8 +115,12 @@ __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aB
 #pragma unroll
             for (int r = 0; r < NR; ++r) a0[r] = lda(r * aStride + (kb + 2) * 32);
         }
+        if (NR == 1) {
+            dmma884(odd0, odd1, a1[0], b1);
+        } else {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a1[r], b1);
+            for (int r = 0; r < NR; ++r) dmma884(acc[r][0], acc[r][1], a1[r], b1);
+        }
     };
     if (KBC > 0) {
 #pragma unroll
@@ -122,6 +129,7 @@ __device__ __forceinline__ void contract(double (&acc)[NRB][2], const double* aB
 #pragma unroll 1
         for (int kb = 0; kb < KB; kb += 2) trip(kb);     // KB = NP/4 is even: NP is a multiple of 8
     }
+    if (NR == 1) { acc[0][0] += odd0; acc[0][1] += odd1; }
 }
 template <int NR, int NRB, int KBC, bool STREAM>
 struct ContractDispatch {

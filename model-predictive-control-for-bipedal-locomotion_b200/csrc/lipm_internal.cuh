@@ -71,6 +71,7 @@ struct lipm_plan {
     double* d_hinv;       // [N,N] (Q I + G)^-1
     double* d_minv;       // [N,N] (Q I + G + rho I)^-1
     double* d_mfrag;      // [(NP/8) x (NP/4) x 32] ADMM matrix in DMMA A-fragment order
+    double* d_hfrag;      // same layout: H^-1 (dense unconstrained preview on the FP64 tensor pipe)
     double* d_gain;       // [N+3] kz, kx
     unsigned char* d_bf16; // [2 x kF16OperandBytesB] FP16 hi / lo images of [M | M G Px] (F16X3 plans only)
     int* d_info;          // [4] factorisation status words

@@ -320,6 +320,8 @@ int build_plan_matrices(lipm_plan* plan) {
 
     const size_t nfrag = (size_t)(NP / 8) * (NP / 4) * 32;
     k_pack_fragments<<<(unsigned)((nfrag + 255) / 256), 256>>>(N, NP, plan->d_minv, plan->d_mfrag);
+    LIPM_CUDA_TRY(cudaMalloc(&plan->d_hfrag, sizeof(double) * nfrag));
+    k_pack_fragments<<<(unsigned)((nfrag + 255) / 256), 256>>>(N, NP, plan->d_hinv, plan->d_hfrag);
     k_gain<<<1, 256>>>(N, d.Q, plan->pu00, plan->d_hinv, plan->d_gpx, plan->d_px, plan->d_gain);
     if (d.precision == LIPM_PRECISION_F16X3) {
         LIPM_CUDA_TRY(cudaMalloc(&plan->d_bf16, 2 * kF16OperandBytesB));

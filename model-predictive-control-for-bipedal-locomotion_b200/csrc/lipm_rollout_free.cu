@@ -9,6 +9,7 @@
 // the lanes of a warp) followed by the 3-state recursion.  The kernel is bandwidth/latency bound:
 // per solve it reads one new (z_min, z_max) sample (16 B) and writes the state (24 B) and a flag.
 #include "lipm_internal.cuh"
+#include "lipm_device.cuh"
 
 namespace lipm {
 
@@ -121,26 +122,112 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
     }
 }
 
-// Full unconstrained preview: zmp_plan[c] = H^-1 (Q zref + G Px x)  (one thread per (column, row)).
-__global__ void k_free_plan(int N, int ncols, int bounds_batch, double Q, const double* __restrict__ hinv,
-                            const double* __restrict__ gpx, const double* __restrict__ state,
-                            const double* __restrict__ z_min, const double* __restrict__ z_max,
-                            double* __restrict__ zmp_plan) {
-    extern __shared__ double rhs[];   // [N] right-hand side of this column
-    const int c = blockIdx.x;
-    if (c >= ncols) return;
-    const long long bz = bounds_batch == 1 ? 0 : c;
-    const double x0 = state[c * 3 + 0], x1 = state[c * 3 + 1], x2 = state[c * 3 + 2];
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        const double zref = (z_max[bz * N + j] + z_min[bz * N + j]) / 2;
-        rhs[j] = fma(Q, zref, fma(gpx[j * 3 + 2], x2, fma(gpx[j * 3 + 1], x1, gpx[j * 3 + 0] * x0)));
+// Full unconstrained preview of a batch: Z = H^-1 (Q Zref + G Px X), one dense [N x N] x [N x columns] product
+// on the FP64 tensor pipe (north_star: "a fixed factor followed by a batched solve over B right-hand sides";
+// H^-1 is formed once per plan from the Cholesky factor, so the batched solve is this product; 2 N^2 flops
+// per column).  Same organisation as the strict kernel: 4-warp groups of 8 columns, H^-1 in DMMA
+// fragment order -- resident in shared memory up to N = 160, read from L2 beyond.
+struct DenseParams {
+    int N, NP, ncols, bounds_batch;
+    double Q;
+    const double *hfrag, *gpx, *state, *z_min, *z_max;
+    double* zmp_plan;
+    unsigned int* tile_counter;
+    unsigned int num_units;
+};
+
+template <int NRB, int NG, bool STREAM>
+__global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_free_dense(const DenseParams P) {
+    constexpr int kGroupThreads = 32 * kRowGroups;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = P.N, NP = P.NP;
+    const int KB = NP / 4, RBLK = NP / 8, KP = NP + 4;
+    const int aStride = KB * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / kRowGroups, gtid = tid & (kGroupThreads - 1);
+    const int rg = warp & (kRowGroups - 1);
+    const int g = lane >> 2, t = lane & 3;
+    const int bar_id = 1 + grp;
+    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem_raw);
+    int* sUnit = reinterpret_cast<int*>(smem_raw + 16) + grp;
+    double* sR = reinterpret_cast<double*>(smem_raw + 64) + grp * (kGroupCols * KP);
+    const double* sM = STREAM ? P.hfrag : reinterpret_cast<double*>(smem_raw + 64) + NG * (kGroupCols * KP);
+    if (!STREAM) {
+        if (tid == 0) mbar_init(sBar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t m_bytes = (uint32_t)((size_t)RBLK * KB * 32 * sizeof(double));
+            mbar_expect_tx(sBar, m_bytes);
+            unsigned char* dst = reinterpret_cast<unsigned char*>(reinterpret_cast<double*>(smem_raw + 64) + NG * (kGroupCols * KP));
+            for (uint32_t off = 0; off < m_bytes; off += 32768) {
+                const uint32_t nb = (m_bytes - off < 32768u) ? (m_bytes - off) : 32768u;
+                bulk_load(dst + off, reinterpret_cast<const unsigned char*>(P.hfrag) + off, nb, sBar);
+            }
+        }
+        mbar_wait(sBar, 0);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        double acc = 0.0;
-        for (int j = 0; j < N; ++j) acc = fma(hinv[(size_t)j * N + i], rhs[j], acc);   // H^-1 symmetric
-        zmp_plan[(size_t)c * N + i] = acc;
+    int nrb = RBLK - rg * NRB;
+    nrb = nrb < 0 ? 0 : (nrb > NRB ? NRB : nrb);
+    const int row0 = rg * NRB * 8 + g;
+    const int lc0 = 2 * t;
+    const double* aBase = sM + (size_t)(rg * NRB) * aStride + lane;
+    const double* bBase = sR + g * KP + t;
+    double* rOut0 = sR + lc0 * KP + row0;
+    for (;;) {
+        group_sync<kGroupThreads>(bar_id);
+        if (gtid == 0) *sUnit = (int)atomicAdd(P.tile_counter, 1u);
+        group_sync<kGroupThreads>(bar_id);
+        const unsigned int unit = (unsigned int)*sUnit;
+        if (unit >= P.num_units) break;
+        const int col0 = (int)unit * kGroupCols;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = col0 + lc0 + e;
+            const bool live = c < P.ncols;
+            const long long bz = P.bounds_batch == 1 ? 0 : (live ? c : 0);
+            const double x0 = live ? P.state[(size_t)c * 3] : 0.0, x1 = live ? P.state[(size_t)c * 3 + 1] : 0.0,
+                         x2 = live ? P.state[(size_t)c * 3 + 2] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NRB; ++r) {
+                const int j = row0 + r * 8;
+                double rhs = 0.0;
+                if (live && r < nrb && j < N) {
+                    const double zref = (P.z_max[bz * N + j] + P.z_min[bz * N + j]) / 2;
+                    rhs = fma(P.Q, zref, fma(P.gpx[j * 3 + 2], x2, fma(P.gpx[j * 3 + 1], x1, P.gpx[j * 3] * x0)));
+                }
+                if (r < nrb) rOut0[e * KP + r * 8] = rhs;
+            }
+        }
+        group_sync<kGroupThreads>(bar_id);
+        double acc[NRB][2];
+#pragma unroll
+        for (int r = 0; r < NRB; ++r) acc[r][0] = acc[r][1] = 0.0;
+        ContractDispatch<NRB, NRB, 0, STREAM>::run(nrb, acc, aBase, aStride, bBase, KB);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = col0 + lc0 + e;
+            if (c >= P.ncols) continue;
+#pragma unroll
+            for (int r = 0; r < NRB; ++r) {
+                const int j = row0 + r * 8;
+                if (r < nrb && j < N) P.zmp_plan[(size_t)c * N + j] = acc[r][e];
+            }
+        }
     }
+}
+
+template <int NRB, int NG, bool STREAM>
+int launch_dense(lipm_plan* plan, DenseParams& P, cudaStream_t stream) {
+    const size_t nfrag = STREAM ? 0 : (size_t)(P.NP / 8) * (P.NP / 4) * 32;
+    const size_t smem = 64 + sizeof(double) * ((size_t)NG * kGroupCols * column_pitch(P.NP) + nfrag);
+    auto kernel = k_free_dense<NRB, NG, STREAM>;
+    LIPM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned ctas = (P.num_units + NG - 1) / NG;
+    const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
+    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
+    kernel<<<grid, 32 * kRowGroups * NG, smem, stream>>>(P);
+    LIPM_CUDA_TRY(cudaGetLastError());
+    return LIPM_OK;
 }
 
 // jerk_plan[c] = Pu^-1 (zmp_plan[c] - Px x): Pu^-1 is lower-triangular Toeplitz with first column t.
@@ -190,11 +277,28 @@ int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStr
 int launch_unconstrained_plan(lipm_plan* plan, int ncols, const double* state, const double* z_min,
                               const double* z_max, int bounds_batch, double* zmp_plan, cudaStream_t stream) {
     if (ncols <= 0) return LIPM_OK;
-    k_free_plan<<<ncols, 128, sizeof(double) * plan->N, stream>>>(plan->N, ncols, bounds_batch, plan->desc.Q,
-                                                                  plan->d_hinv, plan->d_gpx, state, z_min, z_max,
-                                                                  zmp_plan);
-    LIPM_CUDA_TRY(cudaGetLastError());
-    return LIPM_OK;
+    DenseParams P;
+    P.N = plan->N; P.NP = plan->NP; P.ncols = ncols; P.bounds_batch = bounds_batch;
+    P.Q = plan->desc.Q;
+    P.hfrag = plan->d_hfrag; P.gpx = plan->d_gpx; P.state = state; P.z_min = z_min; P.z_max = z_max;
+    P.zmp_plan = zmp_plan;
+    P.tile_counter = plan->d_tile_counter;
+    P.num_units = (unsigned)((ncols + kGroupCols - 1) / kGroupCols);
+    const int rblk = plan->NP / 8;
+    if (plan->N <= kMaxResidentHorizon) {
+        switch ((rblk + kRowGroups - 1) / kRowGroups) {
+            case 1: return launch_dense<1, 4, false>(plan, P, stream);
+            case 2: return launch_dense<2, 4, false>(plan, P, stream);
+            case 3: return launch_dense<3, 4, false>(plan, P, stream);
+            case 4: return launch_dense<4, 4, false>(plan, P, stream);
+            default: return plan->NP <= 152 ? launch_dense<5, 4, false>(plan, P, stream) : launch_dense<5, 2, false>(plan, P, stream);
+        }
+    }
+    const int nrb = (rblk + kRowGroups - 1) / kRowGroups;      // up to 20 row blocks per warp at N = 640
+    if (nrb <= 10) return launch_dense<10, 4, true>(plan, P, stream);
+    if (nrb <= 20) return launch_dense<20, 4, true>(plan, P, stream);
+    set_error("unconstrained preview: horizon %d exceeds the dense kernel's limit 640", plan->N);
+    return LIPM_E_UNSUPPORTED;
 }
 
 int launch_jerk_from_zmp(lipm_plan* plan, int ncols, const double* state, const double* zmp_plan,
