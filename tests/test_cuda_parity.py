@@ -549,3 +549,68 @@ def test_device_bound_generation_is_bit_identical(engine, default_config):
     alone = plan.rollout(engine.MODE_STRICT, zero[:1], zero[:1], z_min0, z_max0)
     assert np.array_equal(res["y_hist"][0, :420].cpu().numpy(), alone["y_hist"][0].cpu().numpy())
     assert np.array_equal(res["y_hist"][3].cpu().numpy(), res["y_hist"][0].cpu().numpy())
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_edge_cases(engine, plan150, plan150_f16):
+    import torch
+
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(4)
+    dev = plan150.device
+    # empty batch: a no-op that succeeds
+    empty = plan150.rollout(engine.MODE_STRICT, np.zeros((0, 3)), np.zeros((0, 3)), z_min[:30], z_max[:30])
+    assert empty["x_hist"].shape == (0, 30, 3)
+    # walks of 0, 1 and 2 samples inside a batch: nothing / nothing / one tick; the others are unaffected
+    n_steps = np.array([0, 1, 2, 30], np.int32)
+    zero = np.zeros((4, 3))
+    for plan in (plan150, plan150_f16):
+        out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min[:30], z_max[:30], n_steps=n_steps)
+        y = out["y_hist"].cpu().numpy()
+        assert not y[0].any() and not y[1].any() and not y[2, 2:].any()
+        alone = plan.rollout(engine.MODE_STRICT, zero[:1], zero[:1], z_min[:30], z_max[:30])
+        assert np.array_equal(alone["y_hist"][0].cpu().numpy(), y[3])
+        two = plan.rollout(engine.MODE_STRICT, zero[:1], zero[:1], z_min[:2], z_max[:2])
+        assert np.array_equal(two["y_hist"][0].cpu().numpy(), y[2, :2])
+    # degenerate box (z_min == z_max): the ZMP plan is the bound itself, both active bits are set
+    x = np.array([[0.01, 0.02, 0.0]])
+    line = np.full((1, 150), 0.02)
+    for plan, tol in ((plan150, 1e-12), (plan150_f16, 1e-12)):
+        res = plan.solve_tick(engine.MODE_STRICT, x, line, line, want_plan=True)
+        assert res["status"].item() == 0
+        assert np.max(np.abs(res["zmp_plan"].cpu().numpy() - 0.02)) <= tol
+    walk = plan150.rollout(engine.MODE_STRICT, zero[:1], zero[:1], np.zeros((20, 2)), np.zeros((20, 2)))
+    assert (walk["flags"][0, 1:].cpu().numpy() & 3 == 3).all()
+    # the smallest horizons
+    for N in (2, 3, 8):
+        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+        p = orc.Problem.make(N)
+        rng = np.random.default_rng(N)
+        xs = rng.normal(size=(9, 3)) * [0.02, 0.05, 0.1]
+        lo = rng.uniform(-0.06, -0.02, size=(9, N)); hi = lo + 0.08
+        res = plan.solve_tick(engine.MODE_STRICT, xs, lo, hi, want_plan=True)
+        for k in range(9):
+            _, want, _ = orc.strict_axis_exact(p, xs[k], hi[k], lo[k])
+            assert np.max(np.abs(res["zmp_plan"][k].cpu().numpy() - want)) < 1e-10, (N, k)
+        free = plan.solve_tick(engine.MODE_UNCONSTRAINED, xs, lo, hi, want_plan=True)
+        for k in range(9):
+            assert np.max(np.abs(free["next_state"][k].cpu().numpy() - orc.unconstrained_axis(p, xs[k], hi[k], lo[k]))) < 1e-9
+    # a QP that cannot converge within max_iter stops its walk there, like the reference raises (:193-194)
+    tight = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=3)
+    out = tight.rollout(engine.MODE_STRICT, zero[:2], zero[:2], z_min[:60], z_max[:60], impulse=[0.0, 0.2], force_tick=[5, 5])
+    status = out["status"].cpu().numpy()
+    flags = out["flags"].cpu().numpy()
+    assert status.max() == 1                                       # at most one failed tick per axis: the walk ends there
+    first_bad = np.argmax(flags[1, :, 1] & engine.FLAG_NOT_CONVERGED != 0)
+    assert first_bad > 0 and not out["y_hist"][1, first_bad + 1:].cpu().numpy().any()
+    from mpc_bipedal.controllers import ZMPController
+    ctrl = ZMPController(cfg)
+    ctrl.solver_options = {"max_iter": 3}
+    with pytest.raises(RuntimeError, match="QP solver did not find a solution"):
+        ctrl.generate_com_trajectory(np.zeros((3, 1)), np.zeros((3, 1)), z_max, z_min)
+    # bad arguments are rejected with a message, never a crash
+    with pytest.raises(ValueError, match="bounds batch"):
+        plan150.rollout(engine.MODE_STRICT, zero, zero, np.zeros((3, 30, 2)), np.zeros((3, 30, 2)))
+    with pytest.raises(ValueError):
+        plan150.solve_tick(engine.MODE_STRICT, zero, np.zeros((4, 149)), np.zeros((4, 149)))
+    with pytest.raises(engine.LipmError, match="mode"):
+        plan150.rollout(7, zero, zero, z_min[:30], z_max[:30])
