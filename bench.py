@@ -195,6 +195,58 @@ def measure_fp64_peak(torch, device, n=4096, reps=5):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def other_configs(torch, engine, device):
+    """BASELINE configs[2] (horizon scaling, one strict tick of 16384 problems) and configs[3] (Herdt, 2048 walks of
+    the class-default timeline) in one device-timed number each.  Not the headline: context for it."""
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import horizon_scaling
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.controllers import ZMPController
+    from mpc_bipedal.generators.speed_generation import SpeedTrajectoryGenerator
+
+    out = {}
+    B = 16384
+    for N in (300, 600):
+        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+        x, lo, hi = horizon_scaling.tick_inputs(N, B)
+        xd, lod, hid = (torch.as_tensor(a).to(device) for a in (x, lo, hi))
+        plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            res = plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / 3
+        iters = int(res["iters"].sum().item())
+        out[f"strict_tick_N{N}_fp64"] = {"batch": B, "ms_per_tick": ms, "solves_per_s": B / (ms * 1e-3),
+                                         "algorithmic_tflops": 2.0 * N * N * iters / (ms * 1e-3) / 1e12,
+                                         "mean_iters_per_solve": iters / B, "start": "cold"}
+    cfg = MPCConfig()
+    cfg.method = "herdt"
+    vx, vy, states = SpeedTrajectoryGenerator(cfg).generate_speed_and_state(save_footsteps=False)
+    v, st = np.stack([vx, vy], 1), np.array(states)
+    ctrl = ZMPController(cfg)
+    walks = 2048
+    zero = np.zeros((walks, 3))
+    ctrl.generate_com_trajectory_herdt_batched(zero[:8], zero[:8], v, st, to_numpy=False)      # builds the timeline
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    res = ctrl.generate_com_trajectory_herdt_batched(zero, zero, v, st, to_numpy=False)
+    torch.cuda.synchronize(device)
+    seconds = time.perf_counter() - t0
+    ticks = len(st) - 1
+    iters = int(res["iters"].sum().item())
+    n_var = cfg.horizon + 7
+    out["herdt_walks_fp64"] = {"walks": walks, "ticks": ticks, "seconds": seconds,
+                               "joint_qp_solves_per_s": walks * ticks / seconds,
+                               "mean_iters_per_joint_solve": iters / (walks * ticks),
+                               "algorithmic_tflops": 2.0 * 2.0 * n_var * n_var * iters / seconds / 1e12,
+                               "timing": "wall clock around the host-driven tick loop (one launch triple per tick)"}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -339,6 +391,11 @@ def run_ours(args, rank, world, local_rank):
     d2h = int(sum(v.nbytes for v in res.values()))
     e2e_value = world * solves_per_step / e2e_s.item()
 
+    # ---- the other BASELINE configs in one number each (single GPU run only; seconds, not minutes) ----------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = other_configs(torch, engine, device)
+
     if rank == 0:
         N = cfg.horizon
         kernel_s = np.mean(step_ms) * 1e-3
@@ -358,7 +415,12 @@ def run_ours(args, rank, world, local_rank):
                                 "useful_column_slot_fraction": iters / max(slots * stats["group_iterations"], 1)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "api": "ZMPController.generate_com_trajectory_batched (NumPy in, NumPy out)",
-                    "ms_per_call": [round(1e3 * c, 2) for c in e2e_calls]},
+                    "ms_per_call": [round(1e3 * c, 2) for c in e2e_calls],
+                    "median_ms_per_call": round(1e3 * float(np.median(e2e_calls)), 2),
+                    "host_loadavg": list(os.getloadavg()),
+                    "note": "value = mean over the calls (wall clock).  On a shared host single calls lose 0.1-0.6 s when the "
+                            "calling thread is descheduled (the device-timed steps are immune: the host runs ahead); "
+                            "the median call is what an undisturbed host sees"},
             # per timed step: k_order_keys + k_unit_work + the rollout kernel (the CUB sort passes between them
             # are library kernels and not counted)
             "gpu_launches": 3 * args.steps if mode == engine.MODE_STRICT else args.steps,
@@ -375,6 +437,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if reduced is not None:
             line["reduced_precision"] = reduced
+        if extras is not None:
+            line["other_configs"] = extras
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_baseline()
             line["cpu_baseline"] = base
@@ -393,6 +457,7 @@ def main():
     ap.add_argument("--mode", choices=["strict", "unconstrained"], default="strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-precision leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the one-number summaries of the other BASELINE configs")
     ap.add_argument("--precision", choices=["fp64", "f16x3"], default="fp64")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

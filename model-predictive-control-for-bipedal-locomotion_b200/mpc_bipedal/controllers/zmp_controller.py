@@ -108,7 +108,11 @@ class ZMPController:
         if to_numpy:
             self._rollout_buffers = out
         x_hist, y_hist = out["x_hist"], out["y_hist"]
-        c = torch.as_tensor(self.C, device=x_hist.device)
+        # C on the device, uploaded once: a host-to-device copy issued behind the walk kernel is a synchronous,
+        # spinning wait for the whole kernel
+        c = getattr(self, "_c_dev", None)
+        if c is None or c.device != x_hist.device:
+            c = self._c_dev = torch.as_tensor(self.C).to(x_hist.device)
         com = torch.stack([x_hist[..., 0], y_hist[..., 0]], dim=-1)
         zmp = torch.stack([x_hist @ c, y_hist @ c], dim=-1)                  # reference run_mpc.py:294
         lean = (com - zmp).abs().amax(dim=(1, 2))

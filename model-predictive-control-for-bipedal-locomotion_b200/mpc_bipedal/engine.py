@@ -357,7 +357,11 @@ def to_host(tensors: Dict[str, torch.Tensor], pool: Optional[HostPool] = None) -
         staged[key] = host
         stream = torch.cuda.current_stream(t.device)
     if stream is not None:
-        stream.synchronize()
+        # sleep until the copies are done instead of spinning: on a shared host a spinning waiter gets
+        # descheduled for hundreds of milliseconds now and then, a sleeping one is woken by the interrupt
+        done = torch.cuda.Event(blocking=True)
+        done.record(stream)
+        done.synchronize()
     return {k: v.numpy() for k, v in staged.items()}
 
 
