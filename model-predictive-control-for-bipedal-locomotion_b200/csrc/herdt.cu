@@ -481,6 +481,8 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
         }
 
         bool done[2] = {!live[0], !live[1]};
+        bool stalled = false;              // the pair stopped without converging (see below)
+        uint32_t checkpoint = 0xffffffffu; // residual (high word) 64 iterations ago
         int iters[2] = {0, 0};
         for (int k = 0; k < P.max_iter; ++k) {
             double acc[NRB][2];
@@ -538,7 +540,16 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
 #pragma unroll
                     for (int q4 = 1; q4 < kRowGroups; ++q4) cd[e] = max(cd[e], S.Res[0][q4][lc0 + e]);
                 }
-                const bool both = (cd[0] <= thr[0]) && (cd[1] <= thr[1]);
+                bool both = (cd[0] <= thr[0]) && (cd[1] <= thr[1]);
+                // A QP whose residual has not even halved over 64 iterations is not going to converge (the
+                // hull-in-front-of-the-CoM ticks of the final stance are infeasible in effect: ADMM's residual
+                // settles on a constant): stop the pair and report it as failed, like an iteration cap would --
+                // 64 iterations later instead of max_iter later.  A healthy solve contracts by 0.8-0.9 per iteration.
+                if (!both && (k & 63) == 63) {
+                    const uint32_t cur = max(cd[0], cd[1]);
+                    if (checkpoint != 0xffffffffu && cur + (1u << 20) > checkpoint) { stalled = true; both = true; }
+                    checkpoint = cur;
+                }
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (live[e]) { ++iters[e]; done[e] = both; }
@@ -563,7 +574,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
             }
             if (rg == 0 && g == 0) {
                 if (P.iters) P.iters[c] = iters[e];
-                if (P.status) P.status[c] = done[e] ? 0 : 1;
+                if (P.status) P.status[c] = (done[e] && !stalled) ? 0 : 1;
             }
         }
     }
