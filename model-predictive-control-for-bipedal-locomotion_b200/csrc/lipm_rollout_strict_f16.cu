@@ -361,6 +361,8 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
             __syncthreads();
             tc_fence_after();
             bool done = !live;
+            bool failed = false;               // stopped without converging (residual stalled far above the threshold)
+            uint32_t checkpoint = 0xffffffffu; // residual 32 iterations ago
             int iters = 0;
             {
                 uint32_t m = S.Qm[0][s];
@@ -436,6 +438,17 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                         for (int p4 = 1; p4 < kParts; ++p4) m = max(m, S.Res[p4][s]);
                         ++iters;
                         done = __uint_as_float(m) <= thr;
+                        // A column whose residual has not halved over 32 iterations while still 16x above its
+                        // threshold is not going to make it (a diverged walk: FP32 noise on a huge linear term);
+                        // give up now instead of dragging the 128-column unit to max_iter.  A healthy solve
+                        // contracts by ~0.55 per iteration.
+                        if (!done && (k & 31) == 31) {
+                            if (checkpoint != 0xffffffffu && m + (1u << 23) > checkpoint && __uint_as_float(m) > 16.f * thr) {
+                                done = true;
+                                failed = true;
+                            }
+                            checkpoint = m;
+                        }
                     }
                     mine = done;
                 }
@@ -499,7 +512,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                 viol = fmax(viol, fmax(fmax(below, above), 0.0));
                 unsigned f = (below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) | (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u) |
                              (act_lo ? LIPM_FLAG_ACTIVE_LO : 0u) | (act_hi ? LIPM_FLAG_ACTIVE_HI : 0u);
-                if (!done) { f |= LIPM_FLAG_NOT_CONVERGED; notconv += 1; }
+                if (!done || failed) { f |= LIPM_FLAG_NOT_CONVERGED; notconv += 1; }
                 if (i == ftick) n1 -= imp;
                 const long long sample = i + 1;
                 if (ph) {
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
             }
             // the reference raises at the first QP without a solution (zmp_controller.py:193-194): the walk of
             // this column ends here (every part of the column reaches the same verdict from the same residuals)
-            if (live && !done) nticks = i + 1;
+            if (live && (!done || failed)) nticks = i + 1;
             tc_fence_before();
             __syncthreads();              // the new state is visible to every part
             tc_fence_after();
