@@ -418,9 +418,7 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_call": [round(1e3 * c, 2) for c in e2e_calls],
                     "median_ms_per_call": round(1e3 * float(np.median(e2e_calls)), 2),
                     "host_loadavg": list(os.getloadavg()),
-                    "note": "value = mean over the calls (wall clock).  On a shared host single calls lose 0.1-0.6 s when the "
-                            "calling thread is descheduled (the device-timed steps are immune: the host runs ahead); "
-                            "the median call is what an undisturbed host sees"},
+                    "note": "value = mean over the calls (wall clock, NumPy in / NumPy out, all histories copied back)"},
             # per timed step: k_order_keys + k_unit_work + the rollout kernel (the CUB sort passes between them
             # are library kernels and not counted)
             "gpu_launches": 3 * args.steps if mode == engine.MODE_STRICT else args.steps,

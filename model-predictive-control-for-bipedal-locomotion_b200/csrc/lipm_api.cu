@@ -113,6 +113,17 @@ int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
         return LIPM_E_UNSUPPORTED;
     }
     plan->sm_count = prop.multiProcessorCount;
+    {
+        // The rollouts take their small scratch buffers (sort keys, dispatch order) from the stream-ordered
+        // allocator.  With the default release threshold (0) the pool hands its memory back to the driver at
+        // every synchronisation and maps it again on the next call; keep it cached instead.
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, d.device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     const int rc = build_plan_matrices(plan);
     if (rc != LIPM_OK) {
         free_plan_buffers(plan);

@@ -1,6 +1,6 @@
 """Device-side phase timing (CUDA events) of the end-to-end push sweep: upload + rollout / post-processing /
-device-to-host.  On this GPU pool the rollout is stable (190-230 ms) while the 141 MB device-to-host copy into
-page-locked memory takes anything between 3 ms and ~1 s (same data, same buffers, idle host)."""
+device-to-host.  This probe found the 0.1-1 s stalls of the result read-back that came from the stream-ordered
+memory pool being trimmed at every synchronisation (fixed in lipm_plan_create: release threshold raised)."""
 import os, sys, time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (REPO, os.path.join(REPO, "model-predictive-control-for-bipedal-locomotion_b200")):
