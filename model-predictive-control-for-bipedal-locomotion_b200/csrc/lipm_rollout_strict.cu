@@ -61,6 +61,11 @@ struct StrictParams {
     unsigned int* tile_counter;
     unsigned long long* stats;   // [0] group iterations executed (8 column slots each), [1] units
     unsigned int num_units;   // 8-column work units
+    unsigned int segments;    // each unit's walk is handed out in this many consecutive tick ranges ...
+    int seg_ticks;            // ... of this many ticks (load balance: the tail of a launch is one range deep)
+    int* seg_done;            // [num_units] ranges completed (release/acquire hand-over between groups)
+    double* seg_state;        // [num_units][seg_stride] iterate, axis state and running outcomes of a unit
+    size_t seg_stride;        // doubles
     int active_groups;        // debug: solver groups per CTA that take work (LIPM_STRICT_GROUPS)
     int debug_skip;           // debug (LIPM_STRICT_SKIP): 1 skip contraction, 2 skip epilogue math, 4 skip barrier, 8 never converge
     size_t nfrag;           // doubles in mfrag
@@ -163,9 +168,14 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
             S.Unit[1] = 0;
         }
         group_sync<kGroupThreads>(bar_id);
-        const unsigned int unit = (unsigned int)S.Unit[0];
-        if (unit >= P.num_units) break;
-        const int col0 = (B.unit_order ? B.unit_order[unit] : (int)(P.num_units - 1u - unit)) * kGroupCols;
+        // Queue entry = (tick range, unit): all first ranges come first, so the range a unit continues from
+        // was handed out num_units entries earlier, to a group that is running.
+        const unsigned int entry = (unsigned int)S.Unit[0];
+        if (entry >= P.num_units * P.segments) break;
+        const unsigned int seg = entry / P.num_units;
+        const unsigned int unit = entry - seg * P.num_units;
+        const int unit_id = B.unit_order ? B.unit_order[unit] : (int)(P.num_units - 1u - unit);
+        const int col0 = unit_id * kGroupCols;
 
         if (gtid < kGroupCols) {
             const int c = col0 + gtid;
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 x0 = s[0]; x1 = s[1]; x2 = s[2];
             }
             double viol = 0.0;
-            if (valid && B.write_initial && ticks > 0) {
+            if (valid && B.write_initial && ticks > 0 && seg == 0) {
                 const double zmp = x0 - P.hg * x2;
                 const double below = plo[0] - zmp, above = zmp - phi[0];
                 viol = fmax(fmax(below, above), 0.0);
@@ -210,8 +220,38 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
         group_sync<kGroupThreads>(bar_id);
         const int max_ticks = S.Unit[1];
         unsigned int group_iters = 0;
+        const int tick_begin = (int)seg * P.seg_ticks;
+        const int tick_end = (seg + 1u == P.segments || tick_begin + P.seg_ticks > max_ticks) ? max_ticks : tick_begin + P.seg_ticks;
+        if (seg > 0 && tick_begin >= max_ticks) continue;      // the walk ended in an earlier range
+        double* carry = P.seg_state + (size_t)unit_id * P.seg_stride;
+        if (seg > 0) {
+            // continue where the previous range of this unit stopped (elements are filed by row group: the
+            // warp that owns a row group differs between the solver groups of a CTA)
+            if (gtid == 0) {
+                const volatile int* ready = P.seg_done + unit_id;
+                while (*ready < (int)seg) __nanosleep(256);
+                __threadfence();
+            }
+            group_sync<kGroupThreads>(bar_id);
+#pragma unroll
+            for (int r = 0; r < NRB; ++r)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) tv[r][e] = __ldcg(carry + (r * 2 + e) * kGroupThreads + rg * 32 + lane);
+            if (gtid < kGroupCols) {
+                const double* c = carry + NRB * 2 * kGroupThreads;
+                S.X[gtid * 3 + 0] = __ldcg(c + gtid * 3 + 0);
+                S.X[gtid * 3 + 1] = __ldcg(c + gtid * 3 + 1);
+                S.X[gtid * 3 + 2] = __ldcg(c + gtid * 3 + 2);
+                S.Viol[gtid] = __ldcg(c + 3 * kGroupCols + gtid);
+                const int* ci = reinterpret_cast<const int*>(c + 4 * kGroupCols);
+                S.Iter[gtid] = __ldcg(ci + gtid);
+                S.NotConv[gtid] = __ldcg(ci + kGroupCols + gtid);
+                S.Nticks[gtid] = __ldcg(ci + 2 * kGroupCols + gtid);
+            }
+            group_sync<kGroupThreads>(bar_id);
+        }
 
-        for (int i = 0; i < max_ticks; ++i) {
+        for (int i = tick_begin; i < tick_end; ++i) {
             bool live[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) live[e] = i < S.Nticks[lc0 + e];
@@ -432,11 +472,34 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
             group_sync<kGroupThreads>(bar_id);
         }
 
-        // ---- per-column summaries -----------------------------------------------------------------
-        if (gtid == 0) {
-            atomicAdd(P.stats, (unsigned long long)group_iters);
-            atomicAdd(P.stats + 1, 1ull);
+        if (gtid == 0) atomicAdd(P.stats, (unsigned long long)group_iters);
+        if (tick_end < max_ticks) {
+            // ---- hand the unit over to whoever takes its next range ---------------------------------
+#pragma unroll
+            for (int r = 0; r < NRB; ++r)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) __stcg(carry + (r * 2 + e) * kGroupThreads + rg * 32 + lane, tv[r][e]);
+            if (gtid < kGroupCols) {
+                double* c = carry + NRB * 2 * kGroupThreads;
+                __stcg(c + gtid * 3 + 0, S.X[gtid * 3 + 0]);
+                __stcg(c + gtid * 3 + 1, S.X[gtid * 3 + 1]);
+                __stcg(c + gtid * 3 + 2, S.X[gtid * 3 + 2]);
+                __stcg(c + 3 * kGroupCols + gtid, S.Viol[gtid]);
+                int* ci = reinterpret_cast<int*>(c + 4 * kGroupCols);
+                __stcg(ci + gtid, S.Iter[gtid]);
+                __stcg(ci + kGroupCols + gtid, S.NotConv[gtid]);
+                __stcg(ci + 2 * kGroupCols + gtid, S.Nticks[gtid]);
+            }
+            __threadfence();
+            group_sync<kGroupThreads>(bar_id);
+            if (gtid == 0) {
+                *reinterpret_cast<volatile int*>(P.seg_done + unit_id) = (int)seg + 1;
+            }
+            continue;
         }
+
+        // ---- per-column summaries -----------------------------------------------------------------
+        if (gtid == 0) atomicAdd(P.stats + 1, 1ull);
         if (gtid < kGroupCols) {
             const int c = col0 + gtid;
             if (c < B.ncols) {
@@ -475,10 +538,35 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
     if (Q.num_units == 0) return LIPM_OK;
     const unsigned ctas = (Q.num_units + NG - 1) / NG;
     const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
+    // Tick ranges: with a few units per solver group the launch ends with groups idling for
+    // up to a whole walk; cutting the walks into ranges makes that tail one range deep.  The arithmetic of a
+    // walk does not depend on where it is cut.
+    const int max_ticks = P.cb.ticks_override > 0 ? P.cb.ticks_override : P.cb.n_max - 1;
+    const unsigned slots = grid * NG;
+    unsigned segments = 1;
+    if (Q.num_units > slots) segments = (16u * slots + Q.num_units - 1) / Q.num_units;
+    if (const char* env = std::getenv("LIPM_STRICT_SEGMENTS")) segments = (unsigned)std::atoi(env);
+    if (segments > 8u) segments = 8u;
+    if (max_ticks < 32 * (int)segments) segments = max_ticks >= 64 ? (unsigned)(max_ticks / 32) : 1u;
+    if (segments < 1u) segments = 1u;
+    Q.segments = segments;
+    Q.seg_ticks = max_ticks > 0 ? (max_ticks + (int)segments - 1) / (int)segments : 1;
+    Q.seg_stride = (size_t)NRB * 2 * 32 * RG + 6 * kGroupCols;
+    Q.seg_done = nullptr; Q.seg_state = nullptr;
+    void* carry = nullptr;
+    if (segments > 1) {
+        const size_t done_bytes = ((size_t)Q.num_units * sizeof(int) + 255) & ~(size_t)255;
+        const size_t bytes = done_bytes + (size_t)Q.num_units * Q.seg_stride * sizeof(double);
+        LIPM_CUDA_TRY(cudaMallocAsync(&carry, bytes, stream));
+        LIPM_CUDA_TRY(cudaMemsetAsync(carry, 0, done_bytes, stream));
+        Q.seg_done = static_cast<int*>(carry);
+        Q.seg_state = reinterpret_cast<double*>(static_cast<unsigned char*>(carry) + done_bytes);
+    }
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
     LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), stream));
     kernel<<<grid, 32 * RG * NG, smem, stream>>>(Q);
     LIPM_CUDA_TRY(cudaGetLastError());
+    if (carry) { LIPM_CUDA_TRY(cudaFreeAsync(carry, stream)); }
     return LIPM_OK;
 }
 

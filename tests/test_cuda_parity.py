@@ -199,6 +199,33 @@ def test_batch_results_do_not_depend_on_batch_layout(engine, plan150):
     assert np.array_equal(per["y_hist"].cpu().numpy(), sub["y_hist"])
 
 
+def test_tick_ranges_do_not_change_results(engine, monkeypatch):
+    """Load balancing hands a unit's walk out as consecutive tick ranges that different solver groups
+    continue (iterate, axis state and running outcomes travel through device memory).  Every split gives
+    the bits of the unsplit walk, ragged lengths and an aborted column included."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(29, seed=5)
+    n = 140
+    z_max, z_min = z_max[:n], z_min[:n]
+    n_steps = np.full(29, n, np.int32)
+    n_steps[[3, 11, 12]] = [35, 2, 97]
+    tick = (tick % 100 + 10).astype(np.int32)
+    zero = np.zeros((29, 3))
+    # 12 iterations are enough before the push and too few after a strong one: those columns stop at their
+    # first QP without a solution, in whatever range that happens
+    plan = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=12, eps=1e-9)
+    results = {}
+    for segments in (1, 2, 3, 4):
+        monkeypatch.setenv("LIPM_STRICT_SEGMENTS", str(segments))
+        out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick)
+        results[segments] = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+    monkeypatch.delenv("LIPM_STRICT_SEGMENTS")
+    failed = results[1]["status"].any(axis=1)
+    assert failed.any() and not failed.all(), failed
+    for segments in (2, 3, 4):
+        for key in ("x_hist", "y_hist", "flags", "iters", "max_violation", "status"):
+            assert np.array_equal(results[segments][key], results[1][key]), (segments, key)
+
+
 def test_ragged_walks(engine, plan150):
     """n_steps per scenario: each walk equals the same walk run alone on its truncated series;
     the last bound row is what gets repeated past the end (zmp_controller.py:81-88)."""
