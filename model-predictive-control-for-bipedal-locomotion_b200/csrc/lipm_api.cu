@@ -34,7 +34,7 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_tile_counter, p->d_stats, p->d_bf16};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_tile_counter, p->d_stats, p->d_bf16, p->d_f16s};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }
@@ -50,7 +50,7 @@ const char* lipm_last_error(void) { return g_error; }
 
 const char* lipm_version(void) { return "lipm_mpc 0.2 (sm_100a; fp64 DMMA ADMM, tcgen05 f16x3 ADMM, gain-row unconstrained)"; }
 
-int lipm_max_reduced_horizon(void) { return kMaxReducedHorizon; }
+int lipm_max_reduced_horizon(void) { return kMaxReducedStreamHorizon; }
 
 int lipm_max_strict_horizon(void) { return kMaxStrictHorizon; }
 
@@ -72,8 +72,8 @@ int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
         return LIPM_E_INVALID;
     }
     if (d.precision == LIPM_PRECISION_F16X3) {
-        if (d.horizon > kMaxReducedHorizon) {
-            set_error("precision F16X3: horizon %d exceeds the reduced-precision kernel's limit %d", d.horizon, kMaxReducedHorizon);
+        if (d.horizon > kMaxReducedStreamHorizon) {
+            set_error("precision F16X3: horizon %d exceeds the reduced-precision kernels' limit %d", d.horizon, kMaxReducedStreamHorizon);
             return LIPM_E_UNSUPPORTED;
         }
         if (!(d.eps > 0)) d.eps = 1e-5;
@@ -238,8 +238,7 @@ int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const in
         }
     }
     cb.unit_order = unit_order;
-    const int rc = plan->desc.precision == LIPM_PRECISION_F16X3 ? launch_strict_rollout_f16(plan, cb, (cudaStream_t)stream)
-                                                                : launch_strict_rollout(plan, cb, (cudaStream_t)stream);
+    const int rc = launch_strict(plan, cb, (cudaStream_t)stream);
     if (order) cudaFreeAsync(order, (cudaStream_t)stream);
     if (unit_order) cudaFreeAsync(unit_order, (cudaStream_t)stream);
     return rc;
@@ -290,8 +289,7 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
         cb.iters = stage + 2 * (size_t)B;
     }
     int rc = mode != LIPM_MODE_STRICT ? launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream)
-             : plan->desc.precision == LIPM_PRECISION_F16X3 ? launch_strict_rollout_f16(plan, cb, (cudaStream_t)stream)
-                                                            : launch_strict_rollout(plan, cb, (cudaStream_t)stream);
+             : launch_strict(plan, cb, (cudaStream_t)stream);
     if (rc == LIPM_OK && stage) {
         if (status) LIPM_CUDA_TRY(cudaMemcpy2DAsync(status, sizeof(int32_t), stage, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         if (iters) LIPM_CUDA_TRY(cudaMemcpy2DAsync(iters, sizeof(int32_t), stage + 2 * (size_t)B, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

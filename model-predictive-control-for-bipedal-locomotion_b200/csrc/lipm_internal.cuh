@@ -40,7 +40,9 @@ constexpr int kMaxStrictHorizon = 8 * 16 * kMaxRowBlocksPerWarp;             // 
 constexpr int kF16Tile = 160;                 // padded horizon = MMA N = MMA K
 constexpr int kF16Cols = 128;                 // columns (scenario axes) per CTA = MMA M = TMEM lanes
 constexpr int kF16StateSlot = 152;            // first contraction slot of the state
-constexpr int kMaxReducedHorizon = 152;
+constexpr int kMaxReducedHorizon = 152;         // resident operands (lipm_rollout_strict_f16.cu)
+constexpr int kMaxReducedStreamK = 640;         // streamed operands (lipm_rollout_strict_f16s.cu): padded contraction length
+constexpr int kMaxReducedStreamHorizon = kMaxReducedStreamK - 3;   // 637: three contraction slots carry the axis state
 constexpr int kF16OperandBytesB = (kF16Tile / 8) * (kF16Tile / 8) * 128;   // 51200: one FP16 image of B
 constexpr int kF16OperandBytesA = (kF16Tile / 8) * (kF16Cols / 8) * 128;   // 40960: one FP16 image of A
 // Byte offset of element (row, k) of a K-major operand without swizzle: 8 x 16-byte core matrices,
@@ -73,7 +75,10 @@ struct lipm_plan {
     double* d_mfrag;      // [(NP/8) x (NP/4) x 32] ADMM matrix in DMMA A-fragment order
     double* d_hfrag;      // same layout: H^-1 (dense unconstrained preview on the FP64 tensor pipe)
     double* d_gain;       // [N+3] kz, kx
-    unsigned char* d_bf16; // [2 x kF16OperandBytesB] FP16 hi / lo images of [M | M G Px] (F16X3 plans only)
+    unsigned char* d_bf16; // [2 x kF16OperandBytesB] FP16 hi / lo images of [M | M G Px] (F16X3 plans, N <= 152)
+    unsigned char* d_f16s; // FP16 hi / lo images of [M | M G Px] cut into 160-row slabs (F16X3 plans, N > 152)
+    int f16s_nk;           // padded contraction length of d_f16s: multiple of 16, >= N + 3
+    int f16s_slabs;        // 160-row slabs
     int* d_info;          // [4] factorisation status words
     unsigned int* d_tile_counter;  // dynamic work-unit scheduler of the strict kernel
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch
@@ -122,6 +127,12 @@ int build_unit_order(int num_units, int width, int ncols, int B, const int* orde
                      const double* impulse, const int32_t* force_tick, int** unit_order_out, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+// strict rollout on the kernel that matches the plan's precision and horizon
+inline int launch_strict(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
+    if (plan->desc.precision != LIPM_PRECISION_F16X3) return launch_strict_rollout(plan, cb, stream);
+    return plan->N <= kMaxReducedHorizon ? launch_strict_rollout_f16(plan, cb, stream) : launch_strict_rollout_f16s(plan, cb, stream);
+}
 int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_jerk_from_zmp(lipm_plan* plan, int ncols, const double* state, const double* zmp_plan,
                          double* jerk_plan, cudaStream_t stream);

@@ -214,6 +214,29 @@ __global__ void k_pack_f16(int N, const double* __restrict__ M, const double* __
     *reinterpret_cast<__half*>(img + kF16OperandBytesB + off) = lo;
 }
 
+// The same matrix for the streamed kernel (lipm_rollout_strict_f16s.cu): output rows cut into 160-row slabs,
+// contraction length NK (multiple of 16), state slots at k = N .. N+2; image layout [slab][k / 8][row][k % 8].
+__global__ void k_pack_f16s(int N, int NK, int slabs, const double* __restrict__ M, const double* __restrict__ gpx,
+                            unsigned char* __restrict__ img, size_t image_bytes) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)slabs * kF16Tile * NK;
+    if (idx >= total) return;
+    const int k = (int)(idx % NK);
+    const int row = (int)(idx / NK);               // 0 .. slabs * 160 - 1
+    const int slab = row / kF16Tile, r = row % kF16Tile;
+    double v = 0.0;
+    if (row < N && k < N) v = M[(size_t)row * N + k];
+    else if (row < N && k < N + 3) {
+        const int c = k - N;
+        for (int j = 0; j < N; ++j) v = fma(M[(size_t)row * N + j], gpx[j * 3 + c], v);
+    }
+    const __half hi = __double2half(v);
+    const __half lo = __double2half(v - (double)__half2float(hi));
+    const size_t off = (((size_t)slab * (NK / 8) + (k >> 3)) * kF16Tile + r) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + image_bytes + off) = lo;
+}
+
 // Largest eigenvalue of the symmetric positive definite G by power iteration (one CTA; N <= 4096).
 __global__ void k_power_iteration(int N, const double* __restrict__ G, int iterations, double* __restrict__ scratch,
                                   double* __restrict__ lambda_out) {
@@ -323,9 +346,17 @@ int build_plan_matrices(lipm_plan* plan) {
     LIPM_CUDA_TRY(cudaMalloc(&plan->d_hfrag, sizeof(double) * nfrag));
     k_pack_fragments<<<(unsigned)((nfrag + 255) / 256), 256>>>(N, NP, plan->d_hinv, plan->d_hfrag);
     k_gain<<<1, 256>>>(N, d.Q, plan->pu00, plan->d_hinv, plan->d_gpx, plan->d_px, plan->d_gain);
-    if (d.precision == LIPM_PRECISION_F16X3) {
+    if (d.precision == LIPM_PRECISION_F16X3 && N <= kMaxReducedHorizon) {
         LIPM_CUDA_TRY(cudaMalloc(&plan->d_bf16, 2 * kF16OperandBytesB));
         k_pack_f16<<<(kF16Tile * kF16Tile + 255) / 256, 256>>>(N, plan->d_minv, plan->d_gpx, plan->d_bf16);
+    } else if (d.precision == LIPM_PRECISION_F16X3) {
+        plan->f16s_nk = (N + 3 + 15) & ~15;
+        plan->f16s_slabs = (plan->f16s_nk + kF16Tile - 1) / kF16Tile;
+        const size_t image = (size_t)plan->f16s_slabs * (plan->f16s_nk / 8) * kF16Tile * 16;
+        LIPM_CUDA_TRY(cudaMalloc(&plan->d_f16s, 2 * image));
+        const long long total = (long long)plan->f16s_slabs * kF16Tile * plan->f16s_nk;
+        k_pack_f16s<<<(unsigned)((total + 255) / 256), 256>>>(N, plan->f16s_nk, plan->f16s_slabs, plan->d_minv, plan->d_gpx,
+                                                              plan->d_f16s, image);
     }
     LIPM_CUDA_TRY(cudaGetLastError());
     LIPM_CUDA_TRY(cudaDeviceSynchronize());

@@ -605,7 +605,7 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
             case 2: return launch_variant<2, 4, 0>(plan, P, stream);
             case 3: return launch_variant<3, 4, 0>(plan, P, stream);
             case 4: return launch_variant<4, 3, 0>(plan, P, stream);
-            case 5: return launch_variant<5, 3, 0>(plan, P, stream);
+            case 5: return launch_variant<5, 2, 0>(plan, P, stream);   // N = 153..160 (N <= 152 took the specialised variant): two groups fit beside the matrix
             default: break;
         }
     } else if (P.RBLK <= 8 * 5) {

@@ -33,6 +33,7 @@
 //     in shared memory.  Columns freeze individually the moment THEIR test passes, so results do
 //     not depend on which other columns share the CTA.
 #include "lipm_internal.cuh"
+#include "lipm_tcgen05.cuh"
 
 #include <cuda_fp16.h>
 
@@ -47,7 +48,6 @@ constexpr int kChunks = 5;                           // 8-row chunks per part
 constexpr int kThreadsF16 = 32 * kEpiWarps;          // 512 (128 registers per thread)
 constexpr int kLboA = (kF16Cols / 8) * 128;          // 2048
 constexpr int kLboB = (kF16Tile / 8) * 128;          // 2560
-constexpr int kSbo = 128;
 constexpr uint32_t kTmemD = 0, kTmemT = 160, kTmemLo = 320;   // column offsets (512 allocated)
 
 struct F16Params {
@@ -78,67 +78,7 @@ struct Control {
 constexpr size_t kSmemOperands = 2 * (size_t)kF16OperandBytesB + 2 * (size_t)kF16OperandBytesA;   // 184,320
 constexpr size_t kSmemF16 = kSmemOperands + sizeof(Control);
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// tcgen05 plumbing ------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// K-major operand, no swizzle: start address, leading (K chunk) and stride (8-row group) byte offsets,
-// descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t operand_desc(uint32_t saddr, uint32_t lbo) {
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((kSbo >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(addr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]),
-                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float clipf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+using namespace tc;
 
 // Eight consecutive contraction slots of one column, split into FP16 hi + lo, as two 16-byte stores
 // into the operand images (K chunk kc, column s: byte offset kc * LBO + s * 16).

@@ -20,7 +20,7 @@ MODE_UNCONSTRAINED = 0
 MODE_STRICT = 1
 
 PRECISION_FP64 = 0     # FP64 tensor pipe (DMMA): <= 1e-9 relative
-PRECISION_F16X3 = 1    # tcgen05, FP16 hi/lo split operands, FP32 accumulate: <= 1e-4 m, horizon <= 152
+PRECISION_F16X3 = 1    # tcgen05, FP16 hi/lo split operands, FP32 accumulate: <= 1e-4 m, horizon <= 637
 
 FLAG_ACTIVE_LO = 1
 FLAG_ACTIVE_HI = 2

@@ -319,7 +319,7 @@ def test_reference_python_surface_on_gpu(golden):
     assert rel_err(x_state, gn["nopush_x_hist"]) < REL and rel_err(y_state, gn["nopush_y_hist"]) < REL
 
 
-@pytest.mark.parametrize("N", [24, 40, 100, 128, 200, 300, 600])
+@pytest.mark.parametrize("N", [24, 40, 100, 128, 145, 153, 160, 161, 200, 300, 600])
 def test_strict_ticks_other_horizons_and_determinism(engine, N):
     """Every kernel variant (row blocks per warp 1..5, partial last row group, padded rows; resident
     matrix up to N=160, L2-streamed matrix with 8- and 16-warp groups beyond -- BASELINE config 3):
@@ -472,7 +472,7 @@ def test_reduced_ragged_and_limits(engine, plan150_f16):
         assert np.array_equal(one["flags"][0].cpu().numpy(), out["flags"][b, :n])
         assert not out["y_hist"][b, n:].any()
     with pytest.raises(engine.LipmError, match="F16X3"):
-        engine.get_plan(300, 0.75, 9.81, 1.5 / 300, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
+        engine.get_plan(638, 0.75, 9.81, 1.5 / 638, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
     # the unconstrained mode of a reduced-precision plan is the same FP64 gain-row kernel
     a = plan150_f16.rollout(engine.MODE_UNCONSTRAINED, zero, zero, z_min[:70], z_max[:70])
     assert np.isfinite(a["y_hist"].cpu().numpy()).all()
@@ -512,9 +512,10 @@ def test_param_sweep_matches_individual_walks(engine, default_config):
         assert bool(res["fell"][0]) == bool(out["fell"][k])
 
 
-@pytest.mark.parametrize("N", [24, 100, 128, 152])
+@pytest.mark.parametrize("N", [24, 100, 128, 152, 153, 200, 300, 318, 477, 600, 637])
 def test_reduced_other_horizons_against_fp64_path(engine, N):
-    """Every horizon the reduced-precision tile serves (zero-padded to 160): solution within 1e-4 m of the FP64
+    """Every horizon the reduced-precision kernels serve (N <= 152: operands resident in shared memory, one 160-row
+    tile; beyond: operands streamed, 1-4 slabs, BASELINE config 3's N = 300 / 600): solution within 1e-4 m of the FP64
     path of the same library, feasible after the FP64 clamp, far fewer iterations, bit-identical when repeated."""
     rng = np.random.default_rng(21 + N)
     fp64 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)

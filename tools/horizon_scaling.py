@@ -47,7 +47,7 @@ def main():
     ap.add_argument("--timed", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--precision", choices=["fp64", "f16x3"], default="fp64",
-                    help="strict-mode arithmetic (f16x3: tcgen05 path, horizons <= 152 only)")
+                    help="strict-mode arithmetic (f16x3: tcgen05 paths, horizons <= 637)")
     args = ap.parse_args()
 
     import torch
