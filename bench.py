@@ -207,22 +207,24 @@ def other_configs(torch, engine, device):
     out = {}
     B = 16384
     for N in (300, 600):
-        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
-        x, lo, hi = horizon_scaling.tick_inputs(N, B)
-        xd, lod, hid = (torch.as_tensor(a).to(device) for a in (x, lo, hi))
-        plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
-        torch.cuda.synchronize(device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            res = plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
-        e1.record()
-        torch.cuda.synchronize(device)
-        ms = e0.elapsed_time(e1) / 3
-        iters = int(res["iters"].sum().item())
-        out[f"strict_tick_N{N}_fp64"] = {"batch": B, "ms_per_tick": ms, "solves_per_s": B / (ms * 1e-3),
-                                         "algorithmic_tflops": 2.0 * N * N * iters / (ms * 1e-3) / 1e12,
-                                         "mean_iters_per_solve": iters / B, "start": "cold"}
+        for precision, tag in ((engine.PRECISION_FP64, "fp64"), (engine.PRECISION_F16X3, "f16x3")):
+            plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=precision)
+            x, lo, hi = horizon_scaling.tick_inputs(N, B)
+            xd, lod, hid = (torch.as_tensor(a).to(device) for a in (x, lo, hi))
+            plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                res = plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms = e0.elapsed_time(e1) / 3
+            iters = int(res["iters"].sum().item())
+            out[f"strict_tick_N{N}_{tag}"] = {"batch": B, "ms_per_tick": ms, "solves_per_s": B / (ms * 1e-3),
+                                              "algorithmic_tflops": 2.0 * N * N * iters / (ms * 1e-3) / 1e12,
+                                              "mean_iters_per_solve": iters / B, "start": "cold",
+                                              "not_converged": int((res["status"] != 0).sum().item())}
     cfg = MPCConfig()
     cfg.method = "herdt"
     vx, vy, states = SpeedTrajectoryGenerator(cfg).generate_speed_and_state(save_footsteps=False)

@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_strict_rollout_f16s(const Stre
                             }
                             if (j == N + 1) rv = x1f;          // contraction slots N, N+1, N+2 = axis state relative to the origin
                             if (j == N + 2) rv = x2f;
-                            Tcur[(size_t)j * kF16Cols + s] = t;
-                            LO[(size_t)j * kF16Cols + s] = l;
-                            HI[(size_t)j * kF16Cols + s] = h;
+                            __stcs(Tcur + (size_t)j * kF16Cols + s, t);
+                            __stcs(LO + (size_t)j * kF16Cols + s, l);
+                            __stcs(HI + (size_t)j * kF16Cols + s, h);
                             r[e] = rv;
                         }
                         publish_rhs(Rh, Rl, jb >> 3, s, r);
@@ -332,48 +332,72 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_strict_rollout_f16s(const Stre
                     const float relax = done ? 0.f : P.alpha;      // a converged column keeps its t and republishes the same r
                     const bool work = __any_sync(0xffffffffu, age < 2);
                     unsigned char* RlN = RhN + rimg_bytes;
-                    for (int slab = 0; slab < slabs; ++slab) {
-                        const uint32_t buf = dcount & 1u, use = dcount >> 1;
-                        mbar_wait(&S.dfull[buf], use & 1u);
-                        tc_fence_after();
-                        if (work) {
-#pragma unroll 1
-                            for (int ch = 0; ch < kChunks; ++ch) {
-                                const int jb = slab * kSlab + part * kPartRows + ch * 8;
-                                if (jb >= NK) continue;
-                                uint32_t vd[8];
-                                tmem_ld8(tmem + buf * kSlab + part * kPartRows + ch * 8, vd);
-                                float t[8], l[8], h[8];
+                    // chunks of 8 rows, (slab, chunk) in order; the state of the NEXT chunk is fetched while this one
+                    // is computed (the loads come from L2 / HBM: one chunk of latency is hidden per chunk)
+                    const int nitems = slabs * kChunks;
+                    float tn[8], ln[8], hn[8];
+                    {
+                        const int jn = part * kPartRows;
+                        if (work && jn < NK) {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const size_t at = (size_t)(jb + e) * kF16Cols + s;
-                                    t[e] = Tcur[at]; l[e] = LO[at]; h[e] = HI[at];
-                                }
-                                tmem_wait_ld();
-                                float r[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const int j = jb + e;
-                                    const float zo = clipf(t[e], l[e], h[e]);
-                                    const float dd = __uint_as_float(vd[e]) - zo;
-                                    const float tn = fmaf(relax, dd, t[e]);        // alpha v + (1 - alpha) zo + (t - zo)
-                                    const float zn = clipf(tn, l[e], h[e]);
-                                    float rv = fmaf(P.qhalf, l[e] + h[e], fmaf(P.two_rho, zn, -P.rho * tn));
-                                    if (j < N) {
-                                        rd = max(rd, __float_as_uint(fabsf(dd)));
-                                        Tcur[(size_t)j * kF16Cols + s] = tn;
-                                    } else {
-                                        rv = (j == N + 1) ? x1f : ((j == N + 2) ? x2f : 0.f);
-                                    }
-                                    r[e] = rv;
-                                }
-                                publish_rhs(RhN, RlN, jb >> 3, s, r);
+                            for (int e = 0; e < 8; ++e) {
+                                const size_t at = (size_t)(jn + e) * kF16Cols + s;
+                                tn[e] = __ldcs(Tcur + at); ln[e] = __ldcs(LO + at); hn[e] = __ldcs(HI + at);
                             }
                         }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.dfree[buf]);
-                        ++dcount;
+                    }
+#pragma unroll 1
+                    for (int idx = 0; idx < nitems; ++idx) {
+                        const int slab = idx / kChunks, ch = idx - slab * kChunks;
+                        const int jb = slab * kSlab + part * kPartRows + ch * 8;
+                        const uint32_t buf = dcount & 1u, use = dcount >> 1;
+                        float t[8], l[8], h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { t[e] = tn[e]; l[e] = ln[e]; h[e] = hn[e]; }
+                        if (idx + 1 < nitems) {
+                            const int sn = (idx + 1) / kChunks, cn = (idx + 1) - sn * kChunks;
+                            const int jn = sn * kSlab + part * kPartRows + cn * 8;
+                            if (work && jn < NK) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const size_t at = (size_t)(jn + e) * kF16Cols + s;
+                                    tn[e] = __ldcs(Tcur + at); ln[e] = __ldcs(LO + at); hn[e] = __ldcs(HI + at);
+                                }
+                            }
+                        }
+                        if (ch == 0) {
+                            mbar_wait(&S.dfull[buf], use & 1u);
+                            tc_fence_after();
+                        }
+                        if (work && jb < NK) {
+                            uint32_t vd[8];
+                            tmem_ld8(tmem + buf * kSlab + part * kPartRows + ch * 8, vd);
+                            tmem_wait_ld();
+                            float r[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int j = jb + e;
+                                const float zo = clipf(t[e], l[e], h[e]);
+                                const float dd = __uint_as_float(vd[e]) - zo;
+                                const float tnew = fmaf(relax, dd, t[e]);        // alpha v + (1 - alpha) zo + (t - zo)
+                                const float zn = clipf(tnew, l[e], h[e]);
+                                float rv = fmaf(P.qhalf, l[e] + h[e], fmaf(P.two_rho, zn, -P.rho * tnew));
+                                if (j < N) {
+                                    rd = max(rd, __float_as_uint(fabsf(dd)));
+                                    __stcs(Tcur + (size_t)j * kF16Cols + s, tnew);
+                                } else {
+                                    rv = (j == N + 1) ? x1f : ((j == N + 2) ? x2f : 0.f);
+                                }
+                                r[e] = rv;
+                            }
+                            publish_rhs(RhN, RlN, jb >> 3, s, r);
+                        }
+                        if (ch == kChunks - 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&S.dfree[buf]);
+                            ++dcount;
+                        }
                     }
                     S.Res[part][s] = done ? 0u : rd;
                     proxy_fence_global();

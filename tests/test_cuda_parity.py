@@ -537,6 +537,36 @@ def test_reduced_other_horizons_against_fp64_path(engine, N):
     assert np.array_equal(again["zmp_plan"].cpu().numpy(), z)
 
 
+def test_reduced_streamed_walks(engine):
+    """Whole walks on the streamed reduced-precision kernel (N = 200, 2 s preview: two slabs; the warm start is shifted
+    through the per-CTA workspace, the axis state rides in contraction slots 200..202): within 1e-4 m of the FP64
+    path, ZMP inside the box, ragged lengths, and each walk bit-identical when it is run alone."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(7, seed=9)
+    n, N = 130, 200
+    z_max, z_min = z_max[:n], z_min[:n]
+    fp64 = engine.get_plan(N, 0.75, 9.81, 0.01, 1.0, 1e-6)
+    f16 = engine.get_plan(N, 0.75, 9.81, 0.01, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
+    n_steps = np.array([130, 130, 60, 130, 2, 101, 130], np.int32)
+    tick = np.array([105, 110, 30, 120, 0, 50, 115], np.int32)
+    zero = np.zeros((7, 3))
+    kw = dict(n_steps=n_steps, impulse=impulse, force_tick=tick)
+    want = {k: v.cpu().numpy() for k, v in fp64.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, **kw).items() if not k.startswith("_")}
+    got = {k: v.cpu().numpy() for k, v in f16.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, **kw).items() if not k.startswith("_")}
+    assert not want["status"].any() and not got["status"].any()
+    for key in ("x_hist", "y_hist"):
+        assert np.max(np.abs(got[key][:, :, 0] - want[key][:, :, 0])) < TOL_REDUCED_M, key
+    assert got["max_violation"].max() < 1e-9
+    assert got["iters"].sum() < want["iters"].sum()
+    for b in (0, 2, 4, 5):
+        nb = int(n_steps[b])
+        one = f16.rollout(engine.MODE_STRICT, zero[:1], zero[:1], z_min[:nb], z_max[:nb], impulse=impulse[b:b + 1],
+                          force_tick=tick[b:b + 1])
+        assert np.array_equal(one["y_hist"][0].cpu().numpy(), got["y_hist"][b, :nb]), b
+        assert np.array_equal(one["x_hist"][0].cpu().numpy(), got["x_hist"][b, :nb]), b
+        assert np.array_equal(one["flags"][0].cpu().numpy(), got["flags"][b, :nb]), b
+        assert not got["y_hist"][b, nb:].any()
+
+
 # ----------------------------------------------------------------------------- device-side generators (SURVEY 8f-2)
 def test_device_bound_generation_is_bit_identical(engine, default_config):
     """lipm_generate_bounds against the host generators (which are pinned against the reference itself):
