@@ -233,6 +233,28 @@ int herdt_tick(herdt_timeline_t* timeline, int tick, int B, const double* x, con
                const double* poly_verts, int n_verts, int warm, double* next_x, double* next_y, double* f1,
                double* solution, int32_t* status, int32_t* iters, void* stream);
 
+/* A whole Herdt walk for B scenarios that share the timeline: the tick loop of generate_com_trajectory_herdt
+ * (zmp_controller.py:475-525) enqueued on `stream` without returning to the host between ticks -- per tick
+ * herdt_tick, then the swing-foot interpolation (:495-498), the footstep commit at the end of a single support
+ * (:501-517), the push (:522-523), the histories and the running totals.
+ *   n           samples of the walk (n - 1 ticks, n - 1 <= n_ticks of the timeline)
+ *   x0, y0      dev [B,3];  fc0 dev [B,2] initial supporting foot;  spread dev [B] or NULL
+ *   vref        dev [vref_batch, n_ext, 2] as for herdt_tick
+ *   foot_side, steps_left, commit, new_run   HOST arrays [n-1]: supporting side of each tick (0 left, 1 right),
+ *               ticks until the next state change (find_nb_steps(...)[i][0]), "this tick ends a single
+ *               support" and "a new support run starts at this tick" (warm start bookkeeping)
+ *   poly_left / poly_right   HOST [n_left|n_right, 2] reachable polygons of the next footstep per supporting side
+ *   warm_start  0: every tick starts cold (as the reference);  1: from the previous tick's iterate
+ *   impulse     dev [B] = dt * F_ext / m applied to the y velocity after tick `force_tick`, or NULL
+ * outputs: x_hist, y_hist dev [B,n,3]; foot_hist dev [B,n,2]; status dev int32 [B] = ticks whose joint QP did not
+ *          converge (they fall back like the reference, :796-804); iters dev int64 [B]; both may be NULL.
+ * Walks of DIFFERENT timelines may be enqueued on different streams and run concurrently. */
+int herdt_rollout(herdt_timeline_t* timeline, int B, int n, const double* x0, const double* y0, const double* fc0,
+                  const double* spread, const double* vref, int vref_batch, int n_ext, const int8_t* foot_side,
+                  const int32_t* steps_left, const uint8_t* commit, const uint8_t* new_run, const double* poly_left,
+                  int n_left, const double* poly_right, int n_right, int warm_start, const double* impulse, int force_tick,
+                  double* x_hist, double* y_hist, double* foot_hist, int32_t* status, long long* iters, void* stream);
+
 /* Library / build information. */
 const char* lipm_last_error(void);
 const char* lipm_version(void);

@@ -604,6 +604,57 @@ __global__ void k_herdt_apply(int B, int NP, int N, int m, double T, double hg, 
     if (f1) f1[(size_t)b * 2 + axis] = m > 0 ? ((failed && air) ? air[(size_t)b * 2 + axis] : sol[(size_t)idx * NP + N]) : nan("");
 }
 
+// Between two ticks of a walk (zmp_controller.py:495-525): swing-foot interpolation towards the first free
+// footstep, footstep commit at the end of a single support, the push, the histories and the running
+// status / iteration totals.  One thread per scenario; explicitly rounded operations (no contraction) so that
+// the result is the same as the element-wise host formulas.
+__global__ void k_herdt_book(int B, int n, int sample, int has_step, double inv_steps, int commit, int push,
+                             const double* __restrict__ impulse, const double* __restrict__ f1,
+                             const int32_t* __restrict__ tick_status, const int32_t* __restrict__ tick_iters,
+                             double* __restrict__ next_x, double* __restrict__ next_y, double* __restrict__ fc,
+                             double* __restrict__ air, double* __restrict__ x_hist, double* __restrict__ y_hist,
+                             double* __restrict__ foot_hist, int32_t* __restrict__ status, long long* __restrict__ iters) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double fcb[2] = {fc[2 * b], fc[2 * b + 1]}, airb[2] = {air[2 * b], air[2 * b + 1]};
+    if (has_step) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) airb[a] = __dadd_rn(airb[a], __dmul_rn(inv_steps, __dsub_rn(f1[2 * b + a], airb[a])));
+    }
+    if (commit) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { fcb[a] = has_step ? f1[2 * b + a] : airb[a]; airb[a] = fcb[a]; }
+    }
+    if (push) next_y[3 * b + 1] = __dsub_rn(next_y[3 * b + 1], impulse[b]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) { fc[2 * b + a] = fcb[a]; air[2 * b + a] = airb[a]; }
+    const size_t at = (size_t)b * n + sample;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { x_hist[at * 3 + k] = next_x[3 * b + k]; y_hist[at * 3 + k] = next_y[3 * b + k]; }
+    foot_hist[at * 2] = fcb[0]; foot_hist[at * 2 + 1] = fcb[1];
+    if (status) status[b] += max(tick_status[2 * b], tick_status[2 * b + 1]);
+    if (iters) iters[b] += max(tick_iters[2 * b], tick_iters[2 * b + 1]);
+}
+
+__global__ void k_herdt_start(int B, int n, const double* __restrict__ x0, const double* __restrict__ y0, const double* __restrict__ fc0,
+                              double* __restrict__ x, double* __restrict__ y, double* __restrict__ fc, double* __restrict__ air,
+                              double* __restrict__ x_hist, double* __restrict__ y_hist, double* __restrict__ foot_hist,
+                              int32_t* __restrict__ status, long long* __restrict__ iters) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t at = (size_t)b * n;
+    for (int k = 0; k < 3; ++k) {
+        x[3 * b + k] = x0[3 * b + k]; y[3 * b + k] = y0[3 * b + k];
+        x_hist[at * 3 + k] = x0[3 * b + k]; y_hist[at * 3 + k] = y0[3 * b + k];
+    }
+    for (int a = 0; a < 2; ++a) {
+        fc[2 * b + a] = fc0[2 * b + a]; air[2 * b + a] = fc0[2 * b + a];
+        foot_hist[at * 2 + a] = fc0[2 * b + a];
+    }
+    if (status) status[b] = 0;
+    if (iters) iters[b] = 0;
+}
+
 template <int NRB, int NG>
 int launch_qp(const QpParams& P, int sm_count, cudaStream_t stream) {
     const size_t nfrag = (size_t)(P.NP / 8) * (P.NP / 4) * 32;
@@ -642,6 +693,7 @@ struct herdt_timeline {
     int cap_cols;
     double *d_q, *d_lo, *d_hi, *d_t0, *d_sol, *d_tprev;
     int prev_tick, prev_cols;   // what d_tprev holds (-1: nothing)
+    unsigned int* d_counter;    // work-unit scheduler of k_qp_tick (per timeline: timelines may run concurrently)
 };
 
 extern "C" {
@@ -760,7 +812,7 @@ int herdt_timeline_create(herdt_plan_t* plan, int n_ticks, int m_max, const int8
 
 void herdt_timeline_destroy(herdt_timeline_t* t) {
     if (!t) return;
-    void* ptrs[] = {t->d_phase, t->d_kind, t->d_frag, t->d_q, t->d_lo, t->d_hi, t->d_t0, t->d_sol, t->d_tprev};
+    void* ptrs[] = {t->d_phase, t->d_kind, t->d_frag, t->d_q, t->d_lo, t->d_hi, t->d_t0, t->d_sol, t->d_tprev, t->d_counter};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete[] t->h_m;
     delete t;
@@ -824,9 +876,10 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
         Q.verts[i][0] = (m > 0 && i < n_verts) ? poly_verts[2 * i] : 0.0;
         Q.verts[i][1] = (m > 0 && i < n_verts) ? poly_verts[2 * i + 1] : 0.0;
     }
-    Q.tile_counter = plan->d_counter;
+    if (!t->d_counter) LIPM_CUDA_TRY(cudaMalloc(&t->d_counter, sizeof(unsigned int)));
+    Q.tile_counter = t->d_counter;
     Q.num_units = (unsigned)((ncols + kGroupCols - 1) / kGroupCols);
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned int), stream));
+    LIPM_CUDA_TRY(cudaMemsetAsync(t->d_counter, 0, sizeof(unsigned int), stream));
     int rc;
     switch ((NP / 8 + kRowGroups - 1) / kRowGroups) {
         case 1: rc = launch_qp<1, 4>(Q, plan->sm_count, stream); break;
@@ -842,6 +895,50 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
                                                            next_x, next_y, f1);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;
+}
+
+int herdt_rollout(herdt_timeline_t* t, int B, int n, const double* x0, const double* y0, const double* fc0,
+                  const double* spread, const double* vref, int vref_batch, int n_ext, const int8_t* foot_side,
+                  const int32_t* steps_left, const uint8_t* commit, const uint8_t* new_run, const double* poly_left,
+                  int n_left, const double* poly_right, int n_right, int warm_start, const double* impulse, int force_tick,
+                  double* x_hist, double* y_hist, double* foot_hist, int32_t* status, long long* iters, void* stream_) {
+    if (!t || B < 0 || n < 1 || n - 1 > t->n_ticks) { set_error("herdt_rollout: bad timeline / sizes"); return LIPM_E_INVALID; }
+    if (!x0 || !y0 || !fc0 || !vref || !foot_side || !steps_left || !commit || !new_run || !x_hist || !y_hist || !foot_hist) {
+        set_error("herdt_rollout: missing argument");
+        return LIPM_E_INVALID;
+    }
+    if (B == 0) return LIPM_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // walk state of the batch: x, y (two copies, alternating), fc, air, f1, per-tick status / iterations
+    const size_t doubles = (size_t)B * (4 * 3 + 3 * 2);
+    unsigned char* scratch = nullptr;
+    LIPM_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), doubles * sizeof(double) + (size_t)B * 4 * sizeof(int32_t), stream));
+    double* xs[2] = {reinterpret_cast<double*>(scratch), reinterpret_cast<double*>(scratch) + (size_t)B * 3};
+    double* ys[2] = {xs[1] + (size_t)B * 3, xs[1] + (size_t)B * 6};
+    double* fc = ys[1] + (size_t)B * 3;
+    double* air = fc + (size_t)B * 2;
+    double* f1 = air + (size_t)B * 2;
+    int32_t* tick_status = reinterpret_cast<int32_t*>(f1 + (size_t)B * 2);
+    int32_t* tick_iters = tick_status + (size_t)B * 2;
+    const unsigned blocks = (unsigned)((B + 127) / 128);
+    k_herdt_start<<<blocks, 128, 0, stream>>>(B, n, x0, y0, fc0, xs[0], ys[0], fc, air, x_hist, y_hist, foot_hist, status, iters);
+    int rc = LIPM_OK;
+    for (int i = 0; i < n - 1 && rc == LIPM_OK; ++i) {
+        const int cur = i & 1, nxt = cur ^ 1;
+        const int side = foot_side[i];
+        const int has_step = t->h_m[i] > 0;
+        const int warm = (i == 0 || !warm_start) ? 0 : (new_run[i] ? 2 : 1);
+        rc = herdt_tick(t, i, B, xs[cur], ys[cur], fc, air, spread, vref, vref_batch, n_ext, side,
+                        has_step ? (side ? poly_right : poly_left) : nullptr, has_step ? (side ? n_right : n_left) : 0, warm,
+                        xs[nxt], ys[nxt], f1, nullptr, tick_status, tick_iters, stream_);
+        if (rc != LIPM_OK) break;
+        k_herdt_book<<<blocks, 128, 0, stream>>>(B, n, i + 1, has_step, has_step ? 1.0 / (double)steps_left[i] : 0.0, commit[i] ? 1 : 0,
+                                                 (impulse != nullptr && i == force_tick) ? 1 : 0, impulse, f1, tick_status, tick_iters,
+                                                 xs[nxt], ys[nxt], fc, air, x_hist, y_hist, foot_hist, status, iters);
+    }
+    if (rc == LIPM_OK && cudaGetLastError() != cudaSuccess) { set_error("herdt_rollout: launch failed"); rc = LIPM_E_CUDA; }
+    cudaFreeAsync(scratch, stream);
+    return rc;
 }
 
 int herdt_timeline_size(const herdt_timeline_t* t) { return t ? t->NP : 0; }

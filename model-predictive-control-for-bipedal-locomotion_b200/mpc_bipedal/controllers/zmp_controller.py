@@ -260,6 +260,16 @@ class ZMPController:
         (B,n,2), x_hist, y_hist (B,n,3), foot_hist (B,n,2), status (B,), iters (B,))."""
         import torch
         from .. import engine
+
+        batch = self.prepare_herdt(state_ref)
+        out = batch.rollout(x_init, y_init, v_ref, F_ext=F_ext, mass=m, foot_spread=foot_spread, add_force=add_force)
+        out["com"] = torch.stack([out["x_hist"][..., 0], out["y_hist"][..., 0]], dim=-1)
+        return engine.to_host(out) if to_numpy else out
+
+    def prepare_herdt(self, state_ref):
+        """Builds (once per timeline) what the Herdt walks of ``state_ref`` share: the support layout, the plan and the
+        per-tick inverted Hessians on the device.  Called implicitly by the walk methods; call it up front to keep
+        the build (which synchronises the device) out of a region where several timelines run on their own streams."""
         from ..herdt import HerdtBatch, state_codes
 
         codes = state_codes(state_ref)
@@ -270,10 +280,7 @@ class ZMPController:
         if cache is None or cache[0] != key:
             batch = HerdtBatch(self.config, state_ref, self.find_nb_steps(padded), solver_options=self.herdt_options)
             self._herdt_cache = (key, batch)
-        batch = self._herdt_cache[1]
-        out = batch.rollout(x_init, y_init, v_ref, F_ext=F_ext, mass=m, foot_spread=foot_spread, add_force=add_force)
-        out["com"] = torch.stack([out["x_hist"][..., 0], out["y_hist"][..., 0]], dim=-1)
-        return engine.to_host(out) if to_numpy else out
+        return self._herdt_cache[1]
 
     def generate_com_trajectory_herdt(self, x_init, y_init, v_ref, state_ref):
         """One Herdt walk: ``(com (n,2), y_hist (n,3,1), foot_hist (n,2))`` -- reference :435-531."""

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = (
     "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
     "lipm_max_reduced_horizon", "lipm_generate_bounds",
     "herdt_plan_create", "herdt_plan_destroy", "herdt_plan_export_w", "herdt_timeline_create",
-    "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick",
+    "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick", "herdt_rollout",
 )
 
 
@@ -382,7 +382,7 @@ class _HerdtDesc(ctypes.Structure):
 
 
 HERDT_SYMBOLS = ("herdt_plan_create", "herdt_plan_destroy", "herdt_plan_export_w", "herdt_timeline_create",
-                 "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick")
+                 "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick", "herdt_rollout")
 
 
 def _herdt_lib() -> ctypes.CDLL:
@@ -403,6 +403,9 @@ def _herdt_lib() -> ctypes.CDLL:
         lib.herdt_timeline_size.restype = i32
         lib.herdt_tick.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.herdt_tick.restype = i32
+        lib.herdt_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp, i32,
+                                      vp, vp, vp, vp, vp, vp]
+        lib.herdt_rollout.restype = i32
         lib._herdt_ready = True
     return lib
 
@@ -496,6 +499,35 @@ class HerdtTimeline:
         if want_solution:
             out["solution"] = sol
         return out
+
+    def rollout(self, x0: torch.Tensor, y0: torch.Tensor, fc0: torch.Tensor, vref: torch.Tensor, *, n: int, foot_side,
+                steps_left, commit, new_run, polygons, spread: Optional[torch.Tensor] = None, warm_start: bool = True,
+                impulse: Optional[torch.Tensor] = None, force_tick: int = -1) -> Dict[str, torch.Tensor]:
+        """``generate_com_trajectory_herdt`` for B scenarios in ONE call (``herdt_rollout``): the tick loop, the swing-foot
+        interpolation, the footstep commits, the push and the histories are enqueued on the current stream without
+        coming back to the host between ticks.  Device tensors in, device tensors out."""
+        dev = self.plan.device
+        B = x0.shape[0]
+        ticks = n - 1
+        side = np.ascontiguousarray(foot_side[:ticks], dtype=np.int8)
+        left = np.ascontiguousarray(steps_left[:ticks], dtype=np.int32)
+        com = np.ascontiguousarray(commit[:ticks], dtype=np.uint8)
+        new = np.ascontiguousarray(new_run[:ticks], dtype=np.uint8)
+        pl, pr = (np.ascontiguousarray(p, dtype=np.float64) for p in polygons)
+        vref_batch = 1 if vref.ndim == 2 else vref.shape[0]
+        x_hist = torch.empty((B, n, 3), dtype=torch.float64, device=dev)
+        y_hist = torch.empty((B, n, 3), dtype=torch.float64, device=dev)
+        foot_hist = torch.empty((B, n, 2), dtype=torch.float64, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        iters = torch.empty((B,), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(self._lib.herdt_rollout(self._handle, B, int(n), x0.data_ptr(), y0.data_ptr(), fc0.data_ptr(), _ptr(spread),
+                                       vref.data_ptr(), vref_batch, vref.shape[-2], side.ctypes.data, left.ctypes.data,
+                                       com.ctypes.data, new.ctypes.data, pl.ctypes.data, len(pl), pr.ctypes.data, len(pr),
+                                       1 if warm_start else 0, _ptr(impulse), int(force_tick), x_hist.data_ptr(),
+                                       y_hist.data_ptr(), foot_hist.data_ptr(), status.data_ptr(), iters.data_ptr(), stream))
+        return {"x_hist": x_hist, "y_hist": y_hist, "foot_hist": foot_hist, "status": status, "iters": iters,
+                "_keepalive": (x0, y0, fc0, vref, spread, impulse)}
 
     def close(self) -> None:
         if getattr(self, "_handle", None):

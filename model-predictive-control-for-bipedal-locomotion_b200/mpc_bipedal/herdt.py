@@ -149,7 +149,15 @@ class HerdtBatch:
             F = np.broadcast_to(np.asarray(cfg.F_ext if F_ext is None else F_ext, float), (B,))
             m_ = np.broadcast_to(np.asarray(cfg.m if mass is None else mass, float), (B,))
             impulse = torch.as_tensor(cfg.dt * F / m_).to(dev)
-        ticks = n - 1 if n_ticks is None else n_ticks
+        if n_ticks is None:
+            # the whole walk in one call: tick loop and foot bookkeeping run on the device (herdt_rollout)
+            steps_left = np.array([self.nb_steps[i][0] for i in range(n - 1)], np.int32)
+            out = self.timeline.rollout(x, y, fc, vref, n=n, foot_side=lay.foot_side, steps_left=steps_left, commit=lay.commit,
+                                        new_run=lay.new_run, polygons=self.polygons, spread=spread, warm_start=self.warm_start,
+                                        impulse=impulse, force_tick=n // 2 if push else -1)
+            return {k: out[k] for k in ("x_hist", "y_hist", "foot_hist", "status", "iters", "_keepalive")}
+        # a prefix of the walk, tick by tick from the host (the same kernels; used by tests and probes)
+        ticks = n_ticks
         x_hist = torch.zeros((B, n, 3), dtype=torch.float64, device=dev)
         y_hist = torch.zeros((B, n, 3), dtype=torch.float64, device=dev)
         foot_hist = torch.zeros((B, n, 2), dtype=torch.float64, device=dev)

@@ -78,20 +78,36 @@ def main(argv=None):
     solves = 0
     first = next(iter(groups.values()))          # warm-up: CUDA context, kernel images, page-locked staging buffers
     ZMPController(config).generate_com_trajectory_herdt_batched(np.zeros((2, 3)), np.zeros((2, 3)), first["v"], first["states"])
+    import torch
+    from mpc_bipedal import engine
+
     t0 = time.perf_counter()
-    for entry in groups.values():
+    # one stream per timeline group: a group's whole walk is ONE enqueue (herdt_rollout), so the groups -- from
+    # 66 to 1913 plans here -- run concurrently and the small ones fill the SMs the large ones leave idle
+    pending = []
+    controllers = []
+    for entry in groups.values():           # per-timeline Hessians first: building them synchronises the device
+        controllers.append(ZMPController(config))
+        controllers[-1].prepare_herdt(entry["states"])
+    t_built = time.perf_counter() - t0
+    for entry, ctrl in zip(groups.values(), controllers):
         ids = np.array(entry["ids"])
-        ctrl = ZMPController(config)
         v = entry["v"][None] * speed[ids, None, None]
-        res = ctrl.generate_com_trajectory_herdt_batched(np.zeros((len(ids), 3)), np.zeros((len(ids), 3)), v, entry["states"],
-                                                         foot_spread=spread[ids])
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            res = ctrl.generate_com_trajectory_herdt_batched(np.zeros((len(ids), 3)), np.zeros((len(ids), 3)), v, entry["states"],
+                                                             foot_spread=spread[ids], to_numpy=False)
+        pending.append((ids, entry, ctrl, stream, res))
+    for ids, entry, ctrl, stream, res in pending:
+        with torch.cuda.stream(stream):
+            res = engine.to_host(res)
         print(f"  group of {len(ids):4d} plans, {len(entry['states'])} samples: {time.perf_counter() - t0:.2f} s elapsed, "
               f"{res['iters'].sum() / (len(ids) * (len(entry['states']) - 1)):.0f} iterations per joint solve")
         final[ids] = res["com"][:, -1]
         status[ids] = res["status"]
         solves += len(ids) * (len(entry["states"]) - 1)
     seconds = time.perf_counter() - t0
-    summary = {"plans": B, "groups": len(groups), "seconds": seconds, "joint_qp_solves": solves,
+    summary = {"plans": B, "groups": len(groups), "seconds": seconds, "seconds_building_timelines": t_built, "joint_qp_solves": solves,
                "joint_qp_solves_per_s": solves / seconds, "not_converged_plans": int((status != 0).sum()),
                "mean_final_x": float(final[:, 0].mean())}
     print(summary)

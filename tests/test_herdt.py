@@ -159,6 +159,28 @@ def test_herdt_walk_matches_oracle(herdt_case, golden):
     # every committed footstep lies in the reachable polygon of the previous one (reference check :814-823)
     lay_commit = np.where(np.any(np.diff(res["foot_hist"][0], axis=0) != 0, axis=1))[0]
     assert len(lay_commit) == 8
+    # the device-side walk (herdt_rollout: one call) is the host-driven tick loop (herdt_tick per tick), bit for bit,
+    # and walks of different timelines enqueued on different streams do not disturb each other
+    import torch
+    batch = ctrl._herdt_cache[1]
+    spread = rng.uniform(0.08, 0.12, B)
+    n = len(state_ref)
+    whole = batch.rollout(x0, y0, v, F_ext=F, foot_spread=spread)
+    ticked = batch.rollout(x0, y0, v, F_ext=F, foot_spread=spread, n_ticks=n - 1)
+    for key in ("x_hist", "y_hist", "foot_hist", "status", "iters"):
+        assert torch.equal(whole[key], ticked[key]), key
+    short_ref = state_ref[:200]
+    other = ZMPController(cfg)
+    alone = other.generate_com_trajectory_herdt_batched(x0, y0, v[:, :200], short_ref, F_ext=F)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        a = ctrl.generate_com_trajectory_herdt_batched(x0, y0, v, state_ref, F_ext=F, to_numpy=False)
+    with torch.cuda.stream(s2):
+        b2 = other.generate_com_trajectory_herdt_batched(x0, y0, v[:, :200], short_ref, F_ext=F, to_numpy=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(a["y_hist"].cpu().numpy(), res["y_hist"])
+    assert np.array_equal(b2["y_hist"].cpu().numpy(), alone["y_hist"]) and np.array_equal(b2["foot_hist"].cpu().numpy(), alone["foot_hist"])
 
 
 @pytest.mark.gpu
