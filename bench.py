@@ -393,6 +393,28 @@ def run_ours(args, rank, world, local_rank):
     d2h = int(sum(v.nbytes for v in res.values()))
     e2e_value = world * solves_per_step / e2e_s.item()
 
+    # ---- p50 latency of ONE control tick for the whole batch (BASELINE metric, second half): x-solve + y-solve of
+    #      all scenarios = 2 B strict QPs in one lipm_solve_tick call, cold start, each call timed by its own
+    #      pair of CUDA events, 100 calls ---------------------------------------------------------------------
+    tick_latency = None
+    if rank == 0 and mode == engine.MODE_STRICT:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import horizon_scaling
+        xt, lot, hit = horizon_scaling.tick_inputs(cfg.horizon, 2 * B, seed=7)
+        xt, lot, hit = (torch.as_tensor(a).to(device) for a in (xt, lot, hit))
+        for _ in range(3):
+            plan.solve_tick(mode, xt, lot, hit)
+        torch.cuda.synchronize(device)
+        events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+        for a, b in events:
+            a.record()
+            plan.solve_tick(mode, xt, lot, hit)
+            b.record()
+        torch.cuda.synchronize(device)
+        tick_ms = np.array([a.elapsed_time(b) for a, b in events])
+        tick_latency = {"p50_ms": float(np.median(tick_ms)), "p99_ms": float(np.percentile(tick_ms, 99)), "ticks": 100,
+                        "problems_per_tick": 2 * B, "start": "cold (no previous iterate), random states and bounds"}
+
     # ---- the other BASELINE configs in one number each (single GPU run only; seconds, not minutes) ----------
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -433,7 +455,8 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_flops_per_step": flops},
             "checks": {"not_converged_columns": status_bad, "max_zmp_violation_m": max_viol},
             "latency": {"p50_step_ms": float(np.median(step_ms)),
-                        "p50_tick_ms_amortised": float(np.median(step_ms)) / (n - 1)},
+                        "p50_tick_ms_amortised": float(np.median(step_ms)) / (n - 1),
+                        "single_tick": tick_latency},
         }
         if reduced is not None:
             line["reduced_precision"] = reduced
