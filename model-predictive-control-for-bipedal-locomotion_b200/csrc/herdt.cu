@@ -679,7 +679,6 @@ struct herdt_plan {
     herdt_plan_desc_t desc;
     int N, sm_count;
     double *d_pzu, *d_pvu, *d_t, *d_v, *d_W;
-    unsigned int* d_counter;
 };
 
 struct herdt_timeline {
@@ -733,7 +732,6 @@ int herdt_plan_create(herdt_plan_t** out, const herdt_plan_desc_t* desc) {
     LIPM_CUDA_TRY(cudaMalloc(&p->d_t, sizeof(double) * N));
     LIPM_CUDA_TRY(cudaMalloc(&p->d_v, sizeof(double) * N));
     LIPM_CUDA_TRY(cudaMalloc(&p->d_W, sizeof(double) * N * N));
-    LIPM_CUDA_TRY(cudaMalloc(&p->d_counter, sizeof(unsigned int)));
     k_herdt_toeplitz<<<(N + 127) / 128, 128>>>(N, d.dt, d.h / d.g, p->d_pzu, p->d_pvu);
     k_herdt_tv<<<1, 256, sizeof(double) * 2 * N>>>(N, p->d_pzu, p->d_pvu, p->d_t, p->d_v);
     k_herdt_w<<<dim3((N + 127) / 128, N), 128>>>(N, d.alpha, d.beta, p->d_t, p->d_v, p->d_W);
@@ -745,7 +743,7 @@ int herdt_plan_create(herdt_plan_t** out, const herdt_plan_desc_t* desc) {
 
 void herdt_plan_destroy(herdt_plan_t* p) {
     if (!p) return;
-    void* ptrs[] = {p->d_pzu, p->d_pvu, p->d_t, p->d_v, p->d_W, p->d_counter};
+    void* ptrs[] = {p->d_pzu, p->d_pvu, p->d_t, p->d_v, p->d_W};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
 }

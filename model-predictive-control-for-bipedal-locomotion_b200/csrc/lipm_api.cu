@@ -222,7 +222,8 @@ int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const in
     // strict walks: group scenarios that will need similar iteration counts (lipm_order.cu)
     int* order = nullptr;
     if (B > 8 && (n_steps || (impulse && force_tick))) {
-        const int rc = build_processing_order(B, n_max, n_steps, impulse, force_tick, &order, (cudaStream_t)stream);
+        const int rc = build_processing_order(B, n_max, n_steps, impulse, force_tick,
+                                              plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : 8, &order, (cudaStream_t)stream);
         if (rc != LIPM_OK) return rc;
     }
     cb.order = order;

@@ -122,7 +122,7 @@ struct ColumnBatch {
 };
 
 int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
-                           const int32_t* force_tick, int** perm_out, cudaStream_t stream);
+                           const int32_t* force_tick, int width, int** perm_out, cudaStream_t stream);
 int build_unit_order(int num_units, int width, int ncols, int B, const int* order, int n_uniform, const int32_t* n_steps,
                      const double* impulse, const int32_t* force_tick, int** unit_order_out, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
