@@ -187,7 +187,7 @@ typedef struct herdt_plan_desc {
     double alpha, beta, gamma;      /* jerk / velocity / ZMP weights (config.py:42-44, zmp_controller.py:605-607) */
     double foot_length, foot_width; /* ZMP box around the supporting foot (:661-680)                      */
     double foot_spread;             /* standing hull (:715-750)                                           */
-    double rho, relax, eps;         /* ADMM penalty (<=0 -> 8), over-relaxation (<=0 -> 1.6), stop (<=0 -> 1e-12) */
+    double rho, relax, eps;         /* ADMM penalty (<=0 -> 6), over-relaxation (<=0 -> 1.8), stop (<=0 -> 1e-12) */
     int32_t max_iter;               /* <=0 -> 600 (a healthy tick needs 60..150 from a cold start)         */
     int32_t device;
 } herdt_plan_desc_t;
