@@ -5,9 +5,10 @@
 // rebuilt (O(N^2) Python loop) and re-inverted (O(N^3)) on every call.  Only X[0] is consumed, and
 //     X[0] = kz . zref_window + kx . x
 // with a gain row (kz, kx) that depends on the plan only.  A walk is therefore a sliding
-// correlation of the zref series with kz (independent of the state, done 32 ticks at a time by
-// the lanes of a warp) followed by the 3-state recursion.  The kernel is bandwidth/latency bound:
-// per solve it reads one new (z_min, z_max) sample (16 B) and writes the state (24 B) and a flag.
+// correlation of the zref series with kz -- independent of the state, so computed once per bound
+// series (k_free_preview), not once per scenario -- followed by the 3-state recursion, one thread
+// per column (k_free_rollout).  Bandwidth bound: per solve one (z_min, z_max) sample is read (16 B,
+// shared through L1 when the series is) and the state (24 B) and a flag are written.
 #include "lipm_internal.cuh"
 #include "lipm_device.cuh"
 
@@ -15,7 +16,11 @@ namespace lipm {
 
 namespace {
 
-constexpr int kFreeWarps = 4;   // columns per CTA (one warp per column)
+constexpr int kFreeWarps = 4;     // warps per CTA
+constexpr int kFreeCols = 8;      // columns per warp (lanes 0..7 run the recursions, all 32 lanes write out): the recursion is a
+                                  // latency chain, so a sweep needs many warps in flight more than it needs full warps
+constexpr int kFreeTicks = 8;     // ticks staged in shared memory before a column's states are written out
+constexpr int kFreeChunk = 65535; // columns per launch pair when every column needs its own preview series
 
 struct FreeParams {
     ColumnBatch cb;
@@ -23,102 +28,232 @@ struct FreeParams {
     double viol_tol;
     double T, c2, c3, hg;
     const double* gain;   // kz[N], kx[3]
+    double* preview;      // [series][ticks_max] state-independent part of the first jerk, kz . zref_window
+    int ticks_max;
+    int per_column;       // 1: one preview series per column; 0: one per (bound series, axis)
+    int col0, ncols;      // columns of this launch
 };
 
-__global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreeParams P) {
-    extern __shared__ double sm[];
-    const int N = P.N;
-    double* sK = sm;                                  // kz
-    double* sZ = sm + N + (threadIdx.x >> 5) * (N + 32);  // this warp's zref samples
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const ColumnBatch& B = P.cb;
+struct ColumnView {
+    int axis, b, n, ticks, last;
+    long long bz;              // bound series of the scenario
+    const double *plo, *phi;
+};
 
-    for (int j = threadIdx.x; j < N; j += blockDim.x) sK[j] = P.gain[j];
-    const double kx0 = P.gain[N], kx1 = P.gain[N + 1], kx2 = P.gain[N + 2];
-    __syncthreads();
-
-    const int c = blockIdx.x * kFreeWarps + warp;
-    if (c >= B.ncols) return;
-    const int axis = c / B.B, b = c - axis * B.B;
-    int n = B.n_steps ? B.n_steps[b] : B.n_uniform;
+// Decodes column c exactly like the strict kernels do.
+__device__ __forceinline__ ColumnView column_view(const ColumnBatch& B, int c) {
+    ColumnView v;
+    v.axis = c / B.B;
+    v.b = c - v.axis * B.B;
+    int n = B.n_steps ? B.n_steps[v.b] : B.n_uniform;
     n = n > B.n_max ? B.n_max : n;
     int ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
     if (n < 1 || ticks < 0) ticks = 0;
-    const long long bz = B.bounds_index ? B.bounds_index[b] : ((B.bounds_batch == 1) ? 0 : b);
-    const double* plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
-    const double* phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
-    double* hist = axis ? B.hist[1] : B.hist[0];
-    if (hist) hist += (long long)b * B.hist_scn_stride;
-    uint8_t* pf = B.flags ? B.flags + ((long long)b * B.n_max) * 2 + axis : nullptr;
-    const double* init = (axis ? B.init[1] : B.init[0]) + (long long)b * 3;
-    double x0 = init[0], x1 = init[1], x2 = init[2];
-    const bool push = axis == 1 && B.impulse != nullptr;
-    const double imp = push ? B.impulse[b] : 0.0;
-    const int ftick = push ? (B.force_tick ? B.force_tick[b] : -1) : -1;
+    v.n = n; v.ticks = ticks; v.last = n - 1;
+    v.bz = B.bounds_index ? B.bounds_index[v.b] : ((B.bounds_batch == 1) ? 0 : v.b);
+    v.plo = B.z_min + v.bz * B.bound_scn_stride + v.axis * B.bound_axis_offset;
+    v.phi = B.z_max + v.bz * B.bound_scn_stride + v.axis * B.bound_axis_offset;
+    return v;
+}
 
-    double viol = 0.0;
-    if (B.write_initial && ticks > 0) {
-        const double zmp = x0 - P.hg * x2;
-        const double below = plo[0] - zmp, above = zmp - phi[0];
-        viol = fmax(fmax(below, above), 0.0);
-        if (lane == 0) {
+// preview[series][i] = sum_j kz[j] * zref[min(i + bias + j, last)]: the part of the first jerk that does not depend
+// on the state.  One thread per (series, tick); scenarios that share their bound series share the result, so a
+// sweep over pushes or initial states computes it twice (x and y), not 2 B times.
+__global__ void __launch_bounds__(128) k_free_preview(const FreeParams P) {
+    extern __shared__ double sK[];
+    const ColumnBatch& B = P.cb;
+    const int N = P.N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) sK[j] = P.gain[j];
+    __syncthreads();
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nseries = P.per_column ? P.ncols : B.bounds_batch * 2;
+    if (gid >= (long long)nseries * P.ticks_max) return;
+    const int series = (int)(gid / P.ticks_max), i = (int)(gid - (long long)series * P.ticks_max);
+    const double *plo, *phi;
+    int last, ticks;
+    if (P.per_column) {
+        const ColumnView v = column_view(B, P.col0 + series);
+        plo = v.plo; phi = v.phi; last = v.last; ticks = v.ticks;
+    } else {
+        const int axis = series & 1;
+        const long long bz = series >> 1;
+        plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
+        phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
+        int n = B.n_uniform > B.n_max ? B.n_max : B.n_uniform;
+        ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
+        if (n < 1 || ticks < 0) ticks = 0;
+        last = n - 1;
+    }
+    if (i >= ticks) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int s0 = i + B.bound_index_bias;
+    int j = 0;
+    for (; j + 4 <= N; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int s = s0 + j + u;
+            s = s > last ? last : s;
+            const double z = (__ldg(plo + (long long)s * B.bound_stride) + __ldg(phi + (long long)s * B.bound_stride)) / 2;
+            acc[u] = fma(sK[j + u], z, acc[u]);
+        }
+    }
+    for (; j < N; ++j) {
+        int s = s0 + j;
+        s = s > last ? last : s;
+        const double z = (__ldg(plo + (long long)s * B.bound_stride) + __ldg(phi + (long long)s * B.bound_stride)) / 2;
+        acc[j & 3] = fma(sK[j], z, acc[j & 3]);
+    }
+    P.preview[(size_t)series * P.ticks_max + i] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// The same for walks (many ticks per series): blockIdx.y = series, a block covers 128 consecutive ticks and stages
+// the N + 127 zref samples they share in shared memory.  Same summation order as k_free_preview, same bits.
+__global__ void __launch_bounds__(128) k_free_preview_walk(const FreeParams P) {
+    extern __shared__ double sm[];
+    const ColumnBatch& B = P.cb;
+    const int N = P.N;
+    double* sK = sm;
+    double* sZ = sm + N;
+    const int series = blockIdx.y, i0 = blockIdx.x * 128;
+    const double *plo, *phi;
+    int last, ticks;
+    if (P.per_column) {
+        const ColumnView v = column_view(B, P.col0 + series);
+        plo = v.plo; phi = v.phi; last = v.last; ticks = v.ticks;
+    } else {
+        const int axis = series & 1;
+        const long long bz = series >> 1;
+        plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
+        phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
+        int n = B.n_uniform > B.n_max ? B.n_max : B.n_uniform;
+        ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
+        if (n < 1 || ticks < 0) ticks = 0;
+        last = n - 1;
+    }
+    if (i0 >= ticks) return;
+    for (int j = threadIdx.x; j < N; j += 128) sK[j] = P.gain[j];
+    for (int k = threadIdx.x; k < N + 127; k += 128) {
+        int s = i0 + B.bound_index_bias + k;
+        s = s > last ? last : s;
+        sZ[k] = (__ldg(plo + (long long)s * B.bound_stride) + __ldg(phi + (long long)s * B.bound_stride)) / 2;
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    if (i >= ticks) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* z = sZ + threadIdx.x;
+    int j = 0;
+    for (; j + 4 <= N; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(sK[j + u], z[j + u], acc[u]);
+    }
+    for (; j < N; ++j) acc[j & 3] = fma(sK[j], z[j], acc[j & 3]);
+    P.preview[(size_t)series * P.ticks_max + i] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// The 3-state recursion of a walk, one THREAD per column (kFreeCols columns per warp): x <- A x + B (preview[i] + kx . x), push, box test.
+// The states of kFreeTicks ticks are staged in shared memory and written out per column as one contiguous run.
+__global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreeParams P) {
+    __shared__ double tile[kFreeWarps][kFreeCols][kFreeTicks * 3 + 1];
+    __shared__ unsigned long long flags8[kFreeWarps][kFreeCols];     // one byte per staged tick
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ColumnBatch& B = P.cb;
+    const int N = P.N;
+    const double kx0 = P.gain[N], kx1 = P.gain[N + 1], kx2 = P.gain[N + 2];
+
+    const int local = (blockIdx.x * kFreeWarps + warp) * kFreeCols + lane;      // column within this launch
+    const bool valid = lane < kFreeCols && local < P.ncols;
+    const int c = P.col0 + (valid ? local : 0);
+    const ColumnView v = column_view(B, c);
+    const int ticks = valid ? v.ticks : 0;
+    double* hist = nullptr;
+    uint8_t* pf = nullptr;
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, imp = 0.0, viol = 0.0;
+    int ftick = -1;
+    const double* preview = P.preview + (size_t)(P.per_column ? (long long)local : v.bz * 2 + v.axis) * P.ticks_max;
+    if (valid) {
+        hist = v.axis ? B.hist[1] : B.hist[0];
+        if (hist) hist += (long long)v.b * B.hist_scn_stride;
+        pf = B.flags ? B.flags + ((long long)v.b * B.n_max) * 2 + v.axis : nullptr;
+        const double* init = (v.axis ? B.init[1] : B.init[0]) + (long long)v.b * 3;
+        x0 = init[0]; x1 = init[1]; x2 = init[2];
+        if (v.axis == 1 && B.impulse != nullptr) {
+            imp = B.impulse[v.b];
+            ftick = B.force_tick ? B.force_tick[v.b] : -1;
+        }
+        if (B.write_initial && ticks > 0) {
+            const double zmp = x0 - P.hg * x2;
+            const double below = v.plo[0] - zmp, above = zmp - v.phi[0];
+            viol = fmax(fmax(below, above), 0.0);
             if (hist) { hist[0] = x0; hist[1] = x1; hist[2] = x2; }
             if (pf) pf[0] = (uint8_t)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                       (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
         }
     }
+    int warp_ticks = ticks;
+    for (int o = 16; o; o >>= 1) warp_ticks = max(warp_ticks, __shfl_xor_sync(0xffffffffu, warp_ticks, o));
 
-    const int last = n - 1;
-    for (int i0 = 0; i0 < ticks; i0 += 32) {
-        // samples i0+bias .. i0+bias+N+30 cover the windows of ticks i0 .. i0+31
-        __syncwarp();
-        for (int k = lane; k < N + 31; k += 32) {
-            int s = i0 + B.bound_index_bias + k;
-            s = s > last ? last : s;
-            sZ[k] = (__ldg(plo + (long long)s * B.bound_stride) + __ldg(phi + (long long)s * B.bound_stride)) / 2;
+    for (int i0 = 0; i0 < warp_ticks; i0 += kFreeTicks) {
+        // everything the block's steps read from memory first (independent of the recursion), then the
+        // recursion in registers
+        double pv[kFreeTicks], l0[kFreeTicks], h0[kFreeTicks];
+#pragma unroll
+        for (int l = 0; l < kFreeTicks; ++l) {
+            const int i = i0 + l;
+            const bool on = i < ticks;
+            int s_row0 = i + B.bound_index_bias;
+            s_row0 = s_row0 > v.last ? v.last : s_row0;
+            s_row0 = s_row0 < 0 ? 0 : s_row0;
+            pv[l] = on ? __ldg(preview + i) : 0.0;
+            l0[l] = on ? __ldg(v.plo + (long long)s_row0 * B.bound_stride) : 0.0;
+            h0[l] = on ? __ldg(v.phi + (long long)s_row0 * B.bound_stride) : 0.0;
         }
-        __syncwarp();
-        // lane l: state-independent part of the first jerk of tick i0 + l
-        double f = 0.0;
-        for (int j = 0; j < N; ++j) f = fma(sK[j], sZ[lane + j], f);
-        // bounds of the sample each tick produces (window row 0)
-        const int my_tick = i0 + lane;
-        int s_row0 = my_tick + B.bound_index_bias;
-        s_row0 = s_row0 > last ? last : s_row0;
-        const double l0 = __ldg(plo + (long long)s_row0 * B.bound_stride);
-        const double h0 = __ldg(phi + (long long)s_row0 * B.bound_stride);
-
-        // the recursion is sequential; every lane runs it (warp-uniform) and keeps its own tick
-        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-        const int steps = (ticks - i0) < 32 ? (ticks - i0) : 32;
-        for (int l = 0; l < steps; ++l) {
-            const double fl = __shfl_sync(0xffffffffu, f, l);
-            const double jerk = fl + fma(kx2, x2, fma(kx1, x1, kx0 * x0));
-            const double n0 = fma(P.c3, jerk, fma(P.c2, x2, fma(P.T, x1, x0)));
-            double n1 = fma(P.c2, jerk, fma(P.T, x2, x1));
-            const double n2 = fma(P.T, jerk, x2);
-            if (i0 + l == ftick) n1 -= imp;
-            x0 = n0; x1 = n1; x2 = n2;
-            if (l == lane) { m0 = n0; m1 = n1; m2 = n2; }
-        }
-        if (lane < steps) {
-            const double zmp = m0 - P.hg * m2;
-            const double below = l0 - zmp, above = zmp - h0;
-            viol = fmax(viol, fmax(fmax(below, above), 0.0));
-            const long long sample = my_tick + 1;
-            if (hist) {
-                double* dst = hist + (sample - B.hist_index_bias) * 3;
-                dst[0] = m0; dst[1] = m1; dst[2] = m2;
+        unsigned long long flag8 = 0ull;
+#pragma unroll
+        for (int l = 0; l < kFreeTicks; ++l) {
+            const int i = i0 + l;
+            if (i < ticks) {
+                const double jerk = pv[l] + fma(kx2, x2, fma(kx1, x1, kx0 * x0));
+                const double n0 = fma(P.c3, jerk, fma(P.c2, x2, fma(P.T, x1, x0)));
+                double n1 = fma(P.c2, jerk, fma(P.T, x2, x1));
+                const double n2 = fma(P.T, jerk, x2);
+                if (i == ftick) n1 -= imp;
+                x0 = n0; x1 = n1; x2 = n2;
+                tile[warp][lane][l * 3 + 0] = n0; tile[warp][lane][l * 3 + 1] = n1; tile[warp][lane][l * 3 + 2] = n2;   // lane < kFreeCols here
+                const double zmp = n0 - P.hg * n2;
+                const double below = l0[l] - zmp, above = zmp - h0[l];
+                viol = fmax(viol, fmax(fmax(below, above), 0.0));
+                flag8 |= (unsigned long long)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
+                                              (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u)) << (8 * l);
             }
-            if (pf) pf[sample * 2] = (uint8_t)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
-                                               (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
         }
+        if (lane < kFreeCols) flags8[warp][lane] = flag8;
+        __syncwarp();
+        // write-out: column by column the run of this block's states (up to 8 x 24 bytes, contiguous), four columns
+        // at a time their flags (8 bytes each at stride 2: x and y flags of a sample are neighbours)
+        int run = ticks - i0;
+        run = run < 0 ? 0 : (run > kFreeTicks ? kFreeTicks : run);
+        const unsigned long long base = hist ? (unsigned long long)(hist + ((long long)(i0 + 1) - B.hist_index_bias) * 3) : 0ull;
+        const unsigned long long fbase = pf ? (unsigned long long)(pf + (long long)(i0 + 1) * 2) : 0ull;
+#pragma unroll
+        for (int col = 0; col < kFreeCols; ++col) {
+            const int nv = __shfl_sync(0xffffffffu, run, col) * 3;
+            const unsigned long long dst = __shfl_sync(0xffffffffu, base, col);
+            if (dst != 0ull && lane < nv) reinterpret_cast<double*>(dst)[lane] = tile[warp][col][lane];
+        }
+#pragma unroll
+        for (int q = 0; q < kFreeCols / 4; ++q) {
+            const int col = q * 4 + (lane >> 3), l = lane & 7;
+            const int nv = __shfl_sync(0xffffffffu, run, col);
+            const unsigned long long dst = __shfl_sync(0xffffffffu, fbase, col);
+            if (dst != 0ull && l < nv) reinterpret_cast<uint8_t*>(dst)[l * 2] = (uint8_t)(flags8[warp][col] >> (8 * l));
+        }
+        __syncwarp();
     }
-    for (int o = 16; o; o >>= 1) viol = fmax(viol, __shfl_xor_sync(0xffffffffu, viol, o));
-    if (lane == 0) {
-        if (B.max_violation) B.max_violation[b * 2 + axis] = viol;
-        if (B.status) B.status[b * 2 + axis] = 0;
-        if (B.iters) B.iters[b * 2 + axis] = 0;
+    if (valid) {
+        if (B.max_violation) B.max_violation[v.b * 2 + v.axis] = viol;
+        if (B.status) B.status[v.b * 2 + v.axis] = 0;
+        if (B.iters) B.iters[v.b * 2 + v.axis] = 0;
     }
 }
 
@@ -265,12 +400,34 @@ int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStr
     P.hg = plan->hg;
     P.gain = plan->d_gain;
     if (cb.ncols <= 0) return LIPM_OK;
-    const size_t smem = sizeof(double) * ((size_t)plan->N + (size_t)kFreeWarps * (plan->N + 32));
-    if (smem > 48 * 1024)
-        LIPM_CUDA_TRY(cudaFuncSetAttribute(k_free_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((cb.ncols + kFreeWarps - 1) / kFreeWarps);
-    k_free_rollout<<<grid, 32 * kFreeWarps, smem, stream>>>(P);
+    P.ticks_max = cb.ticks_override > 0 ? cb.ticks_override : cb.n_max - 1;
+    if (P.ticks_max <= 0) P.ticks_max = 1;
+    // Scenarios that share a bound series (and its length) share the preview term; per-scenario lengths or series
+    // need one preview series per column, computed and consumed in chunks so that the scratch stays small.
+    P.per_column = (cb.n_steps != nullptr || (cb.bounds_batch != 1 && cb.bounds_index == nullptr)) ? 1 : 0;
+    const int chunk = P.per_column ? kFreeChunk : cb.ncols;
+    const size_t series = P.per_column ? (size_t)(cb.ncols < chunk ? cb.ncols : chunk) : (size_t)cb.bounds_batch * 2;
+    double* preview = nullptr;
+    LIPM_CUDA_TRY(cudaMallocAsync(&preview, sizeof(double) * series * (size_t)P.ticks_max, stream));
+    P.preview = preview;
+    for (int col0 = 0; col0 < cb.ncols; col0 += chunk) {
+        P.col0 = col0;
+        P.ncols = cb.ncols - col0 < chunk ? cb.ncols - col0 : chunk;
+        if (P.per_column || col0 == 0) {
+            const int nseries = P.per_column ? P.ncols : cb.bounds_batch * 2;
+            if (P.ticks_max >= 32 && nseries <= 65535) {
+                k_free_preview_walk<<<dim3((unsigned)((P.ticks_max + 127) / 128), (unsigned)nseries), 128,
+                                      sizeof(double) * (2 * (size_t)plan->N + 127), stream>>>(P);
+            } else {
+                const long long threads = (long long)nseries * P.ticks_max;
+                k_free_preview<<<(unsigned)((threads + 127) / 128), 128, sizeof(double) * plan->N, stream>>>(P);
+            }
+        }
+        const unsigned grid = (unsigned)((P.ncols + kFreeCols * kFreeWarps - 1) / (kFreeCols * kFreeWarps));
+        k_free_rollout<<<grid, 32 * kFreeWarps, 0, stream>>>(P);
+    }
     LIPM_CUDA_TRY(cudaGetLastError());
+    LIPM_CUDA_TRY(cudaFreeAsync(preview, stream));
     return LIPM_OK;
 }
 
