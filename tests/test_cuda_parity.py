@@ -245,6 +245,30 @@ def test_ragged_walks(engine, plan150):
             assert not out["y_hist"][b, n:].any()              # untouched past the end
 
 
+def test_unconstrained_large_ragged_batch(engine, plan150):
+    """Unconstrained mode with per-scenario lengths: the preview term is computed per column, in chunks of 65,535
+    columns -- scenarios on both sides of a chunk boundary equal the same walk run alone (shared-series path)."""
+    cfg, z_max, z_min, _, _ = push_sweep_inputs(4, seed=1)
+    n, B = 40, 40000                                  # 80,000 columns: two chunks
+    z_max, z_min = z_max[100:100 + n], z_min[100:100 + n]
+    rng = np.random.default_rng(8)
+    x0 = rng.normal(size=(B, 3)) * [0.01, 0.02, 0.05]
+    y0 = rng.normal(size=(B, 3)) * [0.01, 0.02, 0.05]
+    n_steps = rng.integers(2, n + 1, B).astype(np.int32)
+    impulse = rng.uniform(0, 0.2, B)
+    tick = (n_steps // 2).astype(np.int32)
+    out = plan150.rollout(engine.MODE_UNCONSTRAINED, x0, y0, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick)
+    out = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+    for b in (0, 17, 25534, 32767, 32768, 39999):      # x columns 0..39999, y columns 40000..79999: chunk edge at 65535
+        nb = int(n_steps[b])
+        one = plan150.rollout(engine.MODE_UNCONSTRAINED, x0[b:b + 1], y0[b:b + 1], z_min[:nb], z_max[:nb],
+                              impulse=impulse[b:b + 1], force_tick=tick[b:b + 1])
+        for key in ("x_hist", "y_hist", "flags"):
+            assert np.array_equal(one[key][0].cpu().numpy(), out[key][b, :nb]), (b, key)
+        assert not out["y_hist"][b, nb:].any()
+        assert np.array_equal(one["max_violation"][0].cpu().numpy(), out["max_violation"][b])
+
+
 def test_push_sweep_full_size_properties(engine, plan150):
     """BASELINE config 2 at full size (4096 scenarios, N=150, strict): size-independent properties."""
     B = 4096
