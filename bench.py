@@ -134,7 +134,7 @@ def cpu_baseline(walks_per_thread=16, steps=1):
     solves = n_walks * 2 * (len(z_min) - 1)
     return {"value": solves / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_walks} full default.json strict walks ({solves} solves) per step; C restatement "
-                      f"(oracle/lipm_oracle.c), FP64 ADMM rho=2 alpha=1.7 eps=1e-12, matrices cached, warm start, "
+                      f"(oracle/lipm_oracle.c), FP64 ADMM rho=2 alpha=1.75 eps=1e-12, matrices cached, warm start, "
                       f"OpenMP over scenarios on {threads} threads",
             "mean_iters_per_solve": float(res["iters"].sum()) / solves,
             "seconds_per_step": float(np.mean(times))}, times
@@ -434,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "scenarios_per_gpu": B, "horizon": N, "samples_per_walk": n,
                        "mode": args.mode, "solves_per_step_per_gpu": solves_per_step,
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
-                       "admm": {"rho": 2.0, "alpha": 1.7, "eps": 1e-12,
+                       "admm": {"rho": 2.0, "alpha": 1.75, "eps": 1e-12,
                                 "mean_iters_per_solve": iters / max(solves_per_step, 1),
                                 "useful_column_slot_fraction": iters / max(slots * stats["group_iterations"], 1)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,

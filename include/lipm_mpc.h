@@ -68,7 +68,7 @@ typedef struct lipm_plan_desc {
     double h, g, dt;   /* CoM height, gravity, sample time (dt = 1.5/N unless overridden)   */
     double Q, R;       /* tracking / jerk weights (zmp_controller.py:186, :174)             */
     double rho;        /* ADMM penalty (<=0 -> 2.0 for N <= 160, sqrt(Q (Q + lambda_max(G))) beyond) */
-    double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.7)                        */
+    double alpha;      /* ADMM over-relaxation  (<=0 -> default 1.75)                      */
     double eps;        /* ADMM stop: primal and rho*dual residual <= eps * max(1, |q|_inf)  (<=0 -> 1e-12;
                           F16X3: <=0 -> 1e-5, floor 5e-7)                                   */
     int32_t max_iter;  /* ADMM iteration cap per QP (<=0 -> 2000; F16X3: 500)                */

@@ -65,7 +65,7 @@ int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
         return LIPM_E_INVALID;
     }
     if (!(d.rho > 0)) d.rho = d.horizon <= kMaxResidentHorizon ? 2.0 : 0.0;   // 0: from the spectrum (lipm_plan.cu)
-    if (!(d.alpha > 0)) d.alpha = 1.7;    // tuned on the push sweep: 7 % fewer iterations than 1.6 at rho = 2
+    if (!(d.alpha > 0)) d.alpha = 1.75;   // tools/admm_tune.py: 26.8 iterations per solve on the push sweep (1.7: 27.5, 1.6: 29.5), neutral or better on cold ticks
     if (d.alpha >= 2.0) { set_error("alpha must be in (0, 2), got %g", d.alpha); return LIPM_E_INVALID; }
     if (d.precision != LIPM_PRECISION_FP64 && d.precision != LIPM_PRECISION_F16X3) {
         set_error("unknown precision %d", d.precision);

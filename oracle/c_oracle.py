@@ -35,7 +35,7 @@ def _load(path):
 
 
 class COracle:
-    def __init__(self, N, h=0.75, g=9.81, dt=None, Q=1.0, R=1e-6, rho=2.0, alpha=1.7, eps=1e-12, max_iter=2000,
+    def __init__(self, N, h=0.75, g=9.81, dt=None, Q=1.0, R=1e-6, rho=2.0, alpha=1.75, eps=1e-12, max_iter=2000,
                  viol_tol=1e-9, native=False):
         self.lib = _load(build(native=native))
         self.N = N

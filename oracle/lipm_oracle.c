@@ -82,7 +82,7 @@ oracle_plan *lipm_oracle_plan_create(int N, double h, double g, double dt, doubl
     const double T = dt;
     p->N = N; p->dt = dt; p->h = h; p->g = g; p->Q = Q; p->R = R;
     p->rho = rho > 0 ? rho : 2.0;
-    p->alpha = alpha > 0 ? alpha : 1.7;
+    p->alpha = alpha > 0 ? alpha : 1.75;
     p->eps = eps > 0 ? eps : 1e-12;
     p->max_iter = max_iter > 0 ? max_iter : 2000;
     p->viol_tol = viol_tol >= 0 ? viol_tol : 1e-9;
