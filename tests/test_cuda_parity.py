@@ -269,6 +269,16 @@ def test_unconstrained_large_ragged_batch(engine, plan150):
         assert np.array_equal(one["max_violation"][0].cpu().numpy(), out["max_violation"][b])
 
 
+def test_layout_fuzz(engine):
+    """Randomized batches (size 1..5000, ragged lengths, shared or per-scenario bounds, random pushes): every sampled
+    scenario equals the same walk solved alone, bit for bit, in all three modes (tools/fuzz_layout.py)."""
+    import subprocess
+    import sys as _sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_layout.py")
+    run = subprocess.run([_sys.executable, tool, "8", "3"], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "all trials ok" in run.stdout, run.stdout[-2000:] + run.stderr[-2000:]
+
+
 def test_push_sweep_full_size_properties(engine, plan150):
     """BASELINE config 2 at full size (4096 scenarios, N=150, strict): size-independent properties."""
     B = 4096
