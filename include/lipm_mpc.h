@@ -13,8 +13,9 @@
  *   - every function returns LIPM_OK (0) or a negative LIPM_E_* code and never throws;
  *     lipm_last_error() returns a thread-local message for the last failure;
  *   - calls that take a stream are asynchronous on that stream (pass 0 for the legacy stream);
- *   - a plan is immutable after creation; rollouts on one plan must not overlap in time
- *     (they share the plan's tile counter) -- use one plan per concurrent stream;
+ *   - a plan is immutable after creation and RE-ENTRANT: rollouts / ticks on one plan may overlap on
+ *     different streams or threads as long as their output buffers are distinct (every launch carries
+ *     its own work counter; only lipm_plan_stats, "the last launch", is then ambiguous);
  *   - one axis-solve of one tick of one scenario is one "QP solve"; a scenario with n bound
  *     samples costs 2*(n-1) solves (reference loop zmp_controller.py:93-104).
  */
@@ -132,6 +133,65 @@ int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const in
                          int bounds_batch, const int32_t* bounds_index, const double* impulse,
                          const int32_t* force_tick, double* x_hist, double* y_hist, uint8_t* flags,
                          double* max_violation, int32_t* status, int32_t* iters, void* stream);
+
+/*
+ * Per-scenario outcome of a walk: what a sweep all-gathers across GPUs (32 bytes).  The reference computes no
+ * outcome; its drivers plot  C . state  against the bounds (scripts/run_compare_resistance.py:173-216).
+ */
+typedef struct lipm_outcome {
+    double max_violation;  /* max over axes and samples of max(z_min - zmp, zmp - z_max, 0)              */
+    double lean_max;       /* max over axes and samples of |CoM - ZMP| = (h/g) |CoM acceleration|        */
+    int32_t status;        /* QPs that hit max_iter, both axes (0 = every QP converged)                   */
+    int32_t fell;          /* lean_max > fall_lean (a definition of this library, see lipm_rollout_io_t) */
+    int64_t iters;         /* ADMM iterations, both axes                                                  */
+} lipm_outcome_t;
+
+/*
+ * Arguments of lipm_rollout_ex: lipm_rollout_indexed plus the read-outs the reference's drivers compute on the
+ * host after the walk -- the CoM path (zmp_controller.py:108 `com`), the realised ZMP  C . state
+ * (scripts/run_mpc.py:294, run_compare_resistance.py:173-174) -- and the packed per-scenario outcome.  They are
+ * written by the walk kernels themselves (the ZMP is in registers there), not by a second pass over the histories.
+ * Zero-initialise the struct; any output may be NULL.
+ */
+typedef struct lipm_rollout_io {
+    int32_t B, n_max;
+    const int32_t* n_steps;        /* dev [B] or NULL                                                    */
+    const double *x0, *y0;         /* dev [B,3]                                                          */
+    const double *z_min, *z_max;   /* dev [bounds_batch, n_max, 2]                                       */
+    int32_t bounds_batch;          /* 1, B, or the number of series V when bounds_index is given         */
+    const int32_t* bounds_index;   /* dev [B] or NULL                                                    */
+    const double* impulse;         /* dev [B] or NULL                                                    */
+    const int32_t* force_tick;     /* dev [B] or NULL                                                    */
+    /* outputs */
+    double *x_hist, *y_hist;       /* dev [B,n_max,3]                                                    */
+    double* com;                   /* dev [B,n_max,2]  (x_hist[..,0], y_hist[..,0])                      */
+    double* zmp;                   /* dev [B,n_max,2]  C . state per axis                                */
+    uint8_t* flags;                /* dev [B,n_max,2]                                                    */
+    double* max_violation;         /* dev [B,2]                                                          */
+    double* lean_max;              /* dev [B,2] per axis max |CoM - ZMP|                                 */
+    int32_t* status;               /* dev [B,2]                                                          */
+    int32_t* iters;                /* dev [B,2]                                                          */
+    lipm_outcome_t* outcome;       /* dev [B] packed record (both axes combined)                         */
+    double fall_lean;              /* fell = lean_max > fall_lean; <= 0 -> h tan(30 deg): the pendulum leans more
+                                      than 30 degrees.  In strict mode the ZMP cannot leave the sole, so an
+                                      unrecoverable push shows up as the CoM running away from it           */
+} lipm_rollout_io_t;
+
+int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, void* stream);
+
+/*
+ * Process- or plan-level switches that are off by default.
+ *   LIPM_OPT_KEEP_POOL_MEMORY (plan may be NULL; value = device ordinal): raise the release threshold of that
+ *       device's default stream-ordered memory pool so that the scratch buffers of the rollouts stay cached
+ *       between calls (with the default threshold the pool returns its memory to the driver at every
+ *       synchronisation; measured: 0.1 - 1 s on one call in three).  This changes the memory behaviour of the
+ *       whole process on that device, so the library never does it on its own.
+ *   LIPM_OPT_TICK_RANGES (plan required; value = 0 automatic, 1..8 forced): how many consecutive tick ranges the
+ *       FP64 strict kernel cuts a walk into for load balance.  Results do not depend on it (tested).
+ */
+#define LIPM_OPT_KEEP_POOL_MEMORY 1
+#define LIPM_OPT_TICK_RANGES 2
+int lipm_set_option(lipm_plan_t* plan, int option, long long value);
 
 /*
  * One control tick for a batch of independent axis problems: replaces

@@ -34,12 +34,39 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_tile_counter, p->d_stats, p->d_bf16, p->d_f16s};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }
 
+// One thread per scenario: the per-axis results of a walk -> the packed record a sweep all-gathers.
+__global__ void k_pack_outcomes(int B, const double* __restrict__ viol, const double* __restrict__ lean,
+                                const int32_t* __restrict__ status, const int32_t* __restrict__ iters, double fall_lean,
+                                lipm_outcome_t* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double2 v = reinterpret_cast<const double2*>(viol)[b];
+    const double2 l = reinterpret_cast<const double2*>(lean)[b];
+    const int2 s = reinterpret_cast<const int2*>(status)[b];
+    const int2 it = reinterpret_cast<const int2*>(iters)[b];
+    lipm_outcome_t r;
+    r.max_violation = fmax(v.x, v.y);
+    r.lean_max = fmax(l.x, l.y);
+    r.status = s.x + s.y;
+    r.fell = r.lean_max > fall_lean ? 1 : 0;
+    r.iters = (int64_t)it.x + (int64_t)it.y;
+    out[b] = r;
+}
+
 }  // namespace
+
+int launch_pack_outcomes(int B, const double* max_violation, const double* lean_max, const int32_t* status, const int32_t* iters,
+                         double fall_lean, lipm_outcome_t* outcome, cudaStream_t stream) {
+    if (B <= 0) return LIPM_OK;
+    k_pack_outcomes<<<(B + 255) / 256, 256, 0, stream>>>(B, max_violation, lean_max, status, iters, fall_lean, outcome);
+    LIPM_CUDA_TRY(cudaGetLastError());
+    return LIPM_OK;
+}
 }  // namespace lipm
 
 using namespace lipm;
@@ -48,7 +75,7 @@ extern "C" {
 
 const char* lipm_last_error(void) { return g_error; }
 
-const char* lipm_version(void) { return "lipm_mpc 0.2 (sm_100a; fp64 DMMA ADMM, tcgen05 f16x3 ADMM, gain-row unconstrained)"; }
+const char* lipm_version(void) { return "lipm_mpc 0.3 (sm_100a; fp64 DMMA ADMM, tcgen05 f16x3 ADMM, gain-row unconstrained)"; }
 
 int lipm_max_reduced_horizon(void) { return kMaxReducedStreamHorizon; }
 
@@ -113,17 +140,6 @@ int lipm_plan_create(lipm_plan_t** out, const lipm_plan_desc_t* desc) {
         return LIPM_E_UNSUPPORTED;
     }
     plan->sm_count = prop.multiProcessorCount;
-    {
-        // The rollouts take their small scratch buffers (sort keys, dispatch order) from the stream-ordered
-        // allocator.  With the default release threshold (0) the pool hands its memory back to the driver at
-        // every synchronisation and maps it again on the next call; keep it cached instead.
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, d.device) == cudaSuccess && pool) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
     const int rc = build_plan_matrices(plan);
     if (rc != LIPM_OK) {
         free_plan_buffers(plan);
@@ -169,6 +185,30 @@ int lipm_plan_stats(const lipm_plan_t* plan, uint64_t* host_out) {
     return LIPM_OK;
 }
 
+int lipm_set_option(lipm_plan_t* plan, int option, long long value) {
+    switch (option) {
+        case LIPM_OPT_KEEP_POOL_MEMORY: {
+            int count = 0;
+            if (cudaGetDeviceCount(&count) != cudaSuccess || value < 0 || value >= count) {
+                set_error("lipm_set_option(KEEP_POOL_MEMORY): bad device %lld", value);
+                return LIPM_E_INVALID;
+            }
+            cudaMemPool_t pool = nullptr;
+            LIPM_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, (int)value));
+            unsigned long long keep = ~0ull;
+            LIPM_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            return LIPM_OK;
+        }
+        case LIPM_OPT_TICK_RANGES:
+            if (!plan || value < 0 || value > 8) { set_error("lipm_set_option(TICK_RANGES): need a plan and a value in [0, 8]"); return LIPM_E_INVALID; }
+            plan->force_segments = (int)value;
+            return LIPM_OK;
+        default:
+            set_error("lipm_set_option: unknown option %d", option);
+            return LIPM_E_INVALID;
+    }
+}
+
 int lipm_rollout(lipm_plan_t* plan, int mode, int B, int n_max, const int32_t* n_steps, const double* x0,
                  const double* y0, const double* z_min, const double* z_max, int bounds_batch,
                  const double* impulse, const int32_t* force_tick, double* x_hist, double* y_hist,
@@ -182,13 +222,25 @@ int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const in
                          const int32_t* bounds_index, const double* impulse, const int32_t* force_tick,
                          double* x_hist, double* y_hist, uint8_t* flags, double* max_violation, int32_t* status,
                          int32_t* iters, void* stream) {
-    if (!plan) { set_error("lipm_rollout: null plan"); return LIPM_E_INVALID; }
+    lipm_rollout_io_t io;
+    std::memset(&io, 0, sizeof(io));
+    io.B = B; io.n_max = n_max; io.n_steps = n_steps; io.x0 = x0; io.y0 = y0; io.z_min = z_min; io.z_max = z_max;
+    io.bounds_batch = bounds_batch; io.bounds_index = bounds_index; io.impulse = impulse; io.force_tick = force_tick;
+    io.x_hist = x_hist; io.y_hist = y_hist; io.flags = flags; io.max_violation = max_violation; io.status = status;
+    io.iters = iters;
+    return lipm_rollout_ex(plan, mode, &io, stream);
+}
+
+int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, void* stream_) {
+    if (!plan || !io) { set_error("lipm_rollout: null plan / arguments"); return LIPM_E_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int B = io->B, n_max = io->n_max, bounds_batch = io->bounds_batch;
     if (mode != LIPM_MODE_STRICT && mode != LIPM_MODE_UNCONSTRAINED) { set_error("lipm_rollout: bad mode %d", mode); return LIPM_E_INVALID; }
     if (B < 0 || n_max < 2) { set_error("lipm_rollout: need B >= 0 and n_max >= 2 (got %d, %d)", B, n_max); return LIPM_E_INVALID; }
     if (B == 0) return LIPM_OK;
-    if (!x0 || !y0 || !z_min || !z_max) { set_error("lipm_rollout: x0, y0, z_min, z_max are required"); return LIPM_E_INVALID; }
-    if (!bounds_index && bounds_batch != 1 && bounds_batch != B) { set_error("lipm_rollout: bounds_batch must be 1 or B (got %d, B=%d)", bounds_batch, B); return LIPM_E_INVALID; }
-    if (bounds_index && bounds_batch < 1) { set_error("lipm_rollout_indexed: bounds_batch must be the number of series (got %d)", bounds_batch); return LIPM_E_INVALID; }
+    if (!io->x0 || !io->y0 || !io->z_min || !io->z_max) { set_error("lipm_rollout: x0, y0, z_min, z_max are required"); return LIPM_E_INVALID; }
+    if (!io->bounds_index && bounds_batch != 1 && bounds_batch != B) { set_error("lipm_rollout: bounds_batch must be 1 or B (got %d, B=%d)", bounds_batch, B); return LIPM_E_INVALID; }
+    if (io->bounds_index && bounds_batch < 1) { set_error("lipm_rollout_indexed: bounds_batch must be the number of series (got %d)", bounds_batch); return LIPM_E_INVALID; }
     if ((long long)B * 2 > 0x7fffffffLL / 8) { set_error("lipm_rollout: batch too large"); return LIPM_E_INVALID; }
     DeviceGuard guard(plan->desc.device);
 
@@ -197,51 +249,73 @@ int lipm_rollout_indexed(lipm_plan_t* plan, int mode, int B, int n_max, const in
     cb.ncols = 2 * B;
     cb.B = B;
     cb.bounds_batch = bounds_batch;
-    cb.bounds_index = bounds_index;
+    cb.bounds_index = io->bounds_index;
     cb.bound_scn_stride = (long long)n_max * 2;
     cb.bound_stride = 2;
     cb.bound_axis_offset = 1;
     cb.bound_index_bias = 1;
     cb.n_max = n_max;
-    cb.n_steps = n_steps;
+    cb.n_steps = io->n_steps;
     cb.n_uniform = n_max;
     cb.ticks_override = 0;
-    cb.init[0] = x0; cb.init[1] = y0;
-    cb.z_min = z_min; cb.z_max = z_max;
-    cb.impulse = impulse; cb.force_tick = force_tick;
-    cb.hist[0] = x_hist; cb.hist[1] = y_hist;
+    cb.init[0] = io->x0; cb.init[1] = io->y0;
+    cb.z_min = io->z_min; cb.z_max = io->z_max;
+    cb.impulse = io->impulse; cb.force_tick = io->force_tick;
+    cb.hist[0] = io->x_hist; cb.hist[1] = io->y_hist;
     cb.write_initial = 1;
     cb.hist_scn_stride = (long long)n_max * 3;
     cb.hist_index_bias = 0;
-    cb.flags = flags;
-    cb.max_violation = max_violation;
-    cb.status = status;
-    cb.iters = iters;
+    cb.flags = io->flags;
+    cb.max_violation = io->max_violation;
+    cb.lean_max = io->lean_max;
+    cb.status = io->status;
+    cb.iters = io->iters;
+    cb.com = io->com;
+    cb.zmp = io->zmp;
     cb.zmp_plan = nullptr;
-    if (mode != LIPM_MODE_STRICT) return launch_unconstrained_rollout(plan, cb, (cudaStream_t)stream);
-    // strict walks: group scenarios that will need similar iteration counts (lipm_order.cu)
-    int* order = nullptr;
-    if (B > 8 && (n_steps || (impulse && force_tick))) {
-        const int rc = build_processing_order(B, n_max, n_steps, impulse, force_tick,
-                                              plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : 8, &order, (cudaStream_t)stream);
-        if (rc != LIPM_OK) return rc;
-    }
-    cb.order = order;
-    // longest-expected-first dispatch of the kernel's work units (8 columns FP64, 128 columns reduced precision)
-    int* unit_order = nullptr;
-    {
-        const int width = plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : 8;
-        const int units = (cb.ncols + width - 1) / width;
-        if (units > 1 && impulse && force_tick) {
-            const int rc_u = build_unit_order(units, width, cb.ncols, B, order, n_max, n_steps, impulse, force_tick, &unit_order,
-                                              (cudaStream_t)stream);
-            if (rc_u != LIPM_OK) return rc_u;
+
+    // the packed record needs all four per-axis results: stage the ones the caller did not ask for
+    StreamBuffer axis_scratch;
+    if (io->outcome) {
+        const size_t per = (size_t)B * 2;
+        const size_t need = (cb.max_violation ? 0 : per * sizeof(double)) + (cb.lean_max ? 0 : per * sizeof(double)) +
+                            (cb.status ? 0 : per * sizeof(int32_t)) + (cb.iters ? 0 : per * sizeof(int32_t));
+        if (need) {
+            LIPM_CUDA_TRY(axis_scratch.alloc(need, stream));
+            unsigned char* p = axis_scratch.as<unsigned char>();
+            if (!cb.max_violation) { cb.max_violation = reinterpret_cast<double*>(p); p += per * sizeof(double); }
+            if (!cb.lean_max) { cb.lean_max = reinterpret_cast<double*>(p); p += per * sizeof(double); }
+            if (!cb.status) { cb.status = reinterpret_cast<int32_t*>(p); p += per * sizeof(int32_t); }
+            if (!cb.iters) { cb.iters = reinterpret_cast<int32_t*>(p); p += per * sizeof(int32_t); }
         }
     }
-    cb.unit_order = unit_order;
-    const int rc = launch_strict(plan, cb, (cudaStream_t)stream);
-    if (order) cudaFreeAsync(order, (cudaStream_t)stream);
-    if (unit_order) cudaFreeAsync(unit_order, (cudaStream_t)stream);
+
+    int rc;
+    if (mode != LIPM_MODE_STRICT) {
+        rc = launch_unconstrained_rollout(plan, cb, stream);
+    } else {
+        // strict walks: group scenarios that will need similar iteration counts (lipm_order.cu)
+        const int width = plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : 8;
+        StreamBuffer order, unit_order;        // released on every path out of this scope
+        if (B > 8 && (io->n_steps || (io->impulse && io->force_tick))) {
+            rc = build_processing_order(B, n_max, io->n_steps, io->impulse, io->force_tick, width, order, stream);
+            if (rc != LIPM_OK) return rc;
+        }
+        cb.order = order.as<int>();
+        // longest-expected-first dispatch of the kernel's work units (8 columns FP64, 128 columns reduced precision)
+        const int units = (cb.ncols + width - 1) / width;
+        if (units > 1 && io->impulse && io->force_tick) {
+            rc = build_unit_order(units, width, cb.ncols, B, cb.order, n_max, io->n_steps, io->impulse, io->force_tick, unit_order, stream);
+            if (rc != LIPM_OK) return rc;
+        }
+        cb.unit_order = unit_order.as<int>();
+        rc = launch_strict(plan, cb, stream);
+    }
+    if (rc != LIPM_OK) return rc;
+    if (io->outcome) {
+        const double fall = io->fall_lean > 0 ? io->fall_lean : plan->desc.h * 0.57735026918962576451;   // h tan(30 deg)
+        rc = launch_pack_outcomes(B, cb.max_violation, cb.lean_max, cb.status, cb.iters, fall, io->outcome, stream);
+    }
     return rc;
 }
 
@@ -283,9 +357,11 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
     cb.zmp_plan = (mode == LIPM_MODE_STRICT) ? zmp_plan : nullptr;
 
     // status / iters of the walk kernels are laid out [B,2]; stage them when requested
+    StreamBuffer stage_buf;
     int32_t* stage = nullptr;
     if (status || iters) {
-        LIPM_CUDA_TRY(cudaMallocAsync(&stage, sizeof(int32_t) * 4 * (size_t)B, (cudaStream_t)stream));
+        LIPM_CUDA_TRY(stage_buf.alloc(sizeof(int32_t) * 4 * (size_t)B, (cudaStream_t)stream));
+        stage = stage_buf.as<int32_t>();
         cb.status = stage;
         cb.iters = stage + 2 * (size_t)B;
     }
@@ -295,7 +371,6 @@ int lipm_solve_tick(lipm_plan_t* plan, int mode, int B, const double* state, con
         if (status) LIPM_CUDA_TRY(cudaMemcpy2DAsync(status, sizeof(int32_t), stage, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         if (iters) LIPM_CUDA_TRY(cudaMemcpy2DAsync(iters, sizeof(int32_t), stage + 2 * (size_t)B, 2 * sizeof(int32_t), sizeof(int32_t), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }
-    if (stage) cudaFreeAsync(stage, (cudaStream_t)stream);
     if (rc != LIPM_OK) return rc;
 
     if (zmp_plan && mode == LIPM_MODE_UNCONSTRAINED) {

@@ -22,6 +22,47 @@ void set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// Stream-ordered scratch memory that is released on every exit path (cudaFreeAsync on the stream it
+// was allocated on), so an early LIPM_CUDA_TRY return does not leak it.
+struct StreamBuffer {
+    void* ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    StreamBuffer() = default;
+    StreamBuffer(const StreamBuffer&) = delete;
+    StreamBuffer& operator=(const StreamBuffer&) = delete;
+    ~StreamBuffer() { reset(); }
+    void reset() {
+        if (ptr) cudaFreeAsync(ptr, stream);
+        ptr = nullptr;
+    }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        reset();
+        stream = s;
+        return cudaMallocAsync(&ptr, bytes ? bytes : 16, s);
+    }
+    cudaError_t alloc_zero(size_t bytes, cudaStream_t s) {
+        cudaError_t e = alloc(bytes, s);
+        return e != cudaSuccess ? e : cudaMemsetAsync(ptr, 0, bytes ? bytes : 16, s);
+    }
+    template <class T> T* as() const { return static_cast<T*>(ptr); }
+    void* release() { void* p = ptr; ptr = nullptr; return p; }
+};
+
+// Per-launch scheduler state of the persistent kernels: [0..1] work counter (+pad), [2..9] four 64-bit statistics
+// words.  It lives in stream-ordered memory of ITS launch, so rollouts on one plan may overlap on
+// different streams; the statistics of the launch are copied into the plan afterwards (lipm_plan_stats).
+constexpr size_t kLaunchStateBytes = 16 + 4 * sizeof(unsigned long long);
+struct LaunchState {
+    StreamBuffer buf;
+    cudaError_t begin(cudaStream_t s) { return buf.alloc_zero(kLaunchStateBytes, s); }
+    unsigned int* counter() const { return buf.as<unsigned int>(); }
+    unsigned long long* stats() const { return reinterpret_cast<unsigned long long*>(buf.as<unsigned char>() + 16); }
+    // file the statistics of this launch in the plan (last writer wins when launches overlap)
+    cudaError_t publish(unsigned long long* plan_stats) const {
+        return cudaMemcpyAsync(plan_stats, stats(), 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, buf.stream);
+    }
+};
+
 // ------------------------------------------------------------------ geometry helpers
 // DMMA.8x8x4 tiles: rows and the contraction index are padded to a multiple of 8.
 __host__ __device__ inline int padded8(int n) { return (n + 7) & ~7; }
@@ -79,9 +120,9 @@ struct lipm_plan {
     unsigned char* d_f16s; // FP16 hi / lo images of [M | M G Px] cut into 160-row slabs (F16X3 plans, N > 152)
     int f16s_nk;           // padded contraction length of d_f16s: multiple of 16, >= N + 3
     int f16s_slabs;        // 160-row slabs
+    int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
-    unsigned int* d_tile_counter;  // dynamic work-unit scheduler of the strict kernel
-    unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch
+    unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch (copied from the launch's own state)
 };
 
 namespace lipm {
@@ -119,12 +160,19 @@ struct ColumnBatch {
     int32_t* status;        // [B,2] or nullptr
     int32_t* iters;         // [B,2] or nullptr
     double* zmp_plan;       // [ncols,N] or nullptr: final previewed ZMP of the last tick
+    // read-out fused into the walk kernels (the drivers' C . state, scripts/run_mpc.py:294)
+    double* com;            // [B,n_max,2] CoM position per sample (x, y interleaved) or nullptr
+    double* zmp;            // [B,n_max,2] realised ZMP  C . state  per sample or nullptr
+    double* lean_max;       // [B,2] per axis: max over samples of |CoM - ZMP| or nullptr
 };
 
 int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
-                           const int32_t* force_tick, int width, int** perm_out, cudaStream_t stream);
+                           const int32_t* force_tick, int width, StreamBuffer& out, cudaStream_t stream);
 int build_unit_order(int num_units, int width, int ncols, int B, const int* order, int n_uniform, const int32_t* n_steps,
-                     const double* impulse, const int32_t* force_tick, int** unit_order_out, cudaStream_t stream);
+                     const double* impulse, const int32_t* force_tick, StreamBuffer& out, cudaStream_t stream);
+// per-scenario outcome record from the per-axis results of a walk (lipm_rollout_ex)
+int launch_pack_outcomes(int B, const double* max_violation, const double* lean_max, const int32_t* status, const int32_t* iters,
+                         double fall_lean, lipm_outcome_t* outcome, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);

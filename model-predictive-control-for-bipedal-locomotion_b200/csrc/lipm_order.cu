@@ -93,62 +93,55 @@ __global__ void k_unit_work(int num_units, int width, int ncols, int B, const in
 }  // namespace
 
 // Dispatch order of the units (longest expected first, so that the tail of the launch is filled with short
-// units): unit_order[i] = unit handed out i-th.  Released by the caller with cudaFreeAsync.
+// units): unit_order[i] = unit handed out i-th.  The result lives in `out` (released by its destructor).
 int build_unit_order(int num_units, int width, int ncols, int B, const int* order, int n_uniform, const int32_t* n_steps,
-                     const double* impulse, const int32_t* force_tick, int** unit_order_out, cudaStream_t stream) {
-    *unit_order_out = nullptr;
-    float *keys_in = nullptr, *keys_out = nullptr;
-    int *ids_in = nullptr, *ids_out = nullptr;
-    void* temp = nullptr;
+                     const double* impulse, const int32_t* force_tick, StreamBuffer& out, cudaStream_t stream) {
     size_t temp_bytes = 0;
-    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, ids_in, ids_out, num_units, 0, 32, stream));
-    LIPM_CUDA_TRY(cudaMallocAsync(&keys_in, sizeof(float) * 2 * (size_t)num_units, stream));
-    keys_out = keys_in + num_units;
-    LIPM_CUDA_TRY(cudaMallocAsync(&ids_in, sizeof(int) * (size_t)num_units, stream));
-    LIPM_CUDA_TRY(cudaMallocAsync(&ids_out, sizeof(int) * (size_t)num_units, stream));
-    LIPM_CUDA_TRY(cudaMallocAsync(&temp, temp_bytes ? temp_bytes : 16, stream));
+    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (float*)nullptr, (float*)nullptr, (int*)nullptr, (int*)nullptr,
+                                                  num_units, 0, 32, stream));
+    StreamBuffer keys, ids_in, temp;
+    LIPM_CUDA_TRY(keys.alloc(sizeof(float) * 2 * (size_t)num_units, stream));
+    LIPM_CUDA_TRY(ids_in.alloc(sizeof(int) * (size_t)num_units, stream));
+    LIPM_CUDA_TRY(out.alloc(sizeof(int) * (size_t)num_units, stream));
+    LIPM_CUDA_TRY(temp.alloc(temp_bytes, stream));
+    float* keys_in = keys.as<float>();
     k_unit_work<<<(num_units + 127) / 128, 128, 0, stream>>>(num_units, width, ncols, B, order, n_uniform, n_steps, impulse,
-                                                             force_tick, keys_in, ids_in);
+                                                             force_tick, keys_in, ids_in.as<int>());
     LIPM_CUDA_TRY(cudaGetLastError());
-    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, ids_in, ids_out, num_units, 0, 32, stream));
-    LIPM_CUDA_TRY(cudaFreeAsync(temp, stream));
-    LIPM_CUDA_TRY(cudaFreeAsync(keys_in, stream));
-    LIPM_CUDA_TRY(cudaFreeAsync(ids_in, stream));
-    *unit_order_out = ids_out;
+    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in, keys_in + num_units, ids_in.as<int>(), out.as<int>(),
+                                                  num_units, 0, 32, stream));
     return LIPM_OK;
 }
 
-// perm[slot] = scenario processed in that slot.  Buffers come from the stream-ordered allocator;
-// `*perm_out` must be released with cudaFreeAsync on the same stream after the rollout launch.
+// perm[slot] = scenario processed in that slot, in `out` (stream-ordered memory, released by its destructor).
 int build_processing_order(int B, int n_uniform, const int32_t* n_steps, const double* impulse,
-                           const int32_t* force_tick, int width, int** perm_out, cudaStream_t stream) {
-    *perm_out = nullptr;
-    unsigned long long *keys_in = nullptr, *keys_out = nullptr;
-    int *ids_in = nullptr, *ids_out = nullptr;
-    void* temp = nullptr;
+                           const int32_t* force_tick, int width, StreamBuffer& out, cudaStream_t stream) {
     size_t temp_bytes = 0;
-    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, ids_in, ids_out, B, 0, 64, stream));
-    LIPM_CUDA_TRY(cudaMallocAsync(&keys_in, sizeof(unsigned long long) * 2 * (size_t)B, stream));
-    keys_out = keys_in + B;
-    LIPM_CUDA_TRY(cudaMallocAsync(&ids_in, sizeof(int) * (size_t)B, stream));
-    LIPM_CUDA_TRY(cudaMallocAsync(&ids_out, sizeof(int) * (size_t)B, stream));
-    LIPM_CUDA_TRY(cudaMallocAsync(&temp, temp_bytes ? temp_bytes : 16, stream));
+    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                                  (int*)nullptr, (int*)nullptr, B, 0, 64, stream));
+    StreamBuffer keys, ids_in, temp, span;
+    LIPM_CUDA_TRY(keys.alloc(sizeof(unsigned long long) * 2 * (size_t)B, stream));
+    LIPM_CUDA_TRY(ids_in.alloc(sizeof(int) * (size_t)B, stream));
+    LIPM_CUDA_TRY(out.alloc(sizeof(int) * (size_t)B, stream));
+    LIPM_CUDA_TRY(temp.alloc(temp_bytes, stream));
+    unsigned long long* keys_in = keys.as<unsigned long long>();
     int tick_bin = 0;                                     // 0: from the batch (k_order_keys)
-    if (const char* env = std::getenv("LIPM_ORDER_TICK_BIN")) tick_bin = std::atoi(env);      // measurement knob
-    int* span = nullptr;
-    if (impulse && force_tick && tick_bin <= 0) {
-        LIPM_CUDA_TRY(cudaMallocAsync(&span, 2 * sizeof(int), stream));
-        k_tick_span<<<1, 1024, 0, stream>>>(B, force_tick, span);
+#ifdef LIPM_DEBUG_KNOBS
+    if (const char* env = std::getenv("LIPM_ORDER_TICK_BIN")) {      // measurement knob (tools/admm_tune.py)
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= 4096) tick_bin = v;
     }
-    k_order_keys<<<(B + 255) / 256, 256, 0, stream>>>(B, n_uniform, n_steps, impulse, force_tick, span ? 0 : (tick_bin > 0 ? tick_bin : 1),
-                                                      width, span, keys_in, ids_in);
-    if (span) LIPM_CUDA_TRY(cudaFreeAsync(span, stream));
+#endif
+    if (impulse && force_tick && tick_bin <= 0) {
+        LIPM_CUDA_TRY(span.alloc(2 * sizeof(int), stream));
+        k_tick_span<<<1, 1024, 0, stream>>>(B, force_tick, span.as<int>());
+    }
+    k_order_keys<<<(B + 255) / 256, 256, 0, stream>>>(B, n_uniform, n_steps, impulse, force_tick,
+                                                      span.ptr ? 0 : (tick_bin > 0 ? tick_bin : 1), width, span.as<int>(), keys_in,
+                                                      ids_in.as<int>());
     LIPM_CUDA_TRY(cudaGetLastError());
-    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, ids_in, ids_out, B, 0, 64, stream));
-    LIPM_CUDA_TRY(cudaFreeAsync(temp, stream));
-    LIPM_CUDA_TRY(cudaFreeAsync(keys_in, stream));
-    LIPM_CUDA_TRY(cudaFreeAsync(ids_in, stream));
-    *perm_out = ids_out;
+    LIPM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, keys_in, keys_in + B, ids_in.as<int>(), out.as<int>(), B, 0, 64,
+                                                  stream));
     return LIPM_OK;
 }
 

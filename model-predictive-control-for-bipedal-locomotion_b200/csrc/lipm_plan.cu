@@ -311,9 +311,7 @@ int build_plan_matrices(lipm_plan* plan) {
     LIPM_CUDA_TRY(cudaMalloc(&plan->d_mfrag, sizeof(double) * (size_t)(NP / 8) * (NP / 4) * 32));
     LIPM_CUDA_TRY(cudaMalloc(&plan->d_gain, sizeof(double) * (N + 3)));
     LIPM_CUDA_TRY(cudaMalloc(&plan->d_info, sizeof(int) * 4));
-    LIPM_CUDA_TRY(cudaMalloc(&plan->d_tile_counter, sizeof(unsigned int)));
     LIPM_CUDA_TRY(cudaMemset(plan->d_info, 0, sizeof(int) * 4));
-    LIPM_CUDA_TRY(cudaMemset(plan->d_tile_counter, 0, sizeof(unsigned int)));
     LIPM_CUDA_TRY(cudaMalloc(&plan->d_stats, 4 * sizeof(unsigned long long)));
     LIPM_CUDA_TRY(cudaMemset(plan->d_stats, 0, 4 * sizeof(unsigned long long)));
 

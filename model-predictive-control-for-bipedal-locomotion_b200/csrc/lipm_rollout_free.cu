@@ -167,14 +167,17 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
     const ColumnView v = column_view(B, c);
     const int ticks = valid ? v.ticks : 0;
     double* hist = nullptr;
+    double *pcom = nullptr, *pzmp = nullptr;
     uint8_t* pf = nullptr;
-    double x0 = 0.0, x1 = 0.0, x2 = 0.0, imp = 0.0, viol = 0.0;
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, imp = 0.0, viol = 0.0, lean = 0.0;
     int ftick = -1;
     const double* preview = P.preview + (size_t)(P.per_column ? (long long)local : v.bz * 2 + v.axis) * P.ticks_max;
     if (valid) {
         hist = v.axis ? B.hist[1] : B.hist[0];
         if (hist) hist += (long long)v.b * B.hist_scn_stride;
         pf = B.flags ? B.flags + ((long long)v.b * B.n_max) * 2 + v.axis : nullptr;
+        pcom = B.com ? B.com + ((long long)v.b * B.n_max) * 2 + v.axis : nullptr;
+        pzmp = B.zmp ? B.zmp + ((long long)v.b * B.n_max) * 2 + v.axis : nullptr;
         const double* init = (v.axis ? B.init[1] : B.init[0]) + (long long)v.b * 3;
         x0 = init[0]; x1 = init[1]; x2 = init[2];
         if (v.axis == 1 && B.impulse != nullptr) {
@@ -185,7 +188,10 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
             const double zmp = x0 - P.hg * x2;
             const double below = v.plo[0] - zmp, above = zmp - v.phi[0];
             viol = fmax(fmax(below, above), 0.0);
+            lean = fabs(x0 - zmp);
             if (hist) { hist[0] = x0; hist[1] = x1; hist[2] = x2; }
+            if (pcom) pcom[0] = x0;
+            if (pzmp) pzmp[0] = zmp;
             if (pf) pf[0] = (uint8_t)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                       (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
         }
@@ -223,6 +229,10 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
                 const double zmp = n0 - P.hg * n2;
                 const double below = l0[l] - zmp, above = zmp - h0[l];
                 viol = fmax(viol, fmax(fmax(below, above), 0.0));
+                lean = fmax(lean, fabs(n0 - zmp));
+                // x and y of a sample are neighbours in com / zmp: the two columns of a scenario fill one 16-byte pair
+                if (pcom) pcom[(long long)(i + 1) * 2] = n0;
+                if (pzmp) pzmp[(long long)(i + 1) * 2] = zmp;
                 flag8 |= (unsigned long long)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                               (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u)) << (8 * l);
             }
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
     }
     if (valid) {
         if (B.max_violation) B.max_violation[v.b * 2 + v.axis] = viol;
+        if (B.lean_max) B.lean_max[v.b * 2 + v.axis] = lean;
         if (B.status) B.status[v.b * 2 + v.axis] = 0;
         if (B.iters) B.iters[v.b * 2 + v.axis] = 0;
     }
@@ -359,7 +370,9 @@ int launch_dense(lipm_plan* plan, DenseParams& P, cudaStream_t stream) {
     LIPM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned ctas = (P.num_units + NG - 1) / NG;
     const unsigned grid = ctas < (unsigned)plan->sm_count ? ctas : (unsigned)plan->sm_count;
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
+    LaunchState state;
+    LIPM_CUDA_TRY(state.begin(stream));
+    P.tile_counter = state.counter();
     kernel<<<grid, 32 * kRowGroups * NG, smem, stream>>>(P);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;
@@ -407,9 +420,9 @@ int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStr
     P.per_column = (cb.n_steps != nullptr || (cb.bounds_batch != 1 && cb.bounds_index == nullptr)) ? 1 : 0;
     const int chunk = P.per_column ? kFreeChunk : cb.ncols;
     const size_t series = P.per_column ? (size_t)(cb.ncols < chunk ? cb.ncols : chunk) : (size_t)cb.bounds_batch * 2;
-    double* preview = nullptr;
-    LIPM_CUDA_TRY(cudaMallocAsync(&preview, sizeof(double) * series * (size_t)P.ticks_max, stream));
-    P.preview = preview;
+    StreamBuffer preview;
+    LIPM_CUDA_TRY(preview.alloc(sizeof(double) * series * (size_t)P.ticks_max, stream));
+    P.preview = preview.as<double>();
     for (int col0 = 0; col0 < cb.ncols; col0 += chunk) {
         P.col0 = col0;
         P.ncols = cb.ncols - col0 < chunk ? cb.ncols - col0 : chunk;
@@ -427,7 +440,6 @@ int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStr
         k_free_rollout<<<grid, 32 * kFreeWarps, 0, stream>>>(P);
     }
     LIPM_CUDA_TRY(cudaGetLastError());
-    LIPM_CUDA_TRY(cudaFreeAsync(preview, stream));
     return LIPM_OK;
 }
 
@@ -439,7 +451,7 @@ int launch_unconstrained_plan(lipm_plan* plan, int ncols, const double* state, c
     P.Q = plan->desc.Q;
     P.hfrag = plan->d_hfrag; P.gpx = plan->d_gpx; P.state = state; P.z_min = z_min; P.z_max = z_max;
     P.zmp_plan = zmp_plan;
-    P.tile_counter = plan->d_tile_counter;
+    P.tile_counter = nullptr;
     P.num_units = (unsigned)((ncols + kGroupCols - 1) / kGroupCols);
     const int rblk = plan->NP / 8;
     if (plan->N <= kMaxResidentHorizon) {

@@ -78,6 +78,9 @@ struct GroupFixed {
     double X[kGroupCols * 3];                 // current axis state
     double Imp[kGroupCols];                   // dt*F/m of the push
     double Viol[kGroupCols];                  // running max box violation
+    double Lean[kGroupCols];                  // running max |CoM - ZMP|
+    double* Com[kGroupCols];                  // &com[b][0][axis] / &zmp[b][0][axis] (nullptr: not requested)
+    double* Zmp[kGroupCols];
     const double* Lo[kGroupCols];             // bound series of each column
     const double* Hi[kGroupCols];
     double* Hist[kGroupCols];
@@ -115,6 +118,11 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
     const int g = lane >> 2, t = lane & 3;
     const ColumnBatch& B = P.cb;
     const int bar_id = 1 + grp;
+#ifdef LIPM_DEBUG_KNOBS
+    const int dbg_skip = P.debug_skip;
+#else
+    constexpr int dbg_skip = 0;      // the measurement knobs are compiled out of the shipped library
+#endif
 
     unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem_raw);
     constexpr size_t kFixedStride = (sizeof(GroupFixed<RG>) + 15) & ~(size_t)15;
@@ -198,17 +206,23 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 const double* s = (axis ? B.init[1] : B.init[0]) + (long long)b * 3;
                 x0 = s[0]; x1 = s[1]; x2 = s[2];
             }
-            double viol = 0.0;
+            double viol = 0.0, lean = 0.0;
+            double* pcom = (valid && B.com) ? B.com + ((long long)b * B.n_max) * 2 + axis : nullptr;
+            double* pzmp = (valid && B.zmp) ? B.zmp + ((long long)b * B.n_max) * 2 + axis : nullptr;
             if (valid && B.write_initial && ticks > 0 && seg == 0) {
                 const double zmp = x0 - P.hg * x2;
                 const double below = plo[0] - zmp, above = zmp - phi[0];
                 viol = fmax(fmax(below, above), 0.0);
+                lean = fabs(x0 - zmp);
                 if (ph) { ph[0] = x0; ph[1] = x1; ph[2] = x2; }
+                if (pcom) pcom[0] = x0;
+                if (pzmp) pzmp[0] = zmp;
                 if (pf) pf[0] = (uint8_t)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                           (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
             }
             const bool push = valid && axis == 1 && B.impulse != nullptr;
             S.Lo[gtid] = plo; S.Hi[gtid] = phi; S.Hist[gtid] = ph; S.Flag[gtid] = pf;
+            S.Com[gtid] = pcom; S.Zmp[gtid] = pzmp; S.Lean[gtid] = lean;
             S.Zplan[gtid] = (valid && B.zmp_plan) ? B.zmp_plan + (long long)c * N : nullptr;
             S.Nser[gtid] = n; S.Nticks[gtid] = ticks;
             S.Imp[gtid] = push ? B.impulse[b] : 0.0;
@@ -243,7 +257,8 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 S.X[gtid * 3 + 1] = __ldcg(c + gtid * 3 + 1);
                 S.X[gtid * 3 + 2] = __ldcg(c + gtid * 3 + 2);
                 S.Viol[gtid] = __ldcg(c + 3 * kGroupCols + gtid);
-                const int* ci = reinterpret_cast<const int*>(c + 4 * kGroupCols);
+                S.Lean[gtid] = __ldcg(c + 4 * kGroupCols + gtid);
+                const int* ci = reinterpret_cast<const int*>(c + 5 * kGroupCols);
                 S.Iter[gtid] = __ldcg(ci + gtid);
                 S.NotConv[gtid] = __ldcg(ci + kGroupCols + gtid);
                 S.Nticks[gtid] = __ldcg(ci + 2 * kGroupCols + gtid);
@@ -357,9 +372,9 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 for (int r = 0; r < NRB; ++r) acc[r][0] = acc[r][1] = 0.0;
 
                 long long tc0 = 0;
-                if (P.debug_skip & 16) tc0 = clock64();
-                if (!(P.debug_skip & 1)) ContractDispatch<NRB, NRB, NPC / 4, STREAM>::run(nrb, acc, aBase, aStride, bBase, KB);
-                if ((P.debug_skip & 16) && tid == 0) {
+                if (dbg_skip & 16) tc0 = clock64();
+                if (!(dbg_skip & 1)) ContractDispatch<NRB, NRB, NPC / 4, STREAM>::run(nrb, acc, aBase, aStride, bBase, KB);
+                if ((dbg_skip & 16) && tid == 0) {
                     // wait for the accumulators, then charge the elapsed cycles to the contraction
                     double sink = 0.0;
 #pragma unroll
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 uint32_t rd[2] = {0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    if (!done[e] && !(P.debug_skip & 2)) {
+                    if (!done[e] && !(dbg_skip & 2)) {
 #pragma unroll
                         for (int r = 0; r < NRB; ++r) {
                             if (r >= nrb) continue;
@@ -393,7 +408,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                     for (int o = 4; o <= 16; o <<= 1) rd[e] = max(rd[e], __shfl_xor_sync(0xffffffffu, rd[e], o));
                     if (g == 0) S.Res[0][rg][lc0 + e] = rd[e];
                 }
-                if (!(P.debug_skip & 4)) group_sync<kGroupThreads>(bar_id);   // every warp of the group has consumed R; partials are visible
+                if (!(dbg_skip & 4)) group_sync<kGroupThreads>(bar_id);   // every warp of the group has consumed R; partials are visible
 
                 bool all_mine = true;
 #pragma unroll
@@ -406,13 +421,13 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
 #pragma unroll
                         for (int q4 = 1; q4 < RG; ++q4) cd = max(cd, S.Res[0][q4][lc0 + e]);
                         ++iters[e];
-                        done[e] = (cd <= thr[e]) && !(P.debug_skip & 8);
+                        done[e] = (cd <= thr[e]) && !(dbg_skip & 8);
                     }
                     all_mine = all_mine && done[e];
                 }
                 ++group_iters;
                 const bool stop = group_sync_and<kGroupThreads>(bar_id, all_mine);   // new R visible; partials consumed
-                if ((P.debug_skip & 16) && tid == 0) atomicAdd(P.stats + 3, (unsigned long long)(clock64() - tc0));
+                if ((dbg_skip & 16) && tid == 0) atomicAdd(P.stats + 3, (unsigned long long)(clock64() - tc0));
                 if (stop) break;
             }
 
@@ -433,6 +448,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                     const double zmp = n0 - P.hg * n2;
                     const double below = l0 - zmp, above = zmp - h0;
                     S.Viol[lc] = fmax(S.Viol[lc], fmax(fmax(below, above), 0.0));
+                    S.Lean[lc] = fmax(S.Lean[lc], fabs(n0 - zmp));
                     unsigned f = (below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                  (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u);
                     if (P.strict_flags)
@@ -452,6 +468,8 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                         dst[0] = n0; dst[1] = n1; dst[2] = n2;
                     }
                     if (S.Flag[lc]) S.Flag[lc][sample * 2] = (uint8_t)f;
+                    if (S.Com[lc]) S.Com[lc][sample * 2] = n0;
+                    if (S.Zmp[lc]) S.Zmp[lc][sample * 2] = zmp;
                     S.X[lc * 3 + 0] = n0; S.X[lc * 3 + 1] = n1; S.X[lc * 3 + 2] = n2;
                     S.Iter[lc] += iters[e];
                 }
@@ -485,7 +503,8 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 __stcg(c + gtid * 3 + 1, S.X[gtid * 3 + 1]);
                 __stcg(c + gtid * 3 + 2, S.X[gtid * 3 + 2]);
                 __stcg(c + 3 * kGroupCols + gtid, S.Viol[gtid]);
-                int* ci = reinterpret_cast<int*>(c + 4 * kGroupCols);
+                __stcg(c + 4 * kGroupCols + gtid, S.Lean[gtid]);
+                int* ci = reinterpret_cast<int*>(c + 5 * kGroupCols);
                 __stcg(ci + gtid, S.Iter[gtid]);
                 __stcg(ci + kGroupCols + gtid, S.NotConv[gtid]);
                 __stcg(ci + 2 * kGroupCols + gtid, S.Nticks[gtid]);
@@ -507,6 +526,7 @@ __global__ void __launch_bounds__(32 * RG * NG, 1) k_strict_rollout(const Strict
                 const int slot = c - axis * B.B;
                 const int b = B.order ? B.order[slot] : slot;
                 if (B.max_violation) B.max_violation[b * 2 + axis] = S.Viol[gtid];
+                if (B.lean_max) B.lean_max[b * 2 + axis] = S.Lean[gtid];
                 if (B.status) B.status[b * 2 + axis] = S.NotConv[gtid];
                 if (B.iters) B.iters[b * 2 + axis] = S.Iter[gtid];
             }
@@ -529,11 +549,13 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
     StrictParams Q = P;
     Q.active_groups = NG;
     Q.debug_skip = 0;
-    if (const char* env = std::getenv("LIPM_STRICT_SKIP")) Q.debug_skip = std::atoi(env);
+#ifdef LIPM_DEBUG_KNOBS     // measurement builds only (tools/iter_cost.py): never compiled into the shipped library
+    if (const char* env = std::getenv("LIPM_STRICT_SKIP")) Q.debug_skip = std::atoi(env) & 31;
     if (const char* env = std::getenv("LIPM_STRICT_GROUPS")) {
         const int v = std::atoi(env);
         if (v >= 1 && v < NG) Q.active_groups = v;
     }
+#endif
     Q.num_units = (unsigned)((P.cb.ncols + kGroupCols - 1) / kGroupCols);
     if (Q.num_units == 0) return LIPM_OK;
     const unsigned ctas = (Q.num_units + NG - 1) / NG;
@@ -545,28 +567,36 @@ int launch_variant(lipm_plan* plan, const StrictParams& P, cudaStream_t stream) 
     const unsigned slots = grid * NG;
     unsigned segments = 1;
     if (Q.num_units > slots) segments = (16u * slots + Q.num_units - 1) / Q.num_units;
-    if (const char* env = std::getenv("LIPM_STRICT_SEGMENTS")) segments = (unsigned)std::atoi(env);
+#ifdef LIPM_DEBUG_KNOBS
+    if (const char* env = std::getenv("LIPM_STRICT_SEGMENTS")) {
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= 8) segments = (unsigned)v;
+    }
+#endif
+    if (plan->force_segments > 0) segments = (unsigned)plan->force_segments;   // lipm_set_option (tests)
     if (segments > 8u) segments = 8u;
     if (max_ticks < 32 * (int)segments) segments = max_ticks >= 64 ? (unsigned)(max_ticks / 32) : 1u;
     if (segments < 1u) segments = 1u;
     Q.segments = segments;
     Q.seg_ticks = max_ticks > 0 ? (max_ticks + (int)segments - 1) / (int)segments : 1;
-    Q.seg_stride = (size_t)NRB * 2 * 32 * RG + 6 * kGroupCols;
+    Q.seg_stride = (size_t)NRB * 2 * 32 * RG + 7 * kGroupCols;
     Q.seg_done = nullptr; Q.seg_state = nullptr;
-    void* carry = nullptr;
+    StreamBuffer carry;          // released on every path out of this function
     if (segments > 1) {
         const size_t done_bytes = ((size_t)Q.num_units * sizeof(int) + 255) & ~(size_t)255;
         const size_t bytes = done_bytes + (size_t)Q.num_units * Q.seg_stride * sizeof(double);
-        LIPM_CUDA_TRY(cudaMallocAsync(&carry, bytes, stream));
-        LIPM_CUDA_TRY(cudaMemsetAsync(carry, 0, done_bytes, stream));
-        Q.seg_done = static_cast<int*>(carry);
-        Q.seg_state = reinterpret_cast<double*>(static_cast<unsigned char*>(carry) + done_bytes);
+        LIPM_CUDA_TRY(carry.alloc(bytes, stream));
+        LIPM_CUDA_TRY(cudaMemsetAsync(carry.ptr, 0, done_bytes, stream));
+        Q.seg_done = carry.as<int>();
+        Q.seg_state = reinterpret_cast<double*>(carry.as<unsigned char>() + done_bytes);
     }
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), stream));
+    LaunchState state;           // work counter + statistics of THIS launch: plans are re-entrant across streams
+    LIPM_CUDA_TRY(state.begin(stream));
+    Q.tile_counter = state.counter();
+    Q.stats = state.stats();
     kernel<<<grid, 32 * RG * NG, smem, stream>>>(Q);
     LIPM_CUDA_TRY(cudaGetLastError());
-    if (carry) { LIPM_CUDA_TRY(cudaFreeAsync(carry, stream)); }
+    LIPM_CUDA_TRY(state.publish(plan->d_stats));
     return LIPM_OK;
 }
 
@@ -592,8 +622,8 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
     P.px02 = P.c2 - P.hg;
     P.pu00 = plan->pu00;
     P.mfrag = plan->d_mfrag; P.gpx = plan->d_gpx;
-    P.tile_counter = plan->d_tile_counter;
-    P.stats = plan->d_stats;
+    P.tile_counter = nullptr;
+    P.stats = nullptr;
     P.num_units = 0;
     P.nfrag = (size_t)(plan->NP / 8) * (plan->NP / 4) * 32;
 

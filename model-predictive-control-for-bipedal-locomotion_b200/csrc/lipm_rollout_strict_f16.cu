@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
         const double* plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
         const double* phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
         double* ph = nullptr;
+        double *pcom = nullptr, *pzmp = nullptr;
         uint8_t* pf = nullptr;
-        double imp = 0.0, viol = 0.0;
+        double imp = 0.0, viol = 0.0, lean = 0.0;
         int ftick = -1, notconv = 0, iter_sum = 0;
         if (part == 0) {
             double x0 = 0.0, x1 = 0.0, x2 = 0.0;
@@ -189,6 +190,8 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                 ph = axis ? B.hist[1] : B.hist[0];
                 if (ph) ph += (long long)b * B.hist_scn_stride;
                 pf = B.flags ? B.flags + ((long long)b * B.n_max) * 2 + axis : nullptr;
+                pcom = B.com ? B.com + ((long long)b * B.n_max) * 2 + axis : nullptr;
+                pzmp = B.zmp ? B.zmp + ((long long)b * B.n_max) * 2 + axis : nullptr;
                 if (axis == 1 && B.impulse != nullptr) {
                     imp = B.impulse[b];
                     ftick = B.force_tick ? B.force_tick[b] : -1;
@@ -197,7 +200,10 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                     const double zmp = x0 - P.hg * x2;
                     const double below = plo[0] - zmp, above = zmp - phi[0];
                     viol = fmax(fmax(below, above), 0.0);
+                    lean = fabs(x0 - zmp);
                     if (ph) { ph[0] = x0; ph[1] = x1; ph[2] = x2; }
+                    if (pcom) pcom[0] = x0;
+                    if (pzmp) pzmp[0] = zmp;
                     if (pf) pf[0] = (uint8_t)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                               (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
                 }
@@ -450,6 +456,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                 const double zmp = n0 - P.hg * n2;
                 const double below = l0 - zmp, above = zmp - h0;
                 viol = fmax(viol, fmax(fmax(below, above), 0.0));
+                lean = fmax(lean, fabs(n0 - zmp));
                 unsigned f = (below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) | (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u) |
                              (act_lo ? LIPM_FLAG_ACTIVE_LO : 0u) | (act_hi ? LIPM_FLAG_ACTIVE_HI : 0u);
                 if (!done || failed) { f |= LIPM_FLAG_NOT_CONVERGED; notconv += 1; }
@@ -460,6 +467,8 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
                     dst[0] = n0; dst[1] = n1; dst[2] = n2;
                 }
                 if (pf) pf[sample * 2] = (uint8_t)f;
+                if (pcom) pcom[sample * 2] = n0;
+                if (pzmp) pzmp[sample * 2] = zmp;
                 S.X[s][0] = n0; S.X[s][1] = n1; S.X[s][2] = n2;
                 iter_sum += iters;
             }
@@ -478,6 +487,7 @@ __global__ void __launch_bounds__(kThreadsF16, 1) k_strict_rollout_f16(const F16
         }
         if (part == 0 && valid) {
             if (B.max_violation) B.max_violation[b * 2 + axis] = viol;
+            if (B.lean_max) B.lean_max[b * 2 + axis] = lean;
             if (B.status) B.status[b * 2 + axis] = notconv;
             if (B.iters) B.iters[b * 2 + axis] = iter_sum;
         }
@@ -508,16 +518,17 @@ int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream
     P.pu00 = plan->pu00;
     P.bimg = plan->d_bf16;
     P.gpx = plan->d_gpx;
-    P.tile_counter = plan->d_tile_counter;
-    P.stats = plan->d_stats;
     P.num_units = (unsigned)((cb.ncols + kF16Cols - 1) / kF16Cols);
     if (P.num_units == 0) return LIPM_OK;
     LIPM_CUDA_TRY(cudaFuncSetAttribute(k_strict_rollout_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemF16));
     const unsigned grid = P.num_units < (unsigned)plan->sm_count ? P.num_units : (unsigned)plan->sm_count;
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_tile_counter, 0, sizeof(unsigned int), stream));
-    LIPM_CUDA_TRY(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), stream));
+    LaunchState state;
+    LIPM_CUDA_TRY(state.begin(stream));
+    P.tile_counter = state.counter();
+    P.stats = state.stats();
     k_strict_rollout_f16<<<grid, kThreadsF16, kSmemF16, stream>>>(P);
     LIPM_CUDA_TRY(cudaGetLastError());
+    LIPM_CUDA_TRY(state.publish(plan->d_stats));
     return LIPM_OK;
 }
 

@@ -58,7 +58,7 @@ class ZMPController:
     # ------------------------------------------------------------------ batched entry (new, additive)
     def generate_com_trajectory_batched(self, x_init, y_init, z_max, z_min, *, F_ext=None, m=None,
                                         force_tick=None, n_steps=None, add_force: Optional[bool] = None,
-                                        strict: Optional[bool] = None, to_numpy: bool = True,
+                                        strict: Optional[bool] = None, to_numpy=True,
                                         fall_angle_deg: float = 30.0):
         """Walks of B independent scenarios in one device launch.
 
@@ -67,8 +67,10 @@ class ZMPController:
         velocity after tick ``force_tick`` (default ``n_steps // 2`` as the reference, :90).
         n_steps: (B,) int, bound samples per scenario (default: all n).
         Returns dict(com (B,n,2), x_hist, y_hist (B,n,3), zmp (B,n,2), flags (B,n,2) uint8,
-        max_violation (B,), fell (B,) bool, status (B,), iters (B,2)).  With ``to_numpy`` the arrays are views
-        of page-locked staging buffers that are recycled every second call: copy what must live longer.
+        max_violation (B,), lean_max (B,), fell (B,) bool, status (B,), iters (B,2)), every one of them written by the
+        walk kernel itself (no host or library post-processing).  ``to_numpy=True``: NumPy views of page-locked
+        staging buffers that are recycled every second call (fastest; copy what must live longer);
+        ``to_numpy="copy"``: NumPy arrays the caller owns; ``to_numpy=False``: device tensors.
 
         ``fell`` is a definition of this build (the reference computes no outcome): the walk counts
         as a fall when the CoM gets further from the ZMP than ``h * tan(fall_angle_deg)``, i.e. the
@@ -100,37 +102,31 @@ class ZMPController:
         # samples past their end untouched)
         cache = getattr(self, "_rollout_buffers", None) if to_numpy else None    # device results are the caller's
         if cache is not None:
-            for name in ("x_hist", "y_hist", "flags"):
+            for name in ("x_hist", "y_hist", "flags", "com", "zmp"):
                 if name in cache:
                     cache[name].zero_()
         out = plan.rollout(mode, x_init, y_init, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick,
-                           out=cache)
+                           want_readout=True, fall_lean=cfg.h * float(np.tan(np.radians(fall_angle_deg))), out=cache)
         if to_numpy:
             self._rollout_buffers = out
-        x_hist, y_hist = out["x_hist"], out["y_hist"]
-        # C on the device, uploaded once: a host-to-device copy issued behind the walk kernel is a synchronous,
-        # spinning wait for the whole kernel
-        c = getattr(self, "_c_dev", None)
-        if c is None or c.device != x_hist.device:
-            c = self._c_dev = torch.as_tensor(self.C).to(x_hist.device)
-        com = torch.stack([x_hist[..., 0], y_hist[..., 0]], dim=-1)
-        zmp = torch.stack([x_hist @ c, y_hist @ c], dim=-1)                  # reference run_mpc.py:294
-        lean = (com - zmp).abs().amax(dim=(1, 2))
         res = {
-            "com": com,
-            "x_hist": x_hist, "y_hist": y_hist,
-            "zmp": zmp,
+            "com": out["com"],                                                # reference :108
+            "x_hist": out["x_hist"], "y_hist": out["y_hist"],
+            "zmp": out["zmp"],                                                # reference run_mpc.py:294
             "flags": out["flags"],
-            "max_violation": out["max_violation"].amax(dim=1),
-            "fell": lean > cfg.h * float(np.tan(np.radians(fall_angle_deg))),
-            "status": out["status"].sum(dim=1),
             "iters": out["iters"],
+            "outcome": out["outcome"],
         }
-        if to_numpy:
-            # page-locked staging buffers are recycled: the arrays of a call stay valid until the call after next
-            if getattr(self, "_host_pool", None) is None:
-                self._host_pool = engine.HostPool()
-            res = engine.to_host(res, self._host_pool)
+        if not to_numpy:
+            res.update({k: v for k, v in engine.unpack_outcome(out["outcome"]).items() if k != "iters"})
+            return res
+        # page-locked staging buffers are recycled: the arrays of a call stay valid until the call after next
+        if getattr(self, "_host_pool", None) is None:
+            self._host_pool = engine.HostPool()
+        res = engine.to_host(res, self._host_pool)
+        res.update({k: v for k, v in engine.unpack_outcome_host(res.pop("outcome")).items() if k != "iters"})
+        if to_numpy == "copy":
+            res = {k: np.array(v) for k, v in res.items()}
         return res
 
     # ------------------------------------------------------------------ single walk (reference :59-147)
@@ -263,8 +259,12 @@ class ZMPController:
 
         batch = self.prepare_herdt(state_ref)
         out = batch.rollout(x_init, y_init, v_ref, F_ext=F_ext, mass=m, foot_spread=foot_spread, add_force=add_force)
-        out["com"] = torch.stack([out["x_hist"][..., 0], out["y_hist"][..., 0]], dim=-1)
-        return engine.to_host(out) if to_numpy else out
+        if not to_numpy:
+            out["com"] = torch.stack([out["x_hist"][..., 0], out["y_hist"][..., 0]], dim=-1)
+            return out
+        host = engine.to_host(out)
+        host["com"] = np.stack([host["x_hist"][..., 0], host["y_hist"][..., 0]], axis=-1)    # reference :526-528
+        return host
 
     def prepare_herdt(self, state_ref):
         """Builds (once per timeline) what the Herdt walks of ``state_ref`` share: the support layout, the plan and the
@@ -275,9 +275,15 @@ class ZMPController:
         codes = state_codes(state_ref)
         padded = np.concatenate([np.asarray(state_ref, dtype=object),
                                  np.repeat(np.asarray(state_ref, dtype=object)[-1:], self.config.horizon)])
-        key = (codes.tobytes(), self.config.horizon, self.config.h, self.config.alpha, self.config.beta, self.config.gamma)
+        # every input the plan bakes in (HerdtBatch / HerdtPlan / timeline): a change of any of them rebuilds it
+        c = self.config
+        key = (codes.tobytes(), c.horizon, c.h, c.g, c.dt, c.alpha, c.beta, c.gamma, c.foot_length, c.foot_width,
+               c.foot_spread, np.asarray(c.left_foot_polytope, float).tobytes(), np.asarray(c.right_foot_polytope, float).tobytes(),
+               tuple(sorted(self.herdt_options.items())))
         cache = getattr(self, "_herdt_cache", None)
         if cache is None or cache[0] != key:
+            if cache is not None:
+                cache[1].plan.close()                      # the evicted plan's device memory goes now, not at GC time
             batch = HerdtBatch(self.config, state_ref, self.find_nb_steps(padded), solver_options=self.herdt_options)
             self._herdt_cache = (key, batch)
         return self._herdt_cache[1]

@@ -34,8 +34,8 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBRARY_PATH = os.path.join(_PKG_ROOT, "_lib", "liblipm_mpc.so")
 
 EXPORTED_SYMBOLS = (
-    "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout", "lipm_rollout_indexed",
-    "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
+    "lipm_plan_create", "lipm_plan_destroy", "lipm_plan_export", "lipm_rollout", "lipm_rollout_indexed", "lipm_rollout_ex",
+    "lipm_set_option", "lipm_solve_tick", "lipm_plan_stats", "lipm_last_error", "lipm_version", "lipm_max_strict_horizon",
     "lipm_max_reduced_horizon", "lipm_generate_bounds",
     "herdt_plan_create", "herdt_plan_destroy", "herdt_plan_export_w", "herdt_timeline_create",
     "herdt_timeline_destroy", "herdt_timeline_size", "herdt_tick", "herdt_rollout",
@@ -63,6 +63,25 @@ class _PlanDesc(ctypes.Structure):
     ]
 
 
+class _RolloutIO(ctypes.Structure):
+    """``lipm_rollout_io_t`` of include/lipm_mpc.h."""
+    _fields_ = [
+        ("B", ctypes.c_int32), ("n_max", ctypes.c_int32),
+        ("n_steps", ctypes.c_void_p), ("x0", ctypes.c_void_p), ("y0", ctypes.c_void_p),
+        ("z_min", ctypes.c_void_p), ("z_max", ctypes.c_void_p),
+        ("bounds_batch", ctypes.c_int32), ("bounds_index", ctypes.c_void_p),
+        ("impulse", ctypes.c_void_p), ("force_tick", ctypes.c_void_p),
+        ("x_hist", ctypes.c_void_p), ("y_hist", ctypes.c_void_p), ("com", ctypes.c_void_p), ("zmp", ctypes.c_void_p),
+        ("flags", ctypes.c_void_p), ("max_violation", ctypes.c_void_p), ("lean_max", ctypes.c_void_p),
+        ("status", ctypes.c_void_p), ("iters", ctypes.c_void_p), ("outcome", ctypes.c_void_p),
+        ("fall_lean", ctypes.c_double),
+    ]
+
+
+OPT_KEEP_POOL_MEMORY = 1
+OPT_TICK_RANGES = 2
+OUTCOME_WORDS = 4      # lipm_outcome_t = 4 x 8 bytes: max_violation f64, lean_max f64, (status i32, fell i32), iters i64
+
 _lib = None
 
 
@@ -88,6 +107,10 @@ def load_library() -> ctypes.CDLL:
     lib.lipm_rollout.restype = i32
     lib.lipm_rollout_indexed.argtypes = [vp, i32, i32, i32] + [vp] * 5 + [i32] + [vp] * 10
     lib.lipm_rollout_indexed.restype = i32
+    lib.lipm_rollout_ex.argtypes = [vp, i32, ctypes.POINTER(_RolloutIO), vp]
+    lib.lipm_rollout_ex.restype = i32
+    lib.lipm_set_option.argtypes = [vp, i32, ctypes.c_longlong]
+    lib.lipm_set_option.restype = i32
     lib.lipm_solve_tick.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.lipm_solve_tick.restype = i32
     lib.lipm_plan_stats.argtypes = [vp, vp]
@@ -192,6 +215,7 @@ class LipmPlan:
     # ------------------------------------------------------------------ walks
     def rollout(self, mode: int, x0, y0, z_min, z_max, *, n_steps=None, impulse=None, force_tick=None,
                 bounds_index=None, want_flags: bool = True, want_iters: bool = True, want_hist: bool = True,
+                want_readout: bool = False, want_outcome: bool = True, fall_lean: float = 0.0,
                 out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Batched walks (``lipm_rollout``).  Inputs may be host or device arrays.
 
@@ -200,7 +224,9 @@ class LipmPlan:
         bounds_index: (B,) int32 -> z_min, z_max are a table (V,n,2) of series and scenario b uses
         series bounds_index[b] (``lipm_rollout_indexed``).
         Returns device tensors x_hist, y_hist (B,n,3), flags (B,n,2) uint8,
-        max_violation (B,2), status (B,2) int32, iters (B,2) int32.
+        max_violation (B,2), lean_max (B,2), status (B,2) int32, iters (B,2) int32; with ``want_readout`` also com and
+        zmp (B,n,2), written by the walk kernel itself; with ``want_outcome`` the packed per-scenario record
+        ``outcome`` (B,4) int64 = ``lipm_outcome_t`` (decode with ``unpack_outcome``).
         """
         dev = self.device
         x0 = _dev_tensor(x0, torch.float64, dev)
@@ -238,14 +264,22 @@ class LipmPlan:
         viol = buf("max_violation", (B, 2), torch.float64)
         status = buf("status", (B, 2), torch.int32)
         iters = buf("iters", (B, 2), torch.int32) if want_iters else None
+        lean = buf("lean_max", (B, 2), torch.float64)
+        com = buf("com", (B, n_max, 2), torch.float64) if want_readout else None
+        zmp = buf("zmp", (B, n_max, 2), torch.float64) if want_readout else None
+        outcome = buf("outcome", (B, OUTCOME_WORDS), torch.int64) if want_outcome else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _check(self._lib.lipm_rollout_indexed(
-            self._handle, mode, B, n_max, _ptr(n_steps_t), _ptr(x0), _ptr(y0), _ptr(z_min), _ptr(z_max),
-            bounds_batch, _ptr(index_t), _ptr(impulse_t), _ptr(force_t), _ptr(x_hist), _ptr(y_hist), _ptr(flags),
-            _ptr(viol), _ptr(status), _ptr(iters), stream))
+        io = _RolloutIO(B, n_max, _ptr(n_steps_t), _ptr(x0), _ptr(y0), _ptr(z_min), _ptr(z_max), bounds_batch,
+                        _ptr(index_t), _ptr(impulse_t), _ptr(force_t), _ptr(x_hist), _ptr(y_hist), _ptr(com), _ptr(zmp),
+                        _ptr(flags), _ptr(viol), _ptr(lean), _ptr(status), _ptr(iters), _ptr(outcome), float(fall_lean))
+        _check(self._lib.lipm_rollout_ex(self._handle, mode, ctypes.byref(io), stream))
         # keep inputs alive until the stream has consumed them
         out["_keepalive"] = (x0, y0, z_min, z_max, n_steps_t, impulse_t, force_t, index_t)
         return out
+
+    def set_tick_ranges(self, ranges: int) -> None:
+        """Force the number of tick ranges of the FP64 strict kernel (0 = automatic); results do not depend on it."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_TICK_RANGES, int(ranges)))
 
     # ------------------------------------------------------------------ single ticks
     def solve_tick(self, mode: int, state, z_min, z_max, *, want_plan: bool = False) -> Dict[str, torch.Tensor]:
@@ -280,6 +314,32 @@ class LipmPlan:
         if want_plan:
             res["zmp_plan"], res["jerk_plan"] = zmp_plan, jerk_plan
         return res
+
+
+OUTCOME_DTYPE = np.dtype([("max_violation", "<f8"), ("lean_max", "<f8"), ("status", "<i4"), ("fell", "<i4"), ("iters", "<i8")])
+
+
+def unpack_outcome_host(record: np.ndarray) -> Dict[str, np.ndarray]:
+    """(B,4) int64 ``lipm_outcome_t`` records on the host -> named columns (views, no arithmetic)."""
+    rec = np.ascontiguousarray(record).view(OUTCOME_DTYPE).reshape(-1)
+    return {"max_violation": rec["max_violation"], "lean_max": rec["lean_max"], "status": rec["status"],
+            "fell": rec["fell"] != 0, "iters": rec["iters"]}
+
+
+def unpack_outcome(record: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """(B,4) int64 ``lipm_outcome_t`` records (device or host tensor) -> named columns."""
+    from .parallel import unpack_outcomes
+    out = unpack_outcomes(record)
+    out["status"] = out["status"].to(torch.int32)
+    return out
+
+
+def keep_pool_memory(device: Optional[int] = None) -> None:
+    """Opt in to ``LIPM_OPT_KEEP_POOL_MEMORY`` for a device: the rollouts' stream-ordered scratch buffers stay cached
+    between calls instead of being returned to the driver at every synchronisation (process-wide effect on that
+    device's default memory pool, which is why the library does not do it on its own)."""
+    dev = torch.cuda.current_device() if device is None else int(device)
+    _check(load_library().lipm_set_option(None, OPT_KEEP_POOL_MEMORY, dev))
 
 
 _plan_cache: Dict[PlanKey, LipmPlan] = {}

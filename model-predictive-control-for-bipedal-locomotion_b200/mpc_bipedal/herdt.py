@@ -183,3 +183,67 @@ class HerdtBatch:
             status += out["status"].view(B, 2).amax(dim=1)
             iters += out["iters"].view(B, 2).amax(dim=1)
         return {"x_hist": x_hist, "y_hist": y_hist, "foot_hist": foot_hist, "status": status, "iters": iters}
+
+
+# ====================================================================================== randomized plans (BASELINE config 4)
+def randomized_plans(config, count: int, seed: int = 2) -> Dict[str, object]:
+    """BASELINE configs[3] / SURVEY 8(d) config 4: ``count`` footstep plans with step_length ~ U(0.2, 0.4),
+    foot_spread ~ U(0.08, 0.12), distance ~ U(1.5, 2.5) (and a velocity scale ~ U(0.8, 1.2)), grouped by the state
+    timeline their ``SpeedTrajectoryGenerator`` produces -- scenarios of a group share the per-tick Hessians.
+    Returns dict(step_length, foot_spread, distance, speed (count,), groups = list of dict(ids, states, v))."""
+    from dataclasses import replace
+
+    from .generators.speed_generation import SpeedTrajectoryGenerator
+
+    rng = np.random.default_rng(seed)
+    step_length = rng.uniform(0.2, 0.4, count)
+    spread = rng.uniform(0.08, 0.12, count)
+    distance = rng.uniform(1.5, 2.5, count)
+    speed = rng.uniform(0.8, 1.2, count)
+    groups: Dict[tuple, dict] = {}
+    cache: Dict[tuple, tuple] = {}
+    for b in range(count):
+        cfg_b = replace(config, step_length=float(step_length[b]), foot_spread=float(spread[b]), distance=float(distance[b]))
+        v_x, v_y, states = SpeedTrajectoryGenerator(cfg_b).generate_speed_and_state(save_footsteps=False)
+        key = bytes(state_codes(states))
+        entry = groups.get(key)
+        if entry is None:
+            entry = groups[key] = {"ids": [], "states": np.array(states), "v": np.stack([v_x, v_y], axis=1)}
+        entry["ids"].append(b)
+    for entry in groups.values():
+        entry["ids"] = np.array(entry["ids"])
+    return {"step_length": step_length, "foot_spread": spread, "distance": distance, "speed": speed,
+            "groups": list(groups.values())}
+
+
+def run_plan_groups(config, plans: Dict[str, object], controllers=None, *, solver_options: Optional[dict] = None):
+    """Every timeline group of ``randomized_plans`` as one batch on its own stream (a group's whole walk is ONE enqueue,
+    ``herdt_rollout``, so the groups run concurrently and the small ones fill the SMs the large ones leave idle).
+    Returns (results per group as device-tensor dicts incl. ``com``, the controllers -- reusable: they hold the built
+    timelines -- and the streams to synchronise on)."""
+    import torch
+
+    from .controllers import ZMPController
+
+    groups = plans["groups"]
+    if controllers is None:
+        controllers = []
+        for entry in groups:                 # per-timeline Hessians first: building them synchronises the device
+            ctrl = ZMPController(config)
+            if solver_options:
+                ctrl.herdt_options = dict(solver_options)
+            ctrl.prepare_herdt(entry["states"])
+            controllers.append(ctrl)
+    results, streams = [], []
+    for entry, ctrl in zip(groups, controllers):
+        ids = entry["ids"]
+        v = entry["v"][None] * plans["speed"][ids, None, None]
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            res = ctrl.generate_com_trajectory_herdt_batched(np.zeros((len(ids), 3)), np.zeros((len(ids), 3)), v,
+                                                             entry["states"], foot_spread=plans["foot_spread"][ids],
+                                                             to_numpy=False)
+        results.append(res)
+        streams.append(stream)
+    return results, controllers, streams

@@ -5,26 +5,26 @@ CoM height h, mass m, step length, foot spread and push (F_ext, tick).  What the
 as a Python loop over `MPCConfig`s is organised here for the batched engine:
 
 * `h` changes Pu (`zmp_controller.py:169,171`) and therefore the plan: scenarios are bucketed by `h`;
-* (step_length, foot_spread) only change the bound series (and its length n): one host-generated
-  series per distinct pair (`CoPGenerator`, bit-identical to the reference), shared by its scenarios;
+* (step_length, foot_spread) only change the bound series (and its length n): one series per distinct
+  pair, generated ON THE DEVICE by `lipm_generate_bounds` (bit-identical to the reference's
+  `CoPGenerator`, tested) and shared by its scenarios through `lipm_rollout_ex`'s bounds index;
 * m and F_ext enter only through the impulse dt * F_ext / m (`:106`).
 
-Scenarios are sorted by (h, bounds variant), split into contiguous balanced shards (one per GPU), and
-each shard is run bucket by bucket -- one `lipm_rollout_indexed` per CoM height, the bound series picked
-per scenario from the table of variants.
-The only thing that leaves a rank is the packed per-scenario outcome record.
+Scenarios are sorted by (h, bounds variant).  Inside every h bucket the scenarios are dealt ROUND-ROBIN
+to the ranks, so every GPU runs the same number of launches on the same mix of CoM heights, footstep
+plans and pushes (a contiguous split gives each rank different heights, whose iteration counts differ:
+measured 0.69 weak-scaling efficiency at 8 GPUs in round 1).  The only thing that leaves a rank is the
+packed per-scenario outcome record the library writes (`lipm_outcome_t`).
 """
 
 from __future__ import annotations
 
-from dataclasses import dataclass, replace
+from dataclasses import dataclass
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
 from .config import MPCConfig
-from .generators.cop_generator import CoPGenerator
-from .parallel import shard_range
 
 
 @dataclass
@@ -61,85 +61,92 @@ def make_sweep(batch: int, seed: int = 3, h_values: Sequence[float] = tuple(np.l
                       frac[order], order.astype(np.int64))
 
 
-def variant_bounds(config: MPCConfig, variants: Sequence[Tuple[float, float]]):
-    """Host-side bound series per (step_length, foot_spread): list of (z_max, z_min, first_walking_tick, n)."""
-    out = []
-    for step_length, foot_spread in variants:
-        cfg = replace(config, step_length=step_length, foot_spread=foot_spread)
-        z_max, z_min, states = CoPGenerator(cfg).generate_cop_trajectory(save_footsteps=False)
-        walking = [k for k, s in enumerate(states) if getattr(s, "name", str(s)) != "STANDING"]
-        first = walking[0] if walking else 0
-        last = walking[-1] if walking else len(states) - 1
-        out.append((np.ascontiguousarray(z_max), np.ascontiguousarray(z_min), first, last, len(z_min)))
-    return out
+def series_capacity(config: MPCConfig, variants: Sequence[Tuple[float, float]]) -> int:
+    """Upper bound on the samples of any variant's bound series (`cop_generator.py:73-115`: two standing phases,
+    one double + one single support per footstep of `footstep_generator.py:19-49`, a few samples of clock slack)."""
+    steps = max(int(np.ceil(config.distance / s)) for s, _ in variants) + 4
+    seconds = 2.0 * config.standing_duration + steps * (config.ssp_duration + config.dsp_duration)
+    return int(np.ceil(seconds / config.dt)) + 2 * steps + 16
 
 
-def groups_of_shard(table: SweepTable, rank: int, world: int) -> List[Tuple[int, int, int]]:
-    """(h_index, lo, hi) runs of identical h inside this rank's contiguous shard: one plan and one launch
-    each (the bound series of a run's scenarios are selected per scenario from the table of variants)."""
-    lo, hi = shard_range(len(table), rank, world)
-    runs = []
-    start = lo
-    while start < hi:
-        key = int(table.h_index[start])
-        stop = start + 1
-        while stop < hi and int(table.h_index[stop]) == key:
-            stop += 1
-        runs.append((key, start, stop))
-        start = stop
-    return runs
+def device_bounds(config: MPCConfig, variants: Sequence[Tuple[float, float]]):
+    """Bound series of every variant on the current device + their lengths and walking-phase spans (host)."""
+    from . import engine
+
+    step = np.array([v[0] for v in variants])
+    spread = np.array([v[1] for v in variants])
+    table = engine.generate_bounds(config, np.full(len(variants), config.distance), step, spread,
+                                   n_max=series_capacity(config, variants))
+    n = table["n"].cpu().numpy()
+    if (n <= 0).any():
+        raise RuntimeError(f"bound series capacity too small: {n.tolist()}")
+    states = table["states"].cpu().numpy()
+    first = np.zeros(len(variants), np.int64)
+    last = np.zeros(len(variants), np.int64)
+    for v in range(len(variants)):
+        walking = np.flatnonzero(states[v, : n[v]] != 0)          # 0 = STANDING
+        first[v] = walking[0] if len(walking) else 0
+        last[v] = walking[-1] if len(walking) else n[v] - 1
+    return table["z_max"], table["z_min"], n.astype(np.int32), first, last
 
 
-def push_ticks(table: SweepTable, bounds, lo: int, hi: int) -> np.ndarray:
+def bucket_ranges(table: SweepTable) -> List[Tuple[int, int, int]]:
+    """(h_index, lo, hi) runs of identical CoM height in the sorted table."""
+    edges = np.flatnonzero(np.diff(table.h_index)) + 1
+    starts = np.concatenate([[0], edges]).astype(np.int64)
+    stops = np.concatenate([edges, [len(table)]]).astype(np.int64)
+    return [(int(table.h_index[a]), int(a), int(b)) for a, b in zip(starts, stops) if b > a]
+
+
+def rank_indices(table: SweepTable, rank: int, world: int) -> List[Tuple[int, np.ndarray]]:
+    """Per h bucket, the (sorted-table) indices this rank runs: every `world`-th scenario of the bucket."""
+    return [(h, np.arange(lo + rank, hi, world, dtype=np.int64)) for h, lo, hi in bucket_ranges(table)]
+
+
+def push_ticks(table: SweepTable, idx: np.ndarray, n: np.ndarray, first: np.ndarray, last: np.ndarray) -> np.ndarray:
     """Push tick inside the walking phase of each scenario's own timeline."""
-    first = np.array([bd[2] for bd in bounds])[table.variant[lo:hi]]
-    last = np.array([bd[3] for bd in bounds])[table.variant[lo:hi]]
-    n = np.array([bd[4] for bd in bounds])[table.variant[lo:hi]]
-    span = np.maximum(last - first, 1)
-    tick = first + np.floor(table.tick_fraction[lo:hi] * span).astype(np.int64)
-    return np.clip(tick, 0, n - 2).astype(np.int32)
-
-
-def bounds_table(bounds) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Stack the variants' series into (V, n_max, 2) tables (rows past a series' end are never read:
-    the engine repeats the LAST VALID row of each series, `zmp_controller.py:81-88`) + lengths (V,)."""
-    n_max = max(bd[4] for bd in bounds)
-    z_max = np.zeros((len(bounds), n_max, 2))
-    z_min = np.zeros((len(bounds), n_max, 2))
-    for v, (hi_series, lo_series, _, _, n) in enumerate(bounds):
-        z_max[v, :n], z_min[v, :n] = hi_series, lo_series
-    return z_max, z_min, np.array([bd[4] for bd in bounds], np.int32)
+    v = table.variant[idx]
+    span = np.maximum(last[v] - first[v], 1)
+    tick = first[v] + np.floor(table.tick_fraction[idx] * span).astype(np.int64)
+    return np.clip(tick, 0, n[v] - 2).astype(np.int32)
 
 
 def run_shard(config: MPCConfig, table: SweepTable, rank: int = 0, world: int = 1, *, strict: bool = True,
-              precision: int = 0, fall_angle_deg: float = 30.0) -> Dict[str, np.ndarray]:
-    """Run this rank's shard on the current CUDA device; returns the local outcome record (device tensor,
-    `parallel.RECORD_WIDTH` float64 columns) and the work done."""
+              precision: int = 0, fall_angle_deg: float = 30.0) -> Dict[str, object]:
+    """Run this rank's share on the current CUDA device.  Returns `record` (count, 4) int64 device tensor of
+    `lipm_outcome_t`, `index` (count,) int64 device tensor with the sorted-table index of each record, `solves`
+    (QP solves of the walks that ran to their end; a walk that stopped at an unconverged QP counts for nothing) and
+    `launched` (scenarios run)."""
     import torch
 
     from . import engine
-    from .parallel import pack_outcomes
 
-    bounds = variant_bounds(config, table.variants)
-    z_max_t, z_min_t, lengths = bounds_table(bounds)
-    lo_all, hi_all = shard_range(len(table), rank, world)
     device = torch.device("cuda", torch.cuda.current_device())
-    z_max_d, z_min_d = torch.as_tensor(z_max_t).to(device), torch.as_tensor(z_min_t).to(device)
-    record = torch.zeros((hi_all - lo_all, 4), dtype=torch.float64, device=device)
-    solves = 0
+    z_max_d, z_min_d, lengths, first, last = device_bounds(config, table.variants)
     mode = engine.MODE_STRICT if strict else engine.MODE_UNCONSTRAINED
-    for h_idx, lo, hi in groups_of_shard(table, rank, world):
+    shares = rank_indices(table, rank, world)
+    total = sum(len(idx) for _, idx in shares)
+    record = torch.empty((total, 4), dtype=torch.int64, device=device)
+    index = torch.empty((total,), dtype=torch.int64, device=device)
+    n_all = np.zeros(total, np.int64)
+    pos = 0
+    for h_idx, idx in shares:
+        count = len(idx)
+        if count == 0:
+            continue
         h = float(table.h_values[h_idx])
         plan = engine.get_plan(config.horizon, h, config.g, config.dt, config.Q, config.R, precision=precision)
-        count = hi - lo
         zero = torch.zeros((count, 3), dtype=torch.float64, device=device)
-        impulse = config.dt * table.F_ext[lo:hi] / table.mass[lo:hi]
-        n_steps = lengths[table.variant[lo:hi]]
-        out = plan.rollout(mode, zero, zero, z_min_d, z_max_d, n_steps=n_steps, bounds_index=table.variant[lo:hi],
-                           impulse=impulse, force_tick=push_ticks(table, bounds, lo, hi), want_flags=False)
-        lean = (h / config.g) * out["y_hist"][..., 2].abs().amax(dim=1)     # |CoM - ZMP| = (h/g) |acceleration|
-        lean = torch.maximum(lean, (h / config.g) * out["x_hist"][..., 2].abs().amax(dim=1))
-        fell = lean > h * float(np.tan(np.radians(fall_angle_deg)))
-        record[lo - lo_all:hi - lo_all] = pack_outcomes(out["max_violation"], out["status"], out["iters"], fell)
-        solves += int((2 * (n_steps.astype(np.int64) - 1)).sum())
-    return {"record": record, "solves": solves, "range": (lo_all, hi_all)}
+        variant = table.variant[idx]
+        n_steps = lengths[variant]
+        out = plan.rollout(mode, zero, zero, z_min_d, z_max_d, n_steps=n_steps, bounds_index=variant,
+                           impulse=config.dt * table.F_ext[idx] / table.mass[idx],
+                           force_tick=push_ticks(table, idx, lengths, first, last), want_flags=False, want_hist=False,
+                           fall_lean=h * float(np.tan(np.radians(fall_angle_deg))))
+        record[pos:pos + count] = out["outcome"]
+        index[pos:pos + count] = torch.as_tensor(idx).to(device, non_blocking=True)
+        n_all[pos:pos + count] = n_steps
+        pos += count
+    status = (record[:, 2] & 0xFFFFFFFF).cpu().numpy()
+    solves = int((2 * (n_all - 1))[status == 0].sum())
+    return {"record": record, "index": index, "solves": solves, "launched": total}

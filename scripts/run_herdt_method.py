@@ -58,47 +58,26 @@ def main(argv=None):
         print(f"COM trajectory shape: {com.shape}; final CoM ({com[-1, 0]:.4f}, {com[-1, 1]:.4f}); {seconds:.2f} s")
         return 0
 
-    rng = np.random.default_rng(args.seed)
+    from mpc_bipedal import engine
+    from mpc_bipedal.herdt import randomized_plans, run_plan_groups
+
     B = args.plans
-    step_length = rng.uniform(0.2, 0.4, B)
-    spread = rng.uniform(0.08, 0.12, B)
-    distance = rng.uniform(1.5, 2.5, B)
-    speed = rng.uniform(0.8, 1.2, B)                       # per-plan scale of the reference velocity profile
-    groups = {}
-    for b in range(B):
-        cfg_b = replace(config, step_length=float(step_length[b]), foot_spread=float(spread[b]), distance=float(distance[b]))
-        v_x, v_y, states = SpeedTrajectoryGenerator(cfg_b).generate_speed_and_state(save_footsteps=False,
-                                                                                     output_dir=args.output_dir)
-        key = tuple(s.name if hasattr(s, "name") else int(s) for s in states)
-        entry = groups.setdefault(key, {"ids": [], "states": np.array(states), "v": np.stack([v_x, v_y], axis=1)})
-        entry["ids"].append(b)
+    plans = randomized_plans(config, B, seed=args.seed)
+    groups = plans["groups"]
+    step_length, spread, distance, speed = (plans[k] for k in ("step_length", "foot_spread", "distance", "speed"))
     print(f"{B} plans in {len(groups)} timeline groups")
     final = np.zeros((B, 2))
     status = np.zeros(B, np.int32)
     solves = 0
-    first = next(iter(groups.values()))          # warm-up: CUDA context, kernel images, page-locked staging buffers
-    ZMPController(config).generate_com_trajectory_herdt_batched(np.zeros((2, 3)), np.zeros((2, 3)), first["v"], first["states"])
+    # warm-up: CUDA context, kernel images, page-locked staging buffers
+    ZMPController(config).generate_com_trajectory_herdt_batched(np.zeros((2, 3)), np.zeros((2, 3)), groups[0]["v"], groups[0]["states"])
     import torch
-    from mpc_bipedal import engine
 
     t0 = time.perf_counter()
-    # one stream per timeline group: a group's whole walk is ONE enqueue (herdt_rollout), so the groups -- from
-    # 66 to 1913 plans here -- run concurrently and the small ones fill the SMs the large ones leave idle
-    pending = []
-    controllers = []
-    for entry in groups.values():           # per-timeline Hessians first: building them synchronises the device
-        controllers.append(ZMPController(config))
-        controllers[-1].prepare_herdt(entry["states"])
-    t_built = time.perf_counter() - t0
-    for entry, ctrl in zip(groups.values(), controllers):
-        ids = np.array(entry["ids"])
-        v = entry["v"][None] * speed[ids, None, None]
-        stream = torch.cuda.Stream()
-        with torch.cuda.stream(stream):
-            res = ctrl.generate_com_trajectory_herdt_batched(np.zeros((len(ids), 3)), np.zeros((len(ids), 3)), v, entry["states"],
-                                                             foot_spread=spread[ids], to_numpy=False)
-        pending.append((ids, entry, ctrl, stream, res))
-    for ids, entry, ctrl, stream, res in pending:
+    results, controllers, streams = run_plan_groups(config, plans)
+    t_built = 0.0
+    for entry, res, stream in zip(groups, results, streams):
+        ids = entry["ids"]
         with torch.cuda.stream(stream):
             res = engine.to_host(res)
         print(f"  group of {len(ids):4d} plans, {len(entry['states'])} samples: {time.perf_counter() - t0:.2f} s elapsed, "

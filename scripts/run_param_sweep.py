@@ -37,16 +37,16 @@ def main(argv=None):
     config = base_config(args.config)
     table = sweeps.make_sweep(args.scenarios, seed=args.seed)
     precision = 1 if args.precision == "f16x3" else 0
-    # warm-up: CUDA context, kernel images, plans of this rank's CoM heights, the first collective
+    # warm-up: CUDA context, kernel images, plans of every CoM height (each rank runs all of them), the first collective
     warm = sweeps.make_sweep(min(len(table), 64 * world), seed=args.seed)
-    parallel.gather_outcomes(sweeps.run_shard(config, warm, rank, world, strict=not args.non_strict, precision=precision)["record"],
-                             len(warm), rank, world)
+    w = sweeps.run_shard(config, warm, rank, world, strict=not args.non_strict, precision=precision)
+    parallel.gather_by_index(w["record"], w["index"], len(warm), world)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     local = sweeps.run_shard(config, table, rank, world, strict=not args.non_strict, precision=precision)
-    gathered = parallel.gather_outcomes(local["record"], len(table), rank, world)
+    gathered = parallel.gather_by_index(local["record"], local["index"], len(table), world)
     torch.cuda.synchronize()
     seconds = time.perf_counter() - t0
     solves = torch.tensor([local["solves"]], dtype=torch.float64, device=gathered.device)
@@ -57,14 +57,15 @@ def main(argv=None):
         summary = {"scenarios": len(table), "gpus": world, "seconds": seconds, "qp_solves": int(solves.item()),
                    "qp_solves_per_s": solves.item() / seconds, "precision": args.precision,
                    "fallen": int(out["fell"].sum()), "not_converged": int((out["status"] != 0).sum()),
-                   "max_zmp_violation_m": float(out["max_violation"].max())}
+                   "max_zmp_violation_m": float(out["max_violation"].max()),
+                   "note": "qp_solves counts the walks that ran to their end (a walk that stops at an unconverged QP counts for nothing)"}
         print(json.dumps(summary))
         os.makedirs(args.output_dir, exist_ok=True)
         order = table.scenario_id
         np.savez_compressed(os.path.join(args.output_dir, "param_sweep.npz"), scenario_id=order,
                             h=table.h_values[table.h_index], variant=table.variant, mass=table.mass, F_ext=table.F_ext,
                             fell=out["fell"].numpy(), max_violation=out["max_violation"].numpy(),
-                            iters=out["iters"].numpy())
+                            lean_max=out["lean_max"].numpy(), status=out["status"].numpy(), iters=out["iters"].numpy())
         write_json(os.path.join(args.output_dir, "param_sweep.json"), summary)
     if world > 1:
         dist.destroy_process_group()

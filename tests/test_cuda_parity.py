@@ -199,7 +199,7 @@ def test_batch_results_do_not_depend_on_batch_layout(engine, plan150):
     assert np.array_equal(per["y_hist"].cpu().numpy(), sub["y_hist"])
 
 
-def test_tick_ranges_do_not_change_results(engine, monkeypatch):
+def test_tick_ranges_do_not_change_results(engine):
     """Load balancing hands a unit's walk out as consecutive tick ranges that different solver groups
     continue (iterate, axis state and running outcomes travel through device memory).  Every split gives
     the bits of the unsplit walk, ragged lengths and an aborted column included."""
@@ -215,15 +215,83 @@ def test_tick_ranges_do_not_change_results(engine, monkeypatch):
     plan = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=12, eps=1e-9)
     results = {}
     for segments in (1, 2, 3, 4):
-        monkeypatch.setenv("LIPM_STRICT_SEGMENTS", str(segments))
-        out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick)
+        plan.set_tick_ranges(segments)                  # lipm_set_option(LIPM_OPT_TICK_RANGES)
+        out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick,
+                           want_readout=True)
         results[segments] = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
-    monkeypatch.delenv("LIPM_STRICT_SEGMENTS")
+    plan.set_tick_ranges(0)
     failed = results[1]["status"].any(axis=1)
     assert failed.any() and not failed.all(), failed
     for segments in (2, 3, 4):
-        for key in ("x_hist", "y_hist", "flags", "iters", "max_violation", "status"):
+        for key in ("x_hist", "y_hist", "flags", "iters", "max_violation", "status", "com", "zmp", "lean_max", "outcome"):
             assert np.array_equal(results[segments][key], results[1][key]), (segments, key)
+
+
+def test_readout_and_outcomes_come_from_the_walk_kernels(engine, plan150, plan150_f16):
+    """com, the realised ZMP  C . state  (scripts/run_mpc.py:294), the per-axis maxima and the packed per-scenario
+    record are written by the walk kernels (every mode / precision), ragged walks included: equal to the read-out
+    the reference's drivers compute on the host from the state histories."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(21, seed=9)
+    n = 130
+    z_max, z_min = z_max[:n], z_min[:n]
+    n_steps = np.full(21, n, np.int32)
+    n_steps[[2, 7]] = [50, 2]
+    tick = (tick % 90 + 10).astype(np.int32)
+    impulse[20] *= 6.0                                             # one scenario that falls
+    zero = np.zeros((21, 3))
+    C = np.array([1.0, 0.0, -cfg.h / cfg.g])
+    for plan, mode in ((plan150, engine.MODE_STRICT), (plan150_f16, engine.MODE_STRICT), (plan150, engine.MODE_UNCONSTRAINED)):
+        out = plan.rollout(mode, zero, zero, z_min, z_max, n_steps=n_steps, impulse=impulse, force_tick=tick, want_readout=True,
+                           fall_lean=0.12)
+        out = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+        rec = engine.unpack_outcome_host(out["outcome"])
+        for b in range(21):
+            nb = int(n_steps[b])
+            xh, yh = out["x_hist"][b, :nb], out["y_hist"][b, :nb]
+            assert np.array_equal(out["com"][b, :nb], np.stack([xh[:, 0], yh[:, 0]], 1))
+            zmp = np.stack([np.tensordot(xh, C, axes=([1], [0])), np.tensordot(yh, C, axes=([1], [0]))], 1)
+            # the push changes the y velocity after the sample's ZMP was taken; velocity has weight 0 in C
+            assert np.max(np.abs(out["zmp"][b, :nb] - zmp)) <= 1e-15 * max(1.0, np.abs(zmp).max())
+            assert not out["com"][b, nb:].any() and not out["zmp"][b, nb:].any()
+            lean = np.abs(out["com"][b, :nb] - out["zmp"][b, :nb]).max(axis=0) if nb > 1 else np.zeros(2)
+            assert np.array_equal(out["lean_max"][b], lean), (b, out["lean_max"][b], lean)
+            assert rec["max_violation"][b] == out["max_violation"][b].max()
+            assert rec["lean_max"][b] == lean.max() and bool(rec["fell"][b]) == bool(lean.max() > 0.12)
+            assert rec["status"][b] == out["status"][b].sum() and rec["iters"][b] == out["iters"][b].sum()
+        assert rec["fell"][20] and not rec["fell"][:8].all()
+
+
+def test_one_plan_on_two_streams(engine, plan150):
+    """A plan is re-entrant: two walks enqueued on different streams of the same plan (every launch carries its own
+    work counter) give the bits of the same walks run one after the other."""
+    import torch
+
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(1200, seed=11)
+    n = 120
+    z_max, z_min = z_max[:n], z_min[:n]
+    tick = (tick % 90 + 10).astype(np.int32)
+    dev = plan150.device
+    halves = []
+    for lo, hi in ((0, 600), (600, 1200)):
+        halves.append(dict(x0=torch.zeros((hi - lo, 3), dtype=torch.float64, device=dev),
+                           zmin=torch.as_tensor(z_min).to(dev), zmax=torch.as_tensor(z_max).to(dev),
+                           imp=torch.as_tensor(impulse[lo:hi]).to(dev), tick=torch.as_tensor(tick[lo:hi]).to(dev)))
+    serial = [plan150.rollout(engine.MODE_STRICT, h["x0"], h["x0"], h["zmin"], h["zmax"], impulse=h["imp"], force_tick=h["tick"])
+              for h in halves]
+    torch.cuda.synchronize()
+    serial = [{k: v.clone() for k, v in s.items() if not k.startswith("_")} for s in serial]
+    for attempt in range(3):
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        both = []
+        for h, st in zip(halves, streams):
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                both.append(plan150.rollout(engine.MODE_STRICT, h["x0"], h["x0"], h["zmin"], h["zmax"], impulse=h["imp"],
+                                            force_tick=h["tick"]))
+        torch.cuda.synchronize()
+        for got, want in zip(both, serial):
+            for key in ("x_hist", "y_hist", "flags", "iters", "max_violation", "status", "outcome"):
+                assert torch.equal(got[key], want[key]), (attempt, key)
 
 
 def test_ragged_walks(engine, plan150):
@@ -515,7 +583,8 @@ def test_reduced_ragged_and_limits(engine, plan150_f16):
 # ----------------------------------------------------------------------------- parameter sweep (BASELINE config 5)
 def test_param_sweep_matches_individual_walks(engine, default_config):
     """Each scenario of a (h, m, step_length, foot_spread, F_ext) sweep equals the same walk run alone
-    through the mirrored reference API with that scenario's own MPCConfig."""
+    through the mirrored reference API with that scenario's own MPCConfig, whatever the number of ranks
+    it is dealt to; the corners of BASELINE config 5's box (h 0.6 / 0.9, m 30 / 60) against the oracle."""
     from dataclasses import replace
 
     import torch
@@ -525,25 +594,42 @@ def test_param_sweep_matches_individual_walks(engine, default_config):
     from mpc_bipedal.generators import CoPGenerator
 
     cfg = replace(default_config, distance=0.9, standing_duration=0.4)
-    table = sweeps.make_sweep(96, seed=5, h_values=(0.62, 0.8), step_lengths=(0.25, 0.35), foot_spreads=(0.09,))
-    parts = [sweeps.run_shard(cfg, table, rank, 3) for rank in range(3)]          # three shards on one GPU
-    record = torch.cat([p["record"] for p in parts], dim=0)
+    table = sweeps.make_sweep(96, seed=5, h_values=(0.6, 0.9), step_lengths=(0.25, 0.35), foot_spreads=(0.09,),
+                              mass_range=(30.0, 60.0))
+    table.mass[[0, 40, 95]] = [30.0, 60.0, 30.0]                                  # pin the corners of the mass range
     whole = sweeps.run_shard(cfg, table, 0, 1)
-    assert torch.equal(record, whole["record"])                                   # sharding does not change a bit
-    assert sum(p["solves"] for p in parts) == whole["solves"]
-    out = parallel.unpack_outcomes(whole["record"].cpu())
+    full = parallel.gather_by_index(whole["record"], whole["index"], len(table), 1)
+    parts = [sweeps.run_shard(cfg, table, rank, 3) for rank in range(3)]          # three ranks' shares on one GPU
+    dealt = torch.empty_like(full)
+    for p in parts:
+        dealt[p["index"]] = p["record"]
+    assert torch.equal(dealt, full)                                               # the partition does not change a bit
+    assert sum(p["solves"] for p in parts) == whole["solves"] and sum(p["launched"] for p in parts) == 96
+    out = parallel.unpack_outcomes(full.cpu())
     assert (out["status"] == 0).all() and out["max_violation"].max().item() < 1e-9
-    bounds = sweeps.variant_bounds(cfg, table.variants)
+    _, _, lengths, first, last = sweeps.device_bounds(cfg, table.variants)
+    assert whole["solves"] == int((2 * (lengths[table.variant].astype(np.int64) - 1)).sum())
     for k in (0, 40, 95):
         step_length, foot_spread = table.variants[table.variant[k]]
-        one = replace(cfg, h=float(table.h_values[table.h_index[k]]), m=float(table.mass[k]), F_ext=float(table.F_ext[k]),
+        h = float(table.h_values[table.h_index[k]])
+        one = replace(cfg, h=h, m=float(table.mass[k]), F_ext=float(table.F_ext[k]),
                       step_length=step_length, foot_spread=foot_spread, add_force=True, strict=True)
         z_max, z_min, _ = CoPGenerator(one).generate_cop_trajectory(save_footsteps=False)
-        tick = sweeps.push_ticks(table, bounds, k, k + 1)
+        assert len(z_min) == lengths[table.variant[k]]
+        tick = sweeps.push_ticks(table, np.array([k]), lengths, first, last)
         res = ZMPController(one).generate_com_trajectory_batched(np.zeros((1, 3)), np.zeros((1, 3)), z_max, z_min,
                                                                  F_ext=[one.F_ext], m=[one.m], force_tick=tick)
         assert int(res["iters"].sum()) == int(out["iters"][k])                    # same solves, iteration for iteration
         assert bool(res["fell"][0]) == bool(out["fell"][k])
+        assert float(res["lean_max"][0]) == float(out["lean_max"][k])
+        # ... and the walk itself against the oracle (its own Px / Pu for this CoM height): up to the push plus one second
+        p = orc.Problem.make(one.horizon, one.h, one.g, one.Q, one.R)
+        ticks = min(int(tick[0]) + 100, len(z_min) - 1)
+        want = orc.rollout_wieber(p, np.zeros(3), np.zeros(3), z_max, z_min, strict=True, impulse=one.dt * one.F_ext / one.m,
+                                  force_tick=int(tick[0]), solver="admm", n_ticks=ticks)
+        for key in ("x_hist", "y_hist"):
+            got = res[key][0][: ticks + 1]
+            assert np.max(np.abs(got - want[key])) <= 1e-9 * max(1.0, np.abs(want[key]).max()), (k, key)
 
 
 @pytest.mark.parametrize("N", [24, 100, 128, 152, 153, 200, 300, 318, 477, 600, 637])

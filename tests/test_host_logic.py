@@ -114,33 +114,29 @@ def test_classic_speed_reference(golden):
 # ----------------------------------------------------------------------------- parameter sweeps (config 5)
 def test_sweep_table_groups_and_shards(default_config):
     from mpc_bipedal import sweeps
-    from mpc_bipedal.parallel import shard_range
 
     table = sweeps.make_sweep(1000, seed=3)
     assert len(table) == 1000 and len(table.variants) == 15 and len(table.h_values) == 8
     key = table.h_index.astype(np.int64) * 100 + table.variant
     assert (np.diff(key) >= 0).all()                                  # sorted by (h, variant)
     assert sorted(table.scenario_id.tolist()) == list(range(1000))    # a permutation of the caller's order
-    for world in (1, 2, 8):
+    buckets = sweeps.bucket_ranges(table)
+    assert buckets[0][1] == 0 and buckets[-1][2] == 1000 and len(buckets) == 8
+    for (h_idx, a, b), nxt in zip(buckets, buckets[1:] + [None]):
+        assert a < b and (table.h_index[a:b] == h_idx).all()
+        if nxt is not None:
+            assert nxt[1] == b and nxt[0] != h_idx
+    for world in (1, 2, 3, 8):
         covered = []
+        sizes = []
         for rank in range(world):
-            lo, hi = shard_range(1000, rank, world)
-            runs = sweeps.groups_of_shard(table, rank, world)
-            assert runs[0][1] == lo and runs[-1][2] == hi
-            for (h_idx, a, b), nxt in zip(runs, runs[1:] + [None]):
-                assert a < b and (table.h_index[a:b] == h_idx).all()
-                if nxt is not None:
-                    assert nxt[1] == b and nxt[0] != h_idx
-            covered.extend(range(lo, hi))
-            # "few plans per rank": a contiguous shard of the sorted table touches at most ceil(8/world)+1 heights
-            assert len(runs) <= -(-8 // world) + 1
-        assert covered == list(range(1000))
-    bounds = sweeps.variant_bounds(default_config, table.variants)
-    for z_max, z_min, first, last, n in bounds:
-        assert z_max.shape == (n, 2) and (z_max >= z_min).all() and 0 < first < last < n
-    tick = sweeps.push_ticks(table, bounds, 0, 50)
-    first = np.array([bd[2] for bd in bounds])[table.variant[:50]]
-    last = np.array([bd[3] for bd in bounds])[table.variant[:50]]
-    assert tick.dtype == np.int32 and (tick >= first).all() and (tick <= last).all()
-    z_max_t, z_min_t, lengths = sweeps.bounds_table(bounds)
-    assert z_max_t.shape == (15, lengths.max(), 2) and np.array_equal(z_max_t[3, :lengths[3]], bounds[3][0])
+            shares = sweeps.rank_indices(table, rank, world)
+            assert [h for h, _ in shares] == [h for h, _, _ in buckets]          # every rank runs every CoM height
+            for (h_idx, idx), (_, a, b) in zip(shares, buckets):
+                assert ((idx >= a) & (idx < b)).all() and (np.diff(idx) == world).all()
+                assert abs(len(idx) - (b - a) / world) < 1                       # ... and the same share of each
+                covered.extend(idx.tolist())
+            sizes.append(sum(len(idx) for _, idx in shares))
+        assert sorted(covered) == list(range(1000))                              # a partition of the table
+        assert max(sizes) - min(sizes) <= len(buckets)
+    assert sweeps.series_capacity(default_config, table.variants) >= 600        # longest series (step 0.2): 566 samples

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mpc_bipedal.parallel import gather_outcomes, pack_outcomes, shard_range, unpack_outcomes
+from mpc_bipedal.parallel import gather_by_index, gather_outcomes, pack_outcomes, shard_range, unpack_outcomes
 
 
 def test_shard_ranges_cover_batch_exactly():
@@ -31,10 +31,18 @@ def test_outcome_record_round_trip():
     status = torch.tensor(rng.integers(0, 3, (9, 2)), dtype=torch.int32)
     iters = torch.tensor(rng.integers(0, 50000, (9, 2)), dtype=torch.int32)
     fell = torch.tensor(rng.random(9) < 0.3)
-    rec = pack_outcomes(viol, status, iters, fell)
-    assert rec.shape == (9, 4) and rec.dtype == torch.float64
+    lean = torch.tensor(rng.random((9, 2)))
+    rec = pack_outcomes(viol, status, iters, fell, lean)
+    assert rec.shape == (9, 4) and rec.dtype == torch.int64              # lipm_outcome_t: 32 bytes per scenario
     out = unpack_outcomes(rec)
     assert torch.equal(out["max_violation"], viol.amax(dim=1))
+    assert torch.equal(out["lean_max"], lean.amax(dim=1))
+    # the record is the C struct of include/lipm_mpc.h, bit for bit
+    from mpc_bipedal.engine import OUTCOME_DTYPE, unpack_outcome_host
+    assert OUTCOME_DTYPE.itemsize == 32
+    host = unpack_outcome_host(rec.numpy())
+    assert np.array_equal(host["max_violation"], viol.amax(dim=1).numpy()) and np.array_equal(host["fell"], fell.numpy())
+    assert np.array_equal(host["status"], status.sum(dim=1).numpy()) and np.array_equal(host["iters"], iters.sum(dim=1).numpy())
     assert torch.equal(out["status"], status.sum(dim=1).to(torch.int64))
     assert torch.equal(out["iters"], iters.sum(dim=1).to(torch.int64))
     assert torch.equal(out["fell"], fell)
@@ -56,8 +64,16 @@ def _worker(rank, world, port, B, result_dir):
     status = torch.stack([(idx % 3 == 0).to(torch.int32), torch.zeros_like(idx, dtype=torch.int32)], dim=1)
     iters = torch.stack([idx.to(torch.int32), 2 * idx.to(torch.int32)], dim=1)
     fell = idx % 5 == 0
-    everything = gather_outcomes(pack_outcomes(viol, status, iters, fell), B, rank, world)
+    local = pack_outcomes(viol, status, iters, fell)
+    everything = gather_outcomes(local, B, rank, world)
     torch.save(everything, os.path.join(result_dir, f"rank{rank}.pt"))
+    # the same outcomes, dealt round-robin instead (parameter sweeps): rank r owns scenarios r, r + world, ...
+    mine = torch.arange(rank, B, world)
+    f = mine.to(torch.float64)
+    rr = pack_outcomes(torch.stack([f * 1e-3, f * 2e-3], dim=1),
+                       torch.stack([(f % 3 == 0).to(torch.int32), torch.zeros_like(f, dtype=torch.int32)], dim=1),
+                       torch.stack([f.to(torch.int32), 2 * f.to(torch.int32)], dim=1), f % 5 == 0)
+    torch.save(gather_by_index(rr, mine, B, world), os.path.join(result_dir, f"rr{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -73,3 +89,5 @@ def test_all_gather_of_outcomes_world2(tmp_path, B):
     assert torch.equal(out["iters"], (3 * idx).to(torch.int64))
     assert torch.equal(out["fell"], idx % 5 == 0)
     assert torch.equal(out["status"], (idx % 3 == 0).to(torch.int64))
+    rr = [torch.load(os.path.join(tmp_path, f"rr{r}.pt")) for r in range(world)]
+    assert torch.equal(rr[0], got[0]) and torch.equal(rr[1], got[0])     # round-robin partition: same table
