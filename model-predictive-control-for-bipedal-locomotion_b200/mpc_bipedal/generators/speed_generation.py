@@ -46,3 +46,45 @@ class SpeedTrajectoryGenerator:
             return x_hist[:, 1, 0], y_hist[:, 1, 0], states
 
         raise ValueError(f"Unknown speed_generation mode: {self.config.speed_generation}")
+
+    def generate_speed_and_state_batched(self, distance, step_length, foot_spread, to_numpy: bool = True):
+        """``generate_speed_and_state`` for V walk variants at once (additive API): per-variant ``distance``,
+        ``step_length``, ``foot_spread`` (arrays of length V, or scalars), everything else from ``config``.
+
+        The bound series and state timelines are generated on the device (``lipm_generate_bounds``, bit-identical to
+        ``CoPGenerator``); in "wieber" mode the V push-free walks of ``generate_state_trajectory_wieber`` (reference
+        `speed_generation.py:53-67`) run as ONE batched rollout that reads each variant's series through the bounds
+        index.  Returns dict(v (V, n_max, 2), states (V, n_max) int8 codes, n (V,) samples per variant); rows past a
+        variant's ``n`` are zero."""
+        import torch
+
+        from .. import engine
+        from ..sweeps import series_capacity
+
+        cfg = self.config
+        d = np.atleast_1d(np.asarray(distance, dtype=np.float64))
+        V = len(d)
+        s = np.broadcast_to(np.asarray(step_length, dtype=np.float64), (V,))
+        f = np.broadcast_to(np.asarray(foot_spread, dtype=np.float64), (V,))
+        from dataclasses import replace
+        cap = series_capacity(replace(cfg, distance=float(d.max())), [(float(s.min()), 0.1)])
+        table = engine.generate_bounds(cfg, d, s, f, n_max=cap)
+        n = table["n"]
+        if int(n.min().item()) <= 0:
+            raise RuntimeError("bound series capacity too small")
+        mode = (cfg.speed_generation or "wieber").lower()
+        states = table["states"]
+        if mode == "classic":
+            valid = torch.arange(cap, device=n.device)[None, :] < n[:, None]
+            v = torch.zeros((V, cap, 2), dtype=torch.float64, device=n.device)
+            v[..., 0] = torch.where((states != 0) & valid, CLASSIC_FORWARD_SPEED, 0.0)
+        elif mode == "wieber":
+            plan = self._zmp_controller._plan()
+            zero = torch.zeros((V, 3), dtype=torch.float64, device=n.device)
+            out = plan.rollout(1 if cfg.strict else 0, zero, zero, table["z_min"], table["z_max"], n_steps=n,
+                               bounds_index=torch.arange(V, dtype=torch.int32, device=n.device), want_flags=False)
+            v = torch.stack([out["x_hist"][..., 1], out["y_hist"][..., 1]], dim=-1)
+        else:
+            raise ValueError(f"Unknown speed_generation mode: {cfg.speed_generation}")
+        res = {"v": v, "states": states, "n": n}
+        return engine.to_host(res) if to_numpy else res

@@ -186,30 +186,53 @@ class HerdtBatch:
 
 
 # ====================================================================================== randomized plans (BASELINE config 4)
-def randomized_plans(config, count: int, seed: int = 2) -> Dict[str, object]:
+def randomized_plans(config, count: int, seed: int = 2, on_device: bool = False) -> Dict[str, object]:
     """BASELINE configs[3] / SURVEY 8(d) config 4: ``count`` footstep plans with step_length ~ U(0.2, 0.4),
     foot_spread ~ U(0.08, 0.12), distance ~ U(1.5, 2.5) (and a velocity scale ~ U(0.8, 1.2)), grouped by the state
-    timeline their ``SpeedTrajectoryGenerator`` produces -- scenarios of a group share the per-tick Hessians.
+    timeline of their gait (``CoPGenerator``'s state machine, `cop_generator.py:73-115`) -- scenarios of a group share
+    the per-tick Hessians.  The reference velocity is ``speed_generation = "classic"`` (`speed_generation.py:48-51`:
+    0.3 m/s forward while not STANDING).  ``on_device``: the timelines come from ``lipm_generate_bounds`` (bit-identical
+    to the host generator, tested) instead of ``count`` runs of the Python state machine.
     Returns dict(step_length, foot_spread, distance, speed (count,), groups = list of dict(ids, states, v))."""
     from dataclasses import replace
 
-    from .generators.speed_generation import SpeedTrajectoryGenerator
+    from .generators.speed_generation import CLASSIC_FORWARD_SPEED, SpeedTrajectoryGenerator
 
     rng = np.random.default_rng(seed)
     step_length = rng.uniform(0.2, 0.4, count)
     spread = rng.uniform(0.08, 0.12, count)
     distance = rng.uniform(1.5, 2.5, count)
     speed = rng.uniform(0.8, 1.2, count)
-    groups: Dict[tuple, dict] = {}
-    cache: Dict[tuple, tuple] = {}
-    for b in range(count):
-        cfg_b = replace(config, step_length=float(step_length[b]), foot_spread=float(spread[b]), distance=float(distance[b]))
-        v_x, v_y, states = SpeedTrajectoryGenerator(cfg_b).generate_speed_and_state(save_footsteps=False)
-        key = bytes(state_codes(states))
-        entry = groups.get(key)
-        if entry is None:
-            entry = groups[key] = {"ids": [], "states": np.array(states), "v": np.stack([v_x, v_y], axis=1)}
-        entry["ids"].append(b)
+    groups: Dict[bytes, dict] = {}
+    if on_device:
+        from . import engine
+        from .sweeps import series_capacity
+
+        cap = series_capacity(replace(config, distance=2.5), [(0.2, 0.1)])
+        table = engine.generate_bounds(config, distance, step_length, spread, n_max=cap)
+        n = table["n"].cpu().numpy()
+        if (n <= 0).any():
+            raise RuntimeError("timeline capacity too small")
+        codes = table["states"].cpu().numpy()
+        for b in range(count):
+            row = codes[b, : n[b]]
+            key = row.tobytes()
+            entry = groups.get(key)
+            if entry is None:
+                v_x = np.where(row == STANDING, 0.0, CLASSIC_FORWARD_SPEED)
+                states = np.array([State.STANDING, State.DOUBLE_SUPPORT, State.SINGLE_SUPPORT], dtype=object)[row]
+                entry = groups[key] = {"ids": [], "states": states, "v": np.stack([v_x, np.zeros_like(v_x)], axis=1)}
+            entry["ids"].append(b)
+    else:
+        for b in range(count):
+            cfg_b = replace(config, step_length=float(step_length[b]), foot_spread=float(spread[b]), distance=float(distance[b]),
+                            speed_generation="classic")
+            v_x, v_y, states = SpeedTrajectoryGenerator(cfg_b).generate_speed_and_state(save_footsteps=False)
+            key = bytes(state_codes(states))
+            entry = groups.get(key)
+            if entry is None:
+                entry = groups[key] = {"ids": [], "states": np.array(states), "v": np.stack([v_x, v_y], axis=1)}
+            entry["ids"].append(b)
     for entry in groups.values():
         entry["ids"] = np.array(entry["ids"])
     return {"step_length": step_length, "foot_spread": spread, "distance": distance, "speed": speed,

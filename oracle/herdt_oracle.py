@@ -249,7 +249,7 @@ def predict_joint(cfg, A_model, B_model, x, y, v_ref, x_fc, y_fc, current_state,
 
 
 def rollout_herdt(cfg, A_model, B_model, x_init, y_init, v_ref, state_ref, nb_steps, polytopes,
-                  n_ticks: Optional[int] = None):
+                  n_ticks: Optional[int] = None, stop_when_uncertified: bool = False):
     """Whole walk -- zmp_controller.py:435-531.  ``state_ref``: int codes (n,); ``nb_steps``: the reference's
     ``find_nb_steps`` output for the PADDED timeline; ``polytopes``: {"left": (A, b), "right": (A, b)}."""
     N = cfg.horizon
@@ -272,6 +272,8 @@ def rollout_herdt(cfg, A_model, B_model, x_init, y_init, v_ref, state_ref, nb_st
             cfg, A_model, B_model, x, y, v_ext[i + 1: i + 1 + N], x_fc, y_fc, current, s_ext[i + 1: i + 1 + N],
             foot_side, polytopes[foot_side], mats)
         certs.append(info["kkt"])
+        if stop_when_uncertified and not info["kkt"]["ok"]:
+            break                                    # the caller only keeps the certified prefix
         x, y = x_next, y_next
         if fx1 is not None:
             x_air += (1 / nb_steps[i][0]) * (fx1 - x_air)

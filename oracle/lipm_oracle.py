@@ -133,6 +133,39 @@ def strict_axis_exact(p: Problem, x: np.ndarray, zmax: np.ndarray, zmin: np.ndar
     return p.A @ x + p.B * jerk0, z, sol.active_mask.astype(np.int8)
 
 
+def kkt_certificate_jerk(p: Problem, x: np.ndarray, zmax: np.ndarray, zmin: np.ndarray, z: np.ndarray,
+                         bound_tol: float = 1e-12) -> dict:
+    """Optimality certificate of a previewed-ZMP plan ``z`` in the reference's OWN coordinates and matrices.
+
+    The reference's strict QP (zmp_controller.py:174-189) is over the jerks J:
+        min 1/2 Q |Px x + Pu J - zref|^2 + 1/2 J'(R I)J     s.t.  [Pu; -Pu] J <= [zmax - Px x; -zmin + Px x].
+    Both oracle solvers and every GPU kernel work in z = Px x + Pu J instead; a common-mode error in that change of
+    variables would pass their mutual agreement.  Here J = Pu^-1 (z - Px x) is mapped back and the KKT conditions are
+    evaluated literally: stationarity  Q Pu'(Pu J + Px x - zref) + R J + Pu'(lam_hi - lam_lo) = 0  fixes
+    mu = lam_hi - lam_lo = -Pu^-T grad; optimality <=> mu vanishes on rows strictly inside the box, mu >= 0 only on
+    rows at zmax, mu <= 0 only on rows at zmin, and z is inside the box.  Returns the residuals, relative to the larger of
+    max|mu| and the magnitude of the gradient's own terms Q |z|_inf, Q |zref|_inf (the usual relative KKT residual)."""
+    x = np.asarray(x, float).reshape(3)
+    Pxx = p.Px @ x
+    J = np.linalg.solve(p.Pu, z - Pxx)
+    zref = (zmax + zmin) / 2
+    z_back = Pxx + p.Pu @ J
+    grad = p.Q * (p.Pu.T @ (z_back - zref)) + p.R * J                      # H = R I, :174
+    mu = -np.linalg.solve(p.Pu.T, grad)
+    at_hi = z >= zmax - bound_tol
+    at_lo = z <= zmin + bound_tol
+    free = ~(at_hi | at_lo)
+    scale = max(float(np.abs(mu).max()), p.Q * float(np.abs(z_back).max()), p.Q * float(np.abs(zref).max()), 1e-300)
+    wrong = 0.0
+    if at_hi.any():
+        wrong = max(wrong, float(np.max(-mu[at_hi & ~at_lo], initial=0.0)))
+    if at_lo.any():
+        wrong = max(wrong, float(np.max(mu[at_lo & ~at_hi], initial=0.0)))
+    return dict(primal=float(max(0.0, np.max(z - zmax), np.max(zmin - z))),
+                free_multiplier=float(np.abs(mu[free]).max(initial=0.0)) / scale,
+                wrong_sign=wrong / scale, active_rows=int((at_hi | at_lo).sum()), scale=scale, jerk0=float(J[0]))
+
+
 def admm_matrix(p: Problem, rho: float) -> np.ndarray:
     """(Hz + rho I)^-1 -- the shared iteration matrix."""
     return np.linalg.inv(p._cache()["Hz"] + rho * np.eye(p.N))

@@ -14,6 +14,9 @@ ref_nonstrict_walk.npz reference ``generate_com_trajectory_wieber`` (strict=Fals
                        ``generate_state_trajectory_wieber`` on configs/default.json
 ref_nonstrict_ticks.npz reference ``predict_wieber_axis`` (strict=False) on seeded random inputs
 ref_herdt_helpers.npz  reference ``find_nb_steps`` and ``_polytope_halfspace`` outputs
+ref_speed_wieber.npz   reference ``SpeedTrajectoryGenerator`` in "wieber" mode (strict=False) on two configs
+oracle_herdt_walk.npz  ORACLE Herdt walk of the class-default config (--herdt)
+oracle_herdt_plans.npz ORACLE Herdt walks of three randomized plans with different timelines (--herdt-plans)
 oracle_strict_walk.npz ORACLE (not reference) strict default walk: exact BVLS solver
 oracle_strict_ticks.npz ORACLE strict single ticks on seeded random inputs (N = 16, 50, 150)
 
@@ -185,7 +188,25 @@ def gen_oracle_strict_ticks(out):
     np.savez_compressed(out, **data)
 
 
+def gen_speed_wieber(out):
+    """REFERENCE ``SpeedTrajectoryGenerator`` in "wieber" mode (speed_generation.py:53-67): a whole push-free Wieber walk
+    through the reference's own ``generate_state_trajectory_wieber`` (non-strict: runs without cvxpy), velocities read
+    off the state histories.  Two configs: default.json and a short walk with another step length."""
+    MPCConfig, _, _, _, _ = import_reference()
+    from src.mpc_bipedal.generators.speed_generation import SpeedTrajectoryGenerator
+    data = {}
+    for tag, over in (("default_json", {"strict": False, "speed_generation": "wieber"}),
+                      ("short", {"strict": False, "speed_generation": "wieber", "distance": 0.9, "step_length": 0.25,
+                                 "standing_duration": 0.4, "horizon": 100})):
+        cfg = make_config(MPCConfig, "json", over)
+        vx, vy, states = SpeedTrajectoryGenerator(cfg).generate_speed_and_state(save_footsteps=False)
+        data[f"{tag}/vx"], data[f"{tag}/vy"] = np.asarray(vx), np.asarray(vy)
+        data[f"{tag}/states"] = np.array([STATE_CODE[s.value] for s in states], np.int8)
+    np.savez_compressed(out, **data)
+
+
 TARGETS = {
+    "ref_speed_wieber": gen_speed_wieber,
     "ref_generators": gen_generators,
     "ref_nonstrict_walk": gen_nonstrict_walk,
     "ref_nonstrict_ticks": gen_nonstrict_ticks,
@@ -239,8 +260,61 @@ def make_oracle_herdt_walk():
     print("oracle_herdt_walk.npz written; certified ticks:", last)
 
 
+def make_oracle_herdt_plans():
+    """ORACLE Herdt walks of three RANDOMIZED footstep plans with three different timelines (BASELINE configs[3]:
+    step_length ~ U(0.2, 0.4), foot_spread ~ U(0.08, 0.12), distance ~ U(1.5, 2.5), velocity scale ~ U(0.8, 1.2), seed 2
+    -- the draw of mpc_bipedal.herdt.randomized_plans).  Timeline, reference velocities and nb_steps come from the
+    REFERENCE's own SpeedTrajectoryGenerator / find_nb_steps (imported here); each walk is kept up to its last
+    KKT-certified tick.  ~20 minutes of CPU."""
+    MPCConfig_ref, ZMPController_ref, _, State, _ = import_reference()
+    from src.mpc_bipedal.generators.speed_generation import SpeedTrajectoryGenerator as RefSpeed
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "model-predictive-control-for-bipedal-locomotion_b200"))
+    from dataclasses import replace
+
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.herdt import randomized_plans
+    from mpc_bipedal.models.lipm_model import discrete_model
+    from oracle import herdt_oracle as ho
+
+    g = np.load(os.path.join(HERE, "ref_herdt_helpers.npz"))
+    polys = {s: (g[f"polytope/{s}/A"], g[f"polytope/{s}/b"]) for s in ("left", "right")}
+    base = MPCConfig()
+    plans = randomized_plans(base, 8192, seed=2)
+    groups = sorted(plans["groups"], key=lambda e: len(e["ids"]))
+    picks = [int(groups[0]["ids"][0]), int(groups[len(groups) // 2]["ids"][3]), int(groups[-1]["ids"][7])]
+    code_to_state = {0: State.STANDING, 1: State.DOUBLE_SUPPORT, 2: State.SINGLE_SUPPORT}
+    data = {"plan_ids": np.array(picks)}
+    for k, b in enumerate(picks):
+        over = dict(step_length=float(plans["step_length"][b]), foot_spread=float(plans["foot_spread"][b]),
+                    distance=float(plans["distance"][b]))
+        ref_cfg = MPCConfig_ref(**over)
+        ref_cfg.speed_generation = "classic"
+        vx, vy, states = RefSpeed(ref_cfg).generate_speed_and_state(save_footsteps=False)
+        codes = np.array([STATE_CODE[s.value] for s in states], np.int8)
+        padded = np.concatenate([codes, np.repeat(codes[-1:], ref_cfg.horizon)])
+        nb = np.array(ZMPController_ref(ref_cfg).find_nb_steps(np.array([code_to_state[int(c)] for c in padded], dtype=object)), np.int32)
+        cfg = replace(base, **over)
+        cfg.add_force = True
+        cfg.F_ext = 60.0 + 40.0 * k
+        A, B, _ = discrete_model(cfg.dt, cfg.h, cfg.g)
+        v_ref = np.stack([np.asarray(vx), np.asarray(vy)], 1) * float(plans["speed"][b])
+        res = ho.rollout_herdt(cfg, A, B, np.zeros(3), np.zeros(3), v_ref, codes, nb, polys, stop_when_uncertified=True)
+        ok = np.array([c["ok"] for c in res["kkt"]])
+        last = int(np.where(~ok)[0][0]) if (~ok).any() else len(ok)
+        print(f"plan {b}: n = {len(codes)}, certified ticks = {last}", flush=True)
+        data[f"p{k}/states"], data[f"p{k}/v_ref"], data[f"p{k}/nb_steps"] = codes, v_ref, nb
+        data[f"p{k}/params"] = np.array([over["step_length"], over["foot_spread"], over["distance"], float(plans["speed"][b]), cfg.F_ext])
+        data[f"p{k}/x_hist"], data[f"p{k}/y_hist"] = res["x_hist"][: last + 1], res["y_hist"][: last + 1]
+        data[f"p{k}/foot_hist"], data[f"p{k}/certified_ticks"] = res["foot_hist"][: last + 1], last
+    np.savez_compressed(os.path.join(HERE, "oracle_herdt_plans.npz"), **data)
+    print("oracle_herdt_plans.npz written")
+
+
 if __name__ == "__main__":
-    if "--herdt" in sys.argv:
+    if "--herdt-plans" in sys.argv:
+        make_oracle_herdt_plans()
+    elif "--herdt" in sys.argv:
         make_oracle_herdt_walk()
     else:
         main()

@@ -99,6 +99,33 @@ def test_nonstrict_default_walk_matches_reference(engine, plan150, golden):
 
 
 # ----------------------------------------------------------------------------- strict mode
+def test_strict_gpu_plans_are_kkt_points_of_the_reference_qp(engine, golden):
+    """The ZMP plans the FP64 kernel returns, mapped back to jerks and checked in the reference's literal QP
+    (zmp_controller.py:174-189: H = R I, A_ineq = [Pu; -Pu]): primal feasible, multipliers vanish on free rows and have
+    the right sign on active ones.  Independent of both oracle solvers and of the z-coordinates the kernel works in."""
+    g = golden("oracle_strict_ticks")
+    rng = np.random.default_rng(17)
+    for N in (16, 50, 150):
+        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+        p = orc.Problem.make(N)
+        x, lo, hi = g[f"N{N}/x"], g[f"N{N}/z_min"], g[f"N{N}/z_max"]
+        # golden ticks plus fresh random ones the oracle never saw (narrow boxes: many active rows)
+        xr = rng.normal(size=(16, 3)) * [0.05, 0.1, 0.5]
+        centre = rng.uniform(-0.05, 0.05, size=(16, 1)) + 0.03 * np.sign(rng.normal(size=(16, N))).cumsum(axis=1) / np.sqrt(N)
+        x, lo, hi = np.vstack([x, xr]), np.vstack([lo, centre - 0.02]), np.vstack([hi, centre + 0.02])
+        res = plan.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+        assert (res["status"].cpu().numpy() == 0).all()
+        z, nxt = res["zmp_plan"].cpu().numpy(), res["next_state"].cpu().numpy()
+        active = 0
+        for k in range(len(x)):
+            cert = orc.kkt_certificate_jerk(p, x[k], hi[k], lo[k], z[k], bound_tol=0.0)
+            assert cert["primal"] == 0.0, (N, k, cert)                       # the kernel clips: feasible to the last bit
+            assert cert["free_multiplier"] <= REL and cert["wrong_sign"] <= REL, (N, k, cert)     # north_star: 1e-9 relative
+            assert np.max(np.abs(p.A @ x[k] + p.B * cert["jerk0"] - nxt[k])) <= 1e-9 * max(1.0, np.abs(nxt[k]).max())
+            active += cert["active_rows"]
+        assert active > 10 * N // 16
+
+
 @pytest.mark.parametrize("N", [16, 50, 150])
 def test_strict_ticks_match_exact_oracle(engine, golden, N):
     g = golden("oracle_strict_ticks")
@@ -632,6 +659,38 @@ def test_param_sweep_matches_individual_walks(engine, default_config):
             assert np.max(np.abs(got - want[key])) <= 1e-9 * max(1.0, np.abs(want[key]).max()), (k, key)
 
 
+@pytest.mark.parametrize("N", [152, 318, 477, 637])
+def test_reduced_long_horizons_against_the_oracle(engine, N):
+    """The largest horizon of each reduced-precision kernel shape (N = 152: resident operands; 318 / 477 / 637: 2 / 3 / 4
+    streamed slabs) against the ORACLE's FP64 ADMM (own Px / Pu / Hessian for that horizon), not just against the
+    library's FP64 path: ZMP plan and next state within 1e-4 m, and the FP64 path within 1e-9 of the same oracle."""
+    rng = np.random.default_rng(300 + N)
+    p = orc.Problem.make(N)
+    cases = 3
+    x = rng.normal(size=(cases, 3)) * np.array([0.05, 0.1, 0.5])
+    centre = rng.uniform(-0.05, 0.05, size=(cases, 1)) + np.cumsum(
+        (rng.random((cases, N)) < 0.04) * rng.uniform(-0.1, 0.1, size=(cases, N)), axis=1)
+    lo, hi = centre - 0.055, centre + 0.055
+    rho = float(np.sqrt(p.Q * (p.Q + np.linalg.eigvalsh(p._cache()["Hz"] - p.Q * np.eye(N)).max())))   # fast for cond(H) ~ 100
+    f16 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
+    fp64 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    got16 = f16.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    got64 = fp64.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
+    assert (got16["status"].cpu().numpy() == 0).all() and (got64["status"].cpu().numpy() == 0).all()
+    active = 0
+    for k in range(cases):
+        nxt, z, w, it = orc.strict_axis_admm(p, x[k], hi[k], lo[k], rho=rho, max_iter=20000)
+        assert it < 20000
+        active += int(((z == lo[k]) | (z == hi[k])).sum())
+        assert np.max(np.abs(got64["zmp_plan"][k].cpu().numpy() - z)) < 1e-9
+        assert np.max(np.abs(got64["next_state"][k].cpu().numpy() - nxt)) < 1e-9 * max(1.0, np.abs(nxt).max()) * 10
+        assert np.max(np.abs(got16["zmp_plan"][k].cpu().numpy() - z)) < TOL_REDUCED_M
+        # position and velocity of the next state; its acceleration carries the first jerk (z0 - Px[0] x) / Pu[0,0] with
+        # |dt / Pu[0,0]| = g / h = 13 per metre of ZMP error
+        assert (np.abs(got16["next_state"][k].cpu().numpy() - nxt) < TOL_REDUCED_M * np.array([1.0, 1.0, 20.0])).all()
+    assert active > 0
+
+
 @pytest.mark.parametrize("N", [24, 100, 128, 152, 153, 200, 300, 318, 477, 600, 637])
 def test_reduced_other_horizons_against_fp64_path(engine, N):
     """Every horizon the reduced-precision kernels serve (N <= 152: operands resident in shared memory, one 160-row
@@ -792,3 +851,41 @@ def test_edge_cases(engine, plan150, plan150_f16):
         plan150.solve_tick(engine.MODE_STRICT, zero, np.zeros((4, 149)), np.zeros((4, 149)))
     with pytest.raises(engine.LipmError, match="mode"):
         plan150.rollout(7, zero, zero, z_min[:30], z_max[:30])
+
+
+# ----------------------------------------------------------------------------- SpeedTrajectoryGenerator "wieber" mode
+def test_speed_generator_wieber_mode_matches_reference(engine, golden, default_config):
+    """`SpeedTrajectoryGenerator` in "wieber" mode is a second caller of the hot path (speed_generation.py:53-67): a whole
+    push-free walk on the engine, velocities read off the histories.  Against the REFERENCE's own output (strict=False
+    runs there without cvxpy; tests/golden/ref_speed_wieber.npz), single and batched."""
+    from dataclasses import replace
+
+    from mpc_bipedal.generators.speed_generation import SpeedTrajectoryGenerator
+    from mpc_bipedal.herdt import state_codes
+
+    g = golden("ref_speed_wieber")
+    cases = {"default_json": replace(default_config, strict=False, speed_generation="wieber"),
+             "short": replace(default_config, strict=False, speed_generation="wieber", distance=0.9, step_length=0.25,
+                              standing_duration=0.4, horizon=100, dt=1.5 / 100)}
+    for tag, cfg in cases.items():
+        vx, vy, states = SpeedTrajectoryGenerator(cfg).generate_speed_and_state(save_footsteps=False)
+        assert np.array_equal(state_codes(states), g[f"{tag}/states"])
+        assert rel_err(vx, g[f"{tag}/vx"]) < REL and rel_err(vy, g[f"{tag}/vy"]) < REL, tag
+    # batched over walk variants: variant 0 is the default walk, the others are each equal to their own single run
+    cfg = cases["default_json"]
+    gen = SpeedTrajectoryGenerator(cfg)
+    dist, step, spread = np.array([cfg.distance, 0.9, 1.4]), np.array([cfg.step_length, 0.25, 0.35]), np.array([cfg.foot_spread, 0.09, 0.12])
+    out = gen.generate_speed_and_state_batched(dist, step, spread)
+    n0 = int(out["n"][0])
+    assert n0 == len(g["default_json/vx"])
+    assert rel_err(out["v"][0, :n0, 0], g["default_json/vx"]) < REL and rel_err(out["v"][0, :n0, 1], g["default_json/vy"]) < REL
+    for v in (1, 2):
+        one = replace(cfg, distance=float(dist[v]), step_length=float(step[v]), foot_spread=float(spread[v]))
+        vx, vy, states = SpeedTrajectoryGenerator(one).generate_speed_and_state(save_footsteps=False)
+        nv = int(out["n"][v])
+        assert nv == len(vx) and np.array_equal(out["states"][v, :nv], state_codes(states))
+        assert np.array_equal(out["v"][v, :nv, 0], vx) and np.array_equal(out["v"][v, :nv, 1], vy)      # same kernel, same bits
+        assert not out["v"][v, nv:].any()
+    classic = SpeedTrajectoryGenerator(replace(cfg, speed_generation="classic")).generate_speed_and_state_batched(dist, step, spread)
+    vx, _, _ = SpeedTrajectoryGenerator(replace(cfg, speed_generation="classic")).generate_speed_and_state(save_footsteps=False)
+    assert np.array_equal(classic["v"][0, :n0, 0], vx) and not classic["v"][..., 1].any()

@@ -181,3 +181,103 @@ def test_c_oracle_ragged_and_batched():
         assert np.max(np.abs(res["y_hist"][b, :nb] - want["y_hist"])) < 1e-9
         assert np.max(np.abs(res["x_hist"][b, :nb] - want["x_hist"])) < 1e-9
         assert not res["y_hist"][b, nb:].any()
+
+
+# ----------------------------------------------------------------------------- the oracle IS the optimum of the reference's QP
+KKT_TOL = 1e-12     # multipliers relative to max |multiplier|; primal feasibility absolute in metres
+
+
+@pytest.mark.parametrize("N", [16, 50, 150])
+def test_strict_golden_ticks_are_kkt_points_of_the_reference_qp(golden, N):
+    """Every strict golden tick, mapped back to the jerk coordinates and the literal matrices of the reference's QP
+    (`zmp_controller.py:174-189`: H = R I, A_ineq = [Pu; -Pu]), satisfies its KKT conditions: the golden vectors are
+    the unique optimum of the problem the reference poses, not just the point two z-coordinate solvers agree on."""
+    g = golden("oracle_strict_ticks")
+    p = orc.Problem.make(N)
+    active = 0
+    for x, lo, hi, z, nxt in zip(g[f"N{N}/x"], g[f"N{N}/z_min"], g[f"N{N}/z_max"], g[f"N{N}/z"], g[f"N{N}/next"]):
+        cert = orc.kkt_certificate_jerk(p, x, hi, lo, z)
+        assert cert["primal"] <= 1e-12 and cert["free_multiplier"] <= KKT_TOL and cert["wrong_sign"] <= KKT_TOL, cert
+        # the applied jerk is the first component of J = Pu^-1 (z - Px x): A x + B J0 is the golden next state
+        assert np.allclose(p.A @ x + p.B * cert["jerk0"], nxt, rtol=1e-9, atol=1e-12)
+        active += cert["active_rows"]
+    assert active > 0                                      # the set exercises active constraints
+
+
+def test_strict_golden_walk_ticks_are_kkt_points(golden):
+    """Sampled ticks of the golden strict walk (before, at and after the push, where up to 43 rows are active):
+    re-solving from the recorded state gives a certified KKT point whose first jerk reproduces the next recorded state."""
+    g = golden("oracle_strict_walk")
+    p = orc.Problem.make(150)
+    N, n = 150, len(g["z_min"])
+    hi = np.vstack([g["z_max"], np.tile(g["z_max"][-1:], (N, 1))])
+    lo = np.vstack([g["z_min"], np.tile(g["z_min"][-1:], (N, 1))])
+    force_tick, impulse = int(g["force_tick"]), float(g["impulse"])
+    most_active = 0
+    for i in (0, 99, 150, 209, 210, 211, 215, 230, 260, 300, 417):
+        for ax, hist in ((0, g["x_hist"]), (1, g["y_hist"])):
+            hw, lw = hi[i + 1:i + 1 + N, ax], lo[i + 1:i + 1 + N, ax]
+            nxt, z, _ = orc.strict_axis_exact(p, hist[i], hw, lw)
+            cert = orc.kkt_certificate_jerk(p, hist[i], hw, lw, z)
+            assert cert["primal"] <= 1e-12 and cert["free_multiplier"] <= KKT_TOL and cert["wrong_sign"] <= KKT_TOL, (i, ax, cert)
+            most_active = max(most_active, cert["active_rows"])
+            want = hist[i + 1].copy()
+            if ax == 1 and i == force_tick:
+                want[1] += impulse                          # the recorded sample already carries the push
+            assert np.max(np.abs(nxt - want)) <= 1e-9 * max(1.0, np.abs(want).max()), (i, ax)
+    assert most_active >= 30
+
+
+# ----------------------------------------------------------------------------- what the reference's solver would return
+def test_osqp_restatement_known_answers():
+    """The only solver output recorded anywhere in the reference: `src/mpc_bipedal/test.ipynb` cell 3 projects the point
+    (0.6, -0.25) on the hull of the left footstep polytope with cvxpy -> OSQP and prints `Status: optimal / Optimal u:
+    [ 0.6 -0.25]`.  Plus the solver's two other verdicts on toy problems."""
+    from scipy.spatial import ConvexHull
+
+    from oracle import osqp_restatement as osq
+
+    pts = np.array([(-0.1, -0.3), (-0.1, -0.4), (0.0, -0.4), (0.0, -0.2), (0.1, -0.17), (0.2, -0.13), (0.3, -0.1), (0.7, -0.05),
+                    (0.8, -0.05), (0.8, -0.3), (0.4, -0.35)])
+    eq = ConvexHull(pts).equations
+    A_h, b_h = eq[:, :2], -eq[:, 2]
+    target = np.array([0.6, -0.25])
+    # cvxpy: sum_squares(u - target) -> auxiliary t = u - target, minimise t't: variables [u; t]
+    P = np.zeros((4, 4)); P[2:, 2:] = 2 * np.eye(2)
+    A = np.zeros((2 + len(b_h), 4)); A[:2, :2], A[:2, 2:], A[2:, :2] = np.eye(2), -np.eye(2), A_h
+    res = osq.solve(P, np.zeros(4), A, np.concatenate([target, np.full(len(b_h), -osq.INF)]), np.concatenate([target, b_h]))
+    assert res["status"] == "solved"
+    assert np.array_equal(np.round(res["x"][:2], 4), target)          # what the notebook printed
+    # a target outside the hull lands on its boundary (projection), to the solver's tolerance
+    out = np.array([0.9, 0.1])
+    res = osq.solve(P, np.zeros(4), A, np.concatenate([out, np.full(len(b_h), -osq.INF)]), np.concatenate([out, b_h]))
+    assert res["status"] == "solved" and abs(np.max(A_h @ res["x"][:2] - b_h)) < 1e-4
+    # contradictory rows -> primal infeasible (cvxpy: u.value is None -> the reference's fallback / RuntimeError)
+    res = osq.solve(np.eye(1), np.zeros(1), np.array([[1.0], [1.0]]), np.array([1.0, -osq.INF]), np.array([osq.INF, 0.0]))
+    assert res["status"] == "primal_infeasible"
+    # unbounded below along a free direction -> dual infeasible
+    res = osq.solve(np.zeros((1, 1)), np.array([1.0]), np.array([[1.0]]), np.array([-osq.INF]), np.array([0.0]))
+    assert res["status"] == "dual_infeasible"
+
+
+def test_reference_solver_output_sits_within_its_tolerance_of_the_oracle(golden):
+    """OSQP as cvxpy calls it (non-condensed form, eps_abs = eps_rel = 1e-5, restated) on golden strict ticks: it
+    reports "solved", and what the reference would have returned differs from the exact optimum by about the solver's
+    tolerance -- which is why parity is stated against the optimum, not against the reference's own ~1e-5 output."""
+    from oracle import osqp_restatement as osq
+
+    g = golden("oracle_strict_ticks")
+    N = 150
+    p = orc.Problem.make(N)
+    worst_z = worst_state = 0.0
+    for k in (0, 3, 7, 12):
+        x, lo, hi, z = g[f"N{N}/x"][k], g[f"N{N}/z_min"][k], g[f"N{N}/z_max"][k], g[f"N{N}/z"][k]
+        for interval in (25, 100):
+            nxt, info = osq.wieber_strict_axis(p, x, hi, lo, osq.Settings(adaptive_rho_interval=interval))
+            assert info["status"] == "solved" and info["iters"] <= 500
+            plan = p.Px @ x + p.Pu @ info["x"][:N]
+            worst_z = max(worst_z, float(np.abs(plan - z).max()))
+            worst_state = max(worst_state, float(np.abs(nxt - g[f"N{N}/next"][k]).max()))
+            assert max((plan - hi).max(), (lo - plan).max()) < 1e-4           # feasible to the solver's tolerance only
+    assert worst_z < 1e-3 and worst_state < 1e-3
+    assert worst_z > 1e-9                        # ... and NOT to 1e-9: the reference's own output is not the optimum
