@@ -77,7 +77,7 @@ class SpeedTrajectoryGenerator:
         if mode == "classic":
             valid = torch.arange(cap, device=n.device)[None, :] < n[:, None]
             v = torch.zeros((V, cap, 2), dtype=torch.float64, device=n.device)
-            v[..., 0] = torch.where((states != 0) & valid, CLASSIC_FORWARD_SPEED, 0.0)
+            v[..., 0] = ((states != 0) & valid).to(torch.float64) * CLASSIC_FORWARD_SPEED      # float64: 0.3 exactly as the host value
         elif mode == "wieber":
             plan = self._zmp_controller._plan()
             zero = torch.zeros((V, 3), dtype=torch.float64, device=n.device)

@@ -80,7 +80,7 @@ def test_run_herdt_method(tmp_path):
     one = json.load(open(os.path.join(out, "herdt.json")))
     data = np.load(os.path.join(out, "herdt.npz"))
     assert one["n_steps"] == 302 and data["com"].shape == (302, 2) and data["foot_hist"].shape == (302, 2)
-    assert 1.5 < one["final_com"][0] < 2.3
+    assert 0.3 < one["final_com"][0] < 1.0                               # 0.3 m/s reference speed over ~2 s of walking
     run_script("run_herdt_method.py", "--plans", "96", "--output-dir", out)  # randomized plans, grouped by timeline
     plans = json.load(open(os.path.join(out, "herdt_plans.json")))
     assert plans["plans"] == 96 and plans["groups"] >= 3 and plans["joint_qp_solves"] > 96 * 250
