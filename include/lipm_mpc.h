@@ -250,6 +250,12 @@ typedef struct herdt_plan_desc {
     double rho, relax, eps;         /* ADMM penalty (<=0 -> 6), over-relaxation (<=0 -> 1.8), stop (<=0 -> 1e-12) */
     int32_t max_iter;               /* <=0 -> 600 (a healthy tick needs 60..150 from a cold start)         */
     int32_t device;
+    int32_t stall_window;           /* a pair whose residual lost < 10 % over this many iterations stops (<=0 -> 32;
+                                       >= max_iter: never)                                                 */
+    double accept_eps;              /* a pair that stops WITHOUT reaching eps is still applied (status 2) when its residuals pass
+                                       this looser relative tolerance: 0 -> 1e-5 = the tolerance at which the reference's solver
+                                       (OSQP through cvxpy) declares "solved" and the reference applies the point
+                                       (zmp_controller.py:792-805); < 0 -> never (every such pair falls back, :796-804) */
 } herdt_plan_desc_t;
 
 /* Per (N, h, g, dt, alpha, beta): T = Pzu^-1, V = Pvu Pzu^-1, W = alpha T'T + beta V'V, on the device. */
@@ -286,7 +292,7 @@ int herdt_timeline_size(const herdt_timeline_t* timeline);   /* padded variable 
  *               the current phase (footstep variables move down by one)
  * outputs: next_x, next_y dev [B,3]; f1 dev [B,2] first free footstep (NaN when the window holds none);
  *          solution dev [2B, size] or NULL ((e, F) per axis, x and y columns of a scenario adjacent);
- *          status, iters dev int32 [2B] or NULL.
+ *          status, iters dev int32 [2B] or NULL; status: 0 converged to eps, 2 applied at accept_eps, 1 failed (fallback).
  */
 int herdt_tick(herdt_timeline_t* timeline, int tick, int B, const double* x, const double* y, const double* fc,
                const double* air, const double* spread, const double* vref, int vref_batch, int n_ext, int foot_side,
@@ -306,8 +312,9 @@ int herdt_tick(herdt_timeline_t* timeline, int tick, int B, const double* x, con
  *   poly_left / poly_right   HOST [n_left|n_right, 2] reachable polygons of the next footstep per supporting side
  *   warm_start  0: every tick starts cold (as the reference);  1: from the previous tick's iterate
  *   impulse     dev [B] = dt * F_ext / m applied to the y velocity after tick `force_tick`, or NULL
- * outputs: x_hist, y_hist dev [B,n,3]; foot_hist dev [B,n,2]; status dev int32 [B] = ticks whose joint QP did not
- *          converge (they fall back like the reference, :796-804); iters dev int64 [B]; both may be NULL.
+ * outputs: x_hist, y_hist dev [B,n,3]; foot_hist dev [B,n,2]; status dev int32 [B]: low 16 bits = ticks whose joint QP
+ *          failed (they fall back like the reference, :796-804), high 16 bits = ticks applied at accept_eps;
+ *          iters dev int64 [B]; both may be NULL.
  * Walks of DIFFERENT timelines may be enqueued on different streams and run concurrently. */
 int herdt_rollout(herdt_timeline_t* timeline, int B, int n, const double* x0, const double* y0, const double* fc0,
                   const double* spread, const double* vref, int vref_batch, int n_ext, const int8_t* foot_side,

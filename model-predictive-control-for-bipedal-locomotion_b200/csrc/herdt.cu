@@ -327,6 +327,8 @@ struct QpParams {
     int f1_row;                   // row of the first footstep (N) or -1
     int max_iter;
     double rho, alpha, eps, stop_factor;
+    double accept_eps;            // a pair that stalls / hits max_iter within this (looser) tolerance is still applied; < 0: never
+    int stall_window;             // iterations between two stall checks
     const double* mfrag;
     const double *q, *lo, *hi, *t0;   // [ncols, NP]
     double* sol;                  // [ncols, NP] projected solution
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
             if (g == 0) S.Res[1][rg][lc0 + e] = qmag[e];
         }
         group_sync<kGroupThreads>(bar_id);
-        uint32_t thr[2];
+        uint32_t thr[2], thr_accept[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             uint32_t mm = S.Res[1][0][lc0 + e];
@@ -478,11 +480,15 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
             for (int q4 = 1; q4 < kRowGroups; ++q4) mm = max(mm, S.Res[1][q4][lc0 + e]);
             const double scale = fmax(1.0, __hiloint2double((int)mm, 0));
             thr[e] = mag_hi(P.eps * scale * P.stop_factor);
+            thr_accept[e] = P.accept_eps > 0 ? mag_hi(P.accept_eps * scale * P.stop_factor) : 0u;
         }
 
         bool done[2] = {!live[0], !live[1]};
         bool stalled = false;              // the pair stopped without converging (see below)
-        uint32_t checkpoint = 0xffffffffu; // residual (high word) 32 iterations ago
+        bool accepted = false;             // ... but within the reference solver's own tolerance: applied, status 2
+        uint32_t last[2] = {0xffffffffu, 0xffffffffu};   // residuals of the last iteration (high words)
+        int window = 0;
+        uint32_t checkpoint = 0xffffffffu; // residual (high word) one stall window ago
         int iters[2] = {0, 0};
         for (int k = 0; k < P.max_iter; ++k) {
             double acc[NRB][2];
@@ -541,12 +547,14 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
                     for (int q4 = 1; q4 < kRowGroups; ++q4) cd[e] = max(cd[e], S.Res[0][q4][lc0 + e]);
                 }
                 bool both = (cd[0] <= thr[0]) && (cd[1] <= thr[1]);
-                // A QP whose residual has lost less than 10 % over 32 iterations is not going to converge (the
-                // hull-in-front-of-the-CoM ticks of the final stance are infeasible in effect: ADMM's residual
-                // settles on a constant): stop the pair and report it as failed, like an iteration cap would --
-                // a few dozen iterations later instead of max_iter later.  A healthy solve contracts by 0.8-0.9 per
-                // iteration, i.e. by 30x or more over such a window.
-                if (!both && (k & 31) == 31) {
+                last[0] = cd[0]; last[1] = cd[1];
+                // A QP whose residual has lost less than 10 % over a stall window (32 iterations) has stopped making
+                // progress at this penalty (the final-stance ticks, where the state has left the region the
+                // formulation can steer back: every row is active and the residual creeps): stop the pair a few dozen
+                // iterations later instead of max_iter later.  A healthy solve contracts by 0.8-0.9 per iteration,
+                // i.e. by 30x or more over such a window.
+                if (!both && ++window >= P.stall_window) {
+                    window = 0;
                     const uint32_t cur = max(cd[0], cd[1]);
                     if (checkpoint != 0xffffffffu &&
                         __hiloint2double((int)cur, 0) > 0.9 * __hiloint2double((int)checkpoint, 0)) { stalled = true; both = true; }
@@ -575,8 +583,13 @@ __global__ void __launch_bounds__(32 * kRowGroups * NG, 1) k_qp_tick(const QpPar
                 if (P.t_out) P.t_out[(size_t)c * NP + row0 + r * 8] = tv[r][e];
             }
             if (rg == 0 && g == 0) {
+                // 0: converged to eps.  Not converged (stalled or out of iterations): 2 when the last residuals of BOTH
+                // axes pass the reference solver's own stopping tolerance (OSQP at cvxpy's eps 1e-5 returns such a
+                // point as "solved" and the reference applies it, zmp_controller.py:792-805), else 1 (fallback).
+                const bool tight = done[e] && !stalled;
+                accepted = !tight && last[0] <= thr_accept[0] && last[1] <= thr_accept[1];
                 if (P.iters) P.iters[c] = iters[e];
-                if (P.status) P.status[c] = (done[e] && !stalled) ? 0 : 1;
+                if (P.status) P.status[c] = tight ? 0 : (accepted ? 2 : 1);
             }
         }
     }
@@ -592,7 +605,7 @@ __global__ void k_herdt_apply(int B, int NP, int N, int m, double T, double hg, 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 2 * B) return;
     const int b = idx >> 1, axis = idx & 1;
-    const bool failed = status && (status[2 * b] != 0 || status[2 * b + 1] != 0);
+    const bool failed = status && (status[2 * b] == 1 || status[2 * b + 1] == 1);     // 2 = applied at the reference tolerance
     const double* s = (axis ? y : x) + (size_t)b * 3;
     const double x0 = s[0], x1 = s[1], x2 = s[2];
     const double c3 = T * T * T / 6.0, c2 = T * T / 2.0;
@@ -634,7 +647,11 @@ __global__ void k_herdt_book(int B, int n, int sample, int has_step, double inv_
 #pragma unroll
     for (int k = 0; k < 3; ++k) { x_hist[at * 3 + k] = next_x[3 * b + k]; y_hist[at * 3 + k] = next_y[3 * b + k]; }
     foot_hist[at * 2] = fcb[0]; foot_hist[at * 2 + 1] = fcb[1];
-    if (status) status[b] += max(tick_status[2 * b], tick_status[2 * b + 1]);
+    if (status) {
+        // low 16 bits: ticks that fell back; high 16 bits: ticks applied at the reference solver's tolerance
+        const int worst = (tick_status[2 * b] == 1 || tick_status[2 * b + 1] == 1) ? 1 : max(tick_status[2 * b], tick_status[2 * b + 1]);
+        status[b] += worst == 1 ? 1 : (worst == 2 ? (1 << 16) : 0);
+    }
     if (iters) iters[b] += max(tick_iters[2 * b], tick_iters[2 * b + 1]);
 }
 
@@ -715,6 +732,8 @@ int herdt_plan_create(herdt_plan_t** out, const herdt_plan_desc_t* desc) {
     if (!(d.relax > 0)) d.relax = 1.8;
     if (!(d.eps > 0)) d.eps = 1e-12;
     if (d.max_iter <= 0) d.max_iter = 600;
+    if (d.stall_window <= 0) d.stall_window = 32;
+    if (d.accept_eps == 0) d.accept_eps = 1e-5;       // cvxpy's eps_abs = eps_rel for OSQP
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { set_error("no CUDA device available (this library has no CPU path)"); return LIPM_E_CUDA; }
     if (d.device < 0 || d.device >= count) { set_error("device %d out of range", d.device); return LIPM_E_INVALID; }
@@ -865,6 +884,7 @@ int herdt_tick(herdt_timeline_t* t, int tick, int B, const double* x, const doub
     Q.ncols = ncols; Q.NP = NP; Q.n = t->n; Q.f1_row = m > 0 ? N : -1;
     Q.max_iter = d.max_iter; Q.rho = d.rho; Q.alpha = d.relax; Q.eps = d.eps;
     Q.stop_factor = 1.0 / std::fmax(1.0 + d.relax, d.rho * d.relax);
+    Q.accept_eps = d.accept_eps; Q.stall_window = d.stall_window;
     Q.mfrag = t->d_frag + (size_t)tick * t->nfrag;
     Q.q = t->d_q; Q.lo = t->d_lo; Q.hi = t->d_hi; Q.t0 = t->d_t0; Q.sol = solution ? solution : t->d_sol;
     Q.status = status; Q.iters = iters;

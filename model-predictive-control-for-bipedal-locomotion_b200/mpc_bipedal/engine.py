@@ -438,6 +438,7 @@ class _HerdtDesc(ctypes.Structure):
         ("foot_length", ctypes.c_double), ("foot_width", ctypes.c_double), ("foot_spread", ctypes.c_double),
         ("rho", ctypes.c_double), ("relax", ctypes.c_double), ("eps", ctypes.c_double),
         ("max_iter", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("stall_window", ctypes.c_int32), ("accept_eps", ctypes.c_double),
     ]
 
 
@@ -474,7 +475,7 @@ class HerdtPlan:
     """Device-resident matrices of the Herdt QP for one ``(N, h, g, dt, alpha, beta, gamma, foot)``."""
 
     def __init__(self, horizon, h, g, dt, alpha, beta, gamma, foot_length, foot_width, foot_spread, *,
-                 rho=0.0, relax=0.0, eps=0.0, max_iter=0, device: Optional[int] = None):
+                 rho=0.0, relax=0.0, eps=0.0, max_iter=0, stall_window=0, accept_eps=0.0, device: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("liblipm_mpc needs a CUDA device (B200 / sm_100a); there is no CPU path")
         self._lib = _herdt_lib()
@@ -484,7 +485,7 @@ class HerdtPlan:
             torch.zeros(1, device=self.device)
         self.horizon = int(horizon)
         desc = _HerdtDesc(self.horizon, h, g, dt, alpha, beta, gamma, foot_length, foot_width, foot_spread,
-                          rho, relax, eps, max_iter, self.device_index)
+                          rho, relax, eps, max_iter, self.device_index, stall_window, accept_eps)
         handle = ctypes.c_void_p()
         _check(self._lib.herdt_plan_create(ctypes.byref(handle), ctypes.byref(desc)))
         self._handle = handle

@@ -121,8 +121,9 @@ class HerdtBatch:
     def rollout(self, x_init, y_init, v_ref, *, F_ext=None, mass=None, foot_spread=None,
                 add_force: Optional[bool] = None, n_ticks: Optional[int] = None) -> Dict[str, "torch.Tensor"]:
         """x_init, y_init (B,3); v_ref (n,2) shared or (B,n,2).  Returns device tensors x_hist, y_hist (B,n,3),
-        foot_hist (B,n,2), status (B,) = ticks whose QP did not converge (they fall back to zero jerk and the
-        interpolated footstep like the reference, :796-804), iters (B,)."""
+        foot_hist (B,n,2), status (B,) = ticks whose QP failed (they fall back to zero jerk and the interpolated
+        footstep like the reference, :796-804), accepted (B,) = ticks whose QP stopped short of eps but within the
+        reference solver's own tolerance (applied, like the reference applies what OSQP calls "solved"), iters (B,)."""
         import torch
 
         cfg, lay = self.config, self.layout
@@ -155,7 +156,9 @@ class HerdtBatch:
             out = self.timeline.rollout(x, y, fc, vref, n=n, foot_side=lay.foot_side, steps_left=steps_left, commit=lay.commit,
                                         new_run=lay.new_run, polygons=self.polygons, spread=spread, warm_start=self.warm_start,
                                         impulse=impulse, force_tick=n // 2 if push else -1)
-            return {k: out[k] for k in ("x_hist", "y_hist", "foot_hist", "status", "iters", "_keepalive")}
+            res = {k: out[k] for k in ("x_hist", "y_hist", "foot_hist", "iters", "_keepalive")}
+            res["status"], res["accepted"] = out["status"] & 0xFFFF, out["status"] >> 16
+            return res
         # a prefix of the walk, tick by tick from the host (the same kernels; used by tests and probes)
         ticks = n_ticks
         x_hist = torch.zeros((B, n, 3), dtype=torch.float64, device=dev)
@@ -180,9 +183,12 @@ class HerdtBatch:
                 y = y.clone()
                 y[:, 1] -= impulse
             x_hist[:, i + 1], y_hist[:, i + 1], foot_hist[:, i + 1] = x, y, fc
-            status += out["status"].view(B, 2).amax(dim=1)
+            st = out["status"].view(B, 2)
+            failed = (st == 1).any(dim=1)
+            status += torch.where(failed, 1, torch.where((st == 2).any(dim=1), 1 << 16, 0)).to(torch.int32)
             iters += out["iters"].view(B, 2).amax(dim=1)
-        return {"x_hist": x_hist, "y_hist": y_hist, "foot_hist": foot_hist, "status": status, "iters": iters}
+        return {"x_hist": x_hist, "y_hist": y_hist, "foot_hist": foot_hist, "status": status & 0xFFFF, "accepted": status >> 16,
+                "iters": iters}
 
 
 # ====================================================================================== randomized plans (BASELINE config 4)
