@@ -188,9 +188,13 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
  *       whole process on that device, so the library never does it on its own.
  *   LIPM_OPT_TICK_RANGES (plan required; value = 0 automatic, 1..8 forced): how many consecutive tick ranges the
  *       FP64 strict kernel cuts a walk into for load balance.  Results do not depend on it (tested).
+ *   LIPM_OPT_SINGLE_CTA_F16 (plan required; value 0 / 1): run the reduced-precision walks (N <= 152) on the single-CTA
+ *       tcgen05 kernel instead of the CTA-pair one (cta_group::2).  Same arithmetic, same bits (tested); kept for
+ *       comparison and as the reference point of the pair kernel's speed-up.
  */
 #define LIPM_OPT_KEEP_POOL_MEMORY 1
 #define LIPM_OPT_TICK_RANGES 2
+#define LIPM_OPT_SINGLE_CTA_F16 3
 int lipm_set_option(lipm_plan_t* plan, int option, long long value);
 
 /*

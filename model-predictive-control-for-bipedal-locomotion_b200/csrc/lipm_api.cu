@@ -203,6 +203,10 @@ int lipm_set_option(lipm_plan_t* plan, int option, long long value) {
             if (!plan || value < 0 || value > 8) { set_error("lipm_set_option(TICK_RANGES): need a plan and a value in [0, 8]"); return LIPM_E_INVALID; }
             plan->force_segments = (int)value;
             return LIPM_OK;
+        case LIPM_OPT_SINGLE_CTA_F16:
+            if (!plan || (value != 0 && value != 1)) { set_error("lipm_set_option(SINGLE_CTA_F16): need a plan and 0 / 1"); return LIPM_E_INVALID; }
+            plan->single_cta_f16 = (int)value;
+            return LIPM_OK;
         default:
             set_error("lipm_set_option: unknown option %d", option);
             return LIPM_E_INVALID;

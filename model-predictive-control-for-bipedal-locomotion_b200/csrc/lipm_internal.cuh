@@ -120,6 +120,7 @@ struct lipm_plan {
     unsigned char* d_f16s; // FP16 hi / lo images of [M | M G Px] cut into 160-row slabs (F16X3 plans, N > 152)
     int f16s_nk;           // padded contraction length of d_f16s: multiple of 16, >= N + 3
     int f16s_slabs;        // 160-row slabs
+    int single_cta_f16;   // 1: reduced-precision walks on the single-CTA kernel instead of CTA pairs (lipm_set_option)
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch (copied from the launch's own state)
@@ -176,10 +177,12 @@ int launch_pack_outcomes(int B, const double* max_violation, const double* lean_
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+int launch_strict_rollout_f16p(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // CTA pairs (cta_group::2)
 // strict rollout on the kernel that matches the plan's precision and horizon
 inline int launch_strict(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
     if (plan->desc.precision != LIPM_PRECISION_F16X3) return launch_strict_rollout(plan, cb, stream);
-    return plan->N <= kMaxReducedHorizon ? launch_strict_rollout_f16(plan, cb, stream) : launch_strict_rollout_f16s(plan, cb, stream);
+    if (plan->N > kMaxReducedHorizon) return launch_strict_rollout_f16s(plan, cb, stream);
+    return plan->single_cta_f16 ? launch_strict_rollout_f16(plan, cb, stream) : launch_strict_rollout_f16p(plan, cb, stream);
 }
 int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_jerk_from_zmp(lipm_plan* plan, int ncols, const double* state, const double* zmp_plan,

@@ -80,6 +80,7 @@ class _RolloutIO(ctypes.Structure):
 
 OPT_KEEP_POOL_MEMORY = 1
 OPT_TICK_RANGES = 2
+OPT_SINGLE_CTA_F16 = 3
 OUTCOME_WORDS = 4      # lipm_outcome_t = 4 x 8 bytes: max_violation f64, lean_max f64, (status i32, fell i32), iters i64
 
 _lib = None
@@ -280,6 +281,10 @@ class LipmPlan:
     def set_tick_ranges(self, ranges: int) -> None:
         """Force the number of tick ranges of the FP64 strict kernel (0 = automatic); results do not depend on it."""
         _check(self._lib.lipm_set_option(self._handle, OPT_TICK_RANGES, int(ranges)))
+
+    def set_single_cta_f16(self, on: bool) -> None:
+        """Reduced-precision walks (N <= 152) on the single-CTA tcgen05 kernel instead of the CTA-pair one."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_SINGLE_CTA_F16, 1 if on else 0))
 
     # ------------------------------------------------------------------ single ticks
     def solve_tick(self, mode: int, state, z_min, z_max, *, want_plan: bool = False) -> Dict[str, torch.Tensor]:
