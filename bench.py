@@ -517,7 +517,7 @@ def run_ours(args, rank, world, local_rank):
         reduced = {
             "value": world * solves_per_step / s16, "unit": UNIT, "ms_per_step": float(np.mean(ms16)),
             "dtype": "f16 hi/lo x3 operands, f32 accumulate + ADMM state, f64 walk state",
-            "kernel": "k_strict_rollout_f16 (tcgen05.mma kind::f16, TMEM accumulators)",
+            "kernel": "k_strict_rollout_f16p (tcgen05.mma.cta_group::2 kind::f16 on CTA pairs, TMEM accumulators)",
             "eps": 1e-5, "mean_iters_per_solve": it16 / max(solves_per_step, 1),
             "useful_column_slot_fraction": it16 / max(128 * st16["group_iterations"], 1),
             "not_converged_columns": int((out16["status"] != 0).sum().item()),

@@ -61,12 +61,12 @@ struct PairParams {
 
 template <int kParts>
 struct PairControl {
-    unsigned long long bar_load, bar_mma, bar_ready;
+    unsigned long long bar_load, bar_mma;
     uint32_t tmem_base;
     int unit, max_ticks;
     int other_ticks;             // written by the other CTA of the pair
     int other_unit;              // unit index handed over by the leader
-    int other_done[2];           // written by the other CTA: "all my columns are done" of exchange k (double buffered)
+    uint32_t other_word;         // written by the other CTA: (exchange number << 1) | "all my columns are done"
     float gpx[kF16Tile * 3];
     double X[kPairCols][3];
     uint32_t Res[2 * kParts][kPairCols];
@@ -102,6 +102,16 @@ __device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint3
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     }
+}
+// One word per exchange instead of an mbarrier round trip: the sender stores (sequence << 1 | done) with cluster-scope
+// release, the receiver polls its own copy with cluster-scope acquire.
+__device__ __forceinline__ void remote_store_release(uint32_t remote_addr, uint32_t v) {
+    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t load_acquire_cluster(const void* local) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(local)) : "memory");
+    return v;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -176,7 +186,7 @@ k_strict_rollout_f16p(const PairParams P) {
     if (tid == 0) {
         mbar_init(&S.bar_load, 1);
         mbar_init(&S.bar_mma, 1);
-        mbar_init(&S.bar_ready, 1);
+        S.other_word = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -202,8 +212,7 @@ k_strict_rollout_f16p(const PairParams P) {
     const uint32_t tmem = S.tmem_base + ((uint32_t)(32 * quad) << 16);   // this warp's lane quadrant
     // D = FP32, A = B = FP16, both K-major, N = 160, M = 128 (the pair's tile)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kF16Tile >> 3) << 17) | ((uint32_t)(kF16Cols >> 4) << 24);
-    const uint32_t other_ready = map_to_cta(smem_u32(&S.bar_ready), other);
-    const uint32_t other_done0 = map_to_cta(smem_u32(&S.other_done[0]), other);
+    const uint32_t other_word_addr = map_to_cta(smem_u32(&S.other_word), other);
     const uint32_t other_ticks_addr = map_to_cta(smem_u32(&S.other_ticks), other);
     const uint32_t other_unit_addr = map_to_cta(smem_u32(&S.other_unit), other);
 
@@ -219,7 +228,7 @@ k_strict_rollout_f16p(const PairParams P) {
     }
 
     float hi[kChunks * 8];        // upper bounds of this thread's rows (tick-relative, FP32)
-    uint32_t mma_parity = 0, ready_parity = 0;
+    uint32_t mma_parity = 0;
     unsigned int exchange = 0;    // exchanges with the other CTA so far (flag slot = exchange & 1)
 
     for (;;) {
@@ -416,14 +425,12 @@ k_strict_rollout_f16p(const PairParams P) {
             // ================= ADMM =================
             for (int k = 0; k < P.max_iter; ++k) {
                 // ---- the pair meets: "my right-hand sides are published; all my columns are done / not done" ----
-                if (tid == 0) {
-                    remote_store(other_done0 + 4u * (exchange & 1u), local_done);
-                    remote_arrive(other_ready);
-                }
-                mbar_wait_cluster(&S.bar_ready, ready_parity);
-                ready_parity ^= 1u;
-                const bool pair_done = local_done && (*reinterpret_cast<volatile int*>(&S.other_done[exchange & 1u]) != 0);
                 ++exchange;
+                if (tid == 0) remote_store_release(other_word_addr, (exchange << 1) | (uint32_t)local_done);
+                uint32_t word;
+                do { word = load_acquire_cluster(&S.other_word); } while ((word >> 1) < exchange);
+                // (a word from a LATER exchange means the other CTA went on: the pair was not done at this one)
+                const bool pair_done = local_done && (word >> 1) == exchange && (word & 1u);
                 PC_MARK(pc_exch);
                 if (pair_done) break;
                 if (rank == 0 && warp == 0) {
@@ -589,9 +596,9 @@ k_strict_rollout_f16p(const PairParams P) {
 #endif
 
         // ---- per-column summaries ---------------------------------------------------------------
-        if (tid == 0) {
+        if (tid == 0 && rank == 0) {          // one count per 128-column unit
             atomicAdd(P.stats, (unsigned long long)unit_iters);
-            if (rank == 0) atomicAdd(P.stats + 1, 1ull);
+            atomicAdd(P.stats + 1, 1ull);
         }
         if (head && valid) {
             if (B.max_violation) B.max_violation[b * 2 + axis] = viol;

@@ -889,3 +889,43 @@ def test_speed_generator_wieber_mode_matches_reference(engine, golden, default_c
     classic = SpeedTrajectoryGenerator(replace(cfg, speed_generation="classic")).generate_speed_and_state_batched(dist, step, spread)
     vx, _, _ = SpeedTrajectoryGenerator(replace(cfg, speed_generation="classic")).generate_speed_and_state(save_footsteps=False)
     assert np.array_equal(classic["v"][0, :n0, 0], vx) and not classic["v"][..., 1].any()
+
+
+# ----------------------------------------------------------------------------- CTA-pair kernel (tcgen05.mma cta_group::2)
+def test_reduced_pair_kernel_equals_single_cta_kernel(engine):
+    """The reduced-precision walks run on CTA pairs (cta_group::2, 64 columns per CTA, "2 x 2" tensor-memory layout; 20 warps
+    per CTA for small batches, two 8-warp CTAs per SM for large ones).  Same arithmetic as the single-CTA tcgen05 kernel
+    (LIPM_OPT_SINGLE_CTA_F16): every output is bit-identical -- ragged walks, pushes, partial units, both variants,
+    single ticks with plans."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(9700, seed=13)         # 152 units: the two-CTAs-per-SM variant
+    n = 60
+    z_max, z_min = z_max[100:100 + n], z_min[100:100 + n]
+    rng = np.random.default_rng(13)
+    n_steps = rng.integers(2, n + 1, 9700).astype(np.int32)
+    n_steps[:5] = [n, 0, 1, 2, n]
+    tick = (n_steps // 2).astype(np.int32)
+    x0 = rng.normal(size=(9700, 3)) * [0.01, 0.02, 0.05]
+    plan = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
+    for count in (9700, 300, 64, 5):                                             # 300 -> 5 units: the 20-warp variant
+        results = []
+        for single in (True, False):
+            plan.set_single_cta_f16(single)
+            out = plan.rollout(engine.MODE_STRICT, x0[:count], x0[:count], z_min, z_max, n_steps=n_steps[:count],
+                               impulse=impulse[:count], force_tick=tick[:count], want_readout=True)
+            results.append({k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")})
+        for key in results[0]:
+            assert np.array_equal(results[0][key], results[1][key]), (count, key)
+    # single ticks (the predict_wieber_axis path), other horizons
+    for N in (16, 100, 152):
+        p = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
+        x = rng.normal(size=(200, 3)) * [0.05, 0.1, 0.5]
+        centre = rng.uniform(-0.05, 0.05, size=(200, 1)) + 0.0 * np.zeros((200, N))
+        got = []
+        for single in (True, False):
+            p.set_single_cta_f16(single)
+            res = p.solve_tick(engine.MODE_STRICT, x, centre - 0.03, centre + 0.03, want_plan=True)
+            got.append({k: res[k].cpu().numpy() for k in ("next_state", "zmp_plan", "iters", "status")})
+        for key in got[0]:
+            assert np.array_equal(got[0][key], got[1][key]), (N, key)
+        p.set_single_cta_f16(False)
+    plan.set_single_cta_f16(False)
