@@ -208,3 +208,47 @@ def test_predict_herdt_joint_reference_signature(herdt_case):
     assert abs(out[2] - fx1) < 1e-7 and abs(out[3] - fy1) < 1e-7
     with pytest.raises(ValueError):
         ctrl.generate_com_trajectory(x, y)                  # herdt needs v_ref and state_ref (reference :53-54)
+
+
+@pytest.mark.gpu
+def test_herdt_randomized_plans_match_oracle(golden):
+    """BASELINE configs[3]: three plans of the randomized set (seed 2) with three DIFFERENT timelines (452 / 377 / 302
+    samples), own step length / foot spread / distance / velocity scale / push, against the KKT-certified oracle walks
+    (tests/golden/oracle_herdt_plans.npz: timeline, reference speeds and nb_steps from the REFERENCE's own generators).
+    Every tick up to the final stance carries a certificate; compared over that prefix."""
+    from dataclasses import replace
+
+    from mpc_bipedal.config import MPCConfig
+    from mpc_bipedal.controllers import ZMPController
+    from mpc_bipedal.generators.cop_generator import State
+    from mpc_bipedal.generators.speed_generation import SpeedTrajectoryGenerator
+    from mpc_bipedal.herdt import randomized_plans, state_codes
+
+    g = golden("oracle_herdt_plans")
+    names = np.array([State.STANDING, State.DOUBLE_SUPPORT, State.SINGLE_SUPPORT], dtype=object)
+    lengths = set()
+    plans = randomized_plans(MPCConfig(), 8192, seed=2)
+    for k, b in enumerate(g["plan_ids"]):
+        step_length, spread, distance, speed, F_ext = g[f"p{k}/params"]
+        # the draw is the one the drivers and the bench use
+        assert plans["step_length"][b] == step_length and plans["foot_spread"][b] == spread and plans["speed"][b] == speed
+        cfg = replace(MPCConfig(), step_length=float(step_length), foot_spread=float(spread), distance=float(distance),
+                      speed_generation="classic", add_force=True, F_ext=float(F_ext))
+        cfg.method = "herdt"
+        vx, vy, states = SpeedTrajectoryGenerator(cfg).generate_speed_and_state(save_footsteps=False)
+        codes = g[f"p{k}/states"]
+        assert np.array_equal(state_codes(states), codes)                   # host timeline == the reference's
+        v_ref = np.stack([vx, vy], 1) * speed
+        assert np.array_equal(v_ref, g[f"p{k}/v_ref"])
+        ctrl = ZMPController(cfg)
+        padded = np.concatenate([names[codes], np.repeat(names[codes][-1:], cfg.horizon)])
+        assert np.array_equal(np.array(ctrl.find_nb_steps(padded), np.int32), g[f"p{k}/nb_steps"])
+        com, y_hist, foot_hist = ctrl.generate_com_trajectory(np.zeros((3, 1)), np.zeros((3, 1)), v_ref=v_ref, state_ref=names[codes])
+        m = int(g[f"p{k}/certified_ticks"]) + 1
+        lengths.add(len(codes))
+        assert m > 0.8 * len(codes)
+        assert np.max(np.abs(foot_hist[:m] - g[f"p{k}/foot_hist"])) < 1e-6, k
+        assert np.max(np.abs(y_hist[:m, :2, 0] - g[f"p{k}/y_hist"][:, :2])) < 1e-7, k          # position, velocity
+        assert np.max(np.abs(y_hist[:m, 2, 0] - g[f"p{k}/y_hist"][:, 2])) < 1e-5, k            # acceleration carries the jerk
+        assert np.max(np.abs(com[:m, 0] - g[f"p{k}/x_hist"][:, 0])) < 1e-7, k
+    assert len(lengths) == 3
