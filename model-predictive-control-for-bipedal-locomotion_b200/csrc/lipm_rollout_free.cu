@@ -32,6 +32,8 @@ struct FreeParams {
     int ticks_max;
     int per_column;       // 1: one preview series per column; 0: one per (bound series, axis)
     int col0, ncols;      // columns of this launch
+    int pairs;            // 1 (walks): column c = axis c & 1 of scenario c >> 1, so that the x and y lanes of a scenario are
+                          // neighbours and its com / zmp / flag samples leave as contiguous runs; 0 (single ticks): c -> slot c
 };
 
 struct ColumnView {
@@ -40,11 +42,11 @@ struct ColumnView {
     const double *plo, *phi;
 };
 
-// Decodes column c exactly like the strict kernels do.
-__device__ __forceinline__ ColumnView column_view(const ColumnBatch& B, int c) {
+// Decodes column c: like the strict kernels do (axis-major) or with the axes of a scenario interleaved.
+__device__ __forceinline__ ColumnView column_view(const ColumnBatch& B, int c, int pairs) {
     ColumnView v;
-    v.axis = c / B.B;
-    v.b = c - v.axis * B.B;
+    v.axis = pairs ? (c & 1) : c / B.B;
+    v.b = pairs ? (c >> 1) : c - v.axis * B.B;
     int n = B.n_steps ? B.n_steps[v.b] : B.n_uniform;
     n = n > B.n_max ? B.n_max : n;
     int ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(128) k_free_preview(const FreeParams P) {
     const double *plo, *phi;
     int last, ticks;
     if (P.per_column) {
-        const ColumnView v = column_view(B, P.col0 + series);
+        const ColumnView v = column_view(B, P.col0 + series, P.pairs);
         plo = v.plo; phi = v.phi; last = v.last; ticks = v.ticks;
     } else {
         const int axis = series & 1;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(128) k_free_preview_walk(const FreeParams P) {
     const double *plo, *phi;
     int last, ticks;
     if (P.per_column) {
-        const ColumnView v = column_view(B, P.col0 + series);
+        const ColumnView v = column_view(B, P.col0 + series, P.pairs);
         plo = v.plo; phi = v.phi; last = v.last; ticks = v.ticks;
     } else {
         const int axis = series & 1;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(128) k_free_preview_walk(const FreeParams P) {
 __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreeParams P) {
     __shared__ double tile[kFreeWarps][kFreeCols][kFreeTicks * 3 + 1];
     __shared__ unsigned long long flags8[kFreeWarps][kFreeCols];     // one byte per staged tick
+    __shared__ double tile2[kFreeWarps][2][kFreeCols / 2][kFreeTicks * 2];   // com, zmp of 4 scenarios: (x, y) per staged tick
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ColumnBatch& B = P.cb;
     const int N = P.N;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
     const int local = (blockIdx.x * kFreeWarps + warp) * kFreeCols + lane;      // column within this launch
     const bool valid = lane < kFreeCols && local < P.ncols;
     const int c = P.col0 + (valid ? local : 0);
-    const ColumnView v = column_view(B, c);
+    const ColumnView v = column_view(B, c, P.pairs);
     const int ticks = valid ? v.ticks : 0;
     double* hist = nullptr;
     double *pcom = nullptr, *pzmp = nullptr;
@@ -230,9 +233,13 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
                 const double below = l0[l] - zmp, above = zmp - h0[l];
                 viol = fmax(viol, fmax(fmax(below, above), 0.0));
                 lean = fmax(lean, fabs(n0 - zmp));
-                // x and y of a sample are neighbours in com / zmp: the two columns of a scenario fill one 16-byte pair
-                if (pcom) pcom[(long long)(i + 1) * 2] = n0;
-                if (pzmp) pzmp[(long long)(i + 1) * 2] = zmp;
+                if (P.pairs) {       // staged: the (x, y) lanes of a scenario fill 16-byte pairs, written out as one run below
+                    tile2[warp][0][lane >> 1][l * 2 + (lane & 1)] = n0;
+                    tile2[warp][1][lane >> 1][l * 2 + (lane & 1)] = zmp;
+                } else {
+                    if (pcom) pcom[(long long)(i + 1) * 2] = n0;
+                    if (pzmp) pzmp[(long long)(i + 1) * 2] = zmp;
+                }
                 flag8 |= (unsigned long long)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) |
                                               (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u)) << (8 * l);
             }
@@ -250,6 +257,20 @@ __global__ void __launch_bounds__(32 * kFreeWarps) k_free_rollout(const FreePara
             const int nv = __shfl_sync(0xffffffffu, run, col) * 3;
             const unsigned long long dst = __shfl_sync(0xffffffffu, base, col);
             if (dst != 0ull && lane < nv) reinterpret_cast<double*>(dst)[lane] = tile[warp][col][lane];
+        }
+        if (P.pairs && (B.com || B.zmp)) {
+            // com / zmp: per scenario the (x, y) samples of this block's ticks are 16 * run contiguous bytes
+            const unsigned long long cbase = pcom ? (unsigned long long)(pcom + (long long)(i0 + 1) * 2) : 0ull;
+            const unsigned long long zbase = pzmp ? (unsigned long long)(pzmp + (long long)(i0 + 1) * 2) : 0ull;
+#pragma unroll
+            for (int sc = 0; sc < kFreeCols / 2; ++sc) {
+                const int nv = __shfl_sync(0xffffffffu, run, 2 * sc) * 2;          // x lane of the scenario (axis 0: pointers have no axis offset)
+                const unsigned long long dc = __shfl_sync(0xffffffffu, cbase, 2 * sc);
+                const unsigned long long dz = __shfl_sync(0xffffffffu, zbase, 2 * sc);
+                const int k = lane & 15;
+                const unsigned long long dst = lane < 16 ? dc : dz;
+                if (dst != 0ull && k < nv) reinterpret_cast<double*>(dst)[k] = tile2[warp][lane >> 4][sc][k];
+            }
         }
 #pragma unroll
         for (int q = 0; q < kFreeCols / 4; ++q) {
@@ -418,7 +439,8 @@ int launch_unconstrained_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStr
     // Scenarios that share a bound series (and its length) share the preview term; per-scenario lengths or series
     // need one preview series per column, computed and consumed in chunks so that the scratch stays small.
     P.per_column = (cb.n_steps != nullptr || (cb.bounds_batch != 1 && cb.bounds_index == nullptr)) ? 1 : 0;
-    const int chunk = P.per_column ? kFreeChunk : cb.ncols;
+    P.pairs = (cb.ncols == 2 * cb.B) ? 1 : 0;          // walks: both axes of every scenario (single ticks: ncols == B)
+    const int chunk = P.per_column ? (kFreeChunk & ~1) : cb.ncols;      // even: a scenario's two columns stay in one launch
     const size_t series = P.per_column ? (size_t)(cb.ncols < chunk ? cb.ncols : chunk) : (size_t)cb.bounds_batch * 2;
     StreamBuffer preview;
     LIPM_CUDA_TRY(preview.alloc(sizeof(double) * series * (size_t)P.ticks_max, stream));
