@@ -195,6 +195,19 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
 #define LIPM_OPT_KEEP_POOL_MEMORY 1
 #define LIPM_OPT_TICK_RANGES 2
 #define LIPM_OPT_SINGLE_CTA_F16 3
+#define LIPM_OPT_STRICT_SOLVER 4   /* plan required; LIPM_SOLVER_* of the FP64 strict mode                        */
+#define LIPM_OPT_RICCATI_LANES 5   /* plan required; columns per warp of the active-set kernel (0 automatic,
+                                      else a power of two <= 32); results do not depend on it                    */
+#define LIPM_OPT_MAX_SWEEPS 6      /* plan required; active-set corrections per QP before it is reported as
+                                      not converged (0 -> 64)                                                    */
+
+/* solver of the FP64 strict mode (LIPM_OPT_STRICT_SOLVER).  Both return the unique minimiser of the reference's
+ * QP (zmp_controller.py:173-191); they share no arithmetic, so their agreement is a test (tests/test_cuda_parity.py). */
+#define LIPM_SOLVER_ACTIVE_SET 0   /* default: primal-dual active set, sub-problems solved exactly by an O(N) Riccati
+                                      sweep over the 3-state model (csrc/lipm_rollout_riccati.cu); `iters` counts
+                                      sweep pairs                                                                */
+#define LIPM_SOLVER_ADMM 1         /* fixed-rho ADMM on the condensed QP, FP64 tensor pipe (csrc/lipm_rollout_strict.cu);
+                                      `iters` counts ADMM iterations; rho / alpha / eps / max_iter apply           */
 int lipm_set_option(lipm_plan_t* plan, int option, long long value);
 
 /*

@@ -75,7 +75,7 @@ extern "C" {
 
 const char* lipm_last_error(void) { return g_error; }
 
-const char* lipm_version(void) { return "lipm_mpc 0.3 (sm_100a; fp64 DMMA ADMM, tcgen05 f16x3 ADMM, gain-row unconstrained)"; }
+const char* lipm_version(void) { return "lipm_mpc 0.4 (sm_100a; fp64 active-set Riccati, fp64 DMMA ADMM, tcgen05 f16x3 ADMM, gain-row unconstrained)"; }
 
 int lipm_max_reduced_horizon(void) { return kMaxReducedStreamHorizon; }
 
@@ -207,6 +207,18 @@ int lipm_set_option(lipm_plan_t* plan, int option, long long value) {
             if (!plan || (value != 0 && value != 1)) { set_error("lipm_set_option(SINGLE_CTA_F16): need a plan and 0 / 1"); return LIPM_E_INVALID; }
             plan->single_cta_f16 = (int)value;
             return LIPM_OK;
+        case LIPM_OPT_STRICT_SOLVER:
+            if (!plan || (value != LIPM_SOLVER_ACTIVE_SET && value != LIPM_SOLVER_ADMM)) { set_error("lipm_set_option(STRICT_SOLVER): need a plan and LIPM_SOLVER_ACTIVE_SET / LIPM_SOLVER_ADMM"); return LIPM_E_INVALID; }
+            plan->solver = (int)value;
+            return LIPM_OK;
+        case LIPM_OPT_RICCATI_LANES:
+            if (!plan || value < 0 || value > 32 || (value & (value - 1)) != 0) { set_error("lipm_set_option(RICCATI_LANES): need a plan and 0 or a power of two <= 32"); return LIPM_E_INVALID; }
+            plan->riccati_lanes = (int)value;
+            return LIPM_OK;
+        case LIPM_OPT_MAX_SWEEPS:
+            if (!plan || value < 0 || value > 100000) { set_error("lipm_set_option(MAX_SWEEPS): need a plan and a value in [0, 100000]"); return LIPM_E_INVALID; }
+            plan->riccati_max_sweeps = (int)value;
+            return LIPM_OK;
         default:
             set_error("lipm_set_option: unknown option %d", option);
             return LIPM_E_INVALID;
@@ -299,7 +311,9 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
         rc = launch_unconstrained_rollout(plan, cb, stream);
     } else {
         // strict walks: group scenarios that will need similar iteration counts (lipm_order.cu)
-        const int width = plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : 8;
+        const bool active_set = plan->desc.precision != LIPM_PRECISION_F16X3 && plan->solver != LIPM_SOLVER_ADMM;
+        // columns that share a solver group (ADMM kernels) or a warp (active-set kernel: lock-step sweeps)
+        const int width = plan->desc.precision == LIPM_PRECISION_F16X3 ? kF16Cols : (active_set ? 16 : 8);
         StreamBuffer order, unit_order;        // released on every path out of this scope
         if (B > 8 && (io->n_steps || (io->impulse && io->force_tick))) {
             rc = build_processing_order(B, n_max, io->n_steps, io->impulse, io->force_tick, width, order, stream);
@@ -308,7 +322,7 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
         cb.order = order.as<int>();
         // longest-expected-first dispatch of the kernel's work units (8 columns FP64, 128 columns reduced precision)
         const int units = (cb.ncols + width - 1) / width;
-        if (units > 1 && io->impulse && io->force_tick) {
+        if (units > 1 && io->impulse && io->force_tick && !active_set) {
             rc = build_unit_order(units, width, cb.ncols, B, cb.order, n_max, io->n_steps, io->impulse, io->force_tick, unit_order, stream);
             if (rc != LIPM_OK) return rc;
         }

@@ -121,6 +121,9 @@ struct lipm_plan {
     int f16s_nk;           // padded contraction length of d_f16s: multiple of 16, >= N + 3
     int f16s_slabs;        // 160-row slabs
     int single_cta_f16;   // 1: reduced-precision walks on the single-CTA kernel instead of CTA pairs (lipm_set_option)
+    int solver;           // LIPM_SOLVER_* of the FP64 strict mode (lipm_set_option; 0 = active set + Riccati sweeps)
+    int riccati_lanes;    // columns per warp of the active-set kernel (0 = automatic)
+    int riccati_max_sweeps;   // active-set corrections per QP (0 -> 64)
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch (copied from the launch's own state)
@@ -175,12 +178,14 @@ int build_unit_order(int num_units, int width, int ncols, int B, const int* orde
 int launch_pack_outcomes(int B, const double* max_violation, const double* lean_max, const int32_t* status, const int32_t* iters,
                          double fall_lean, lipm_outcome_t* outcome, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
+int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // active set + Riccati sweeps
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16p(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // CTA pairs (cta_group::2)
 // strict rollout on the kernel that matches the plan's precision and horizon
 inline int launch_strict(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
-    if (plan->desc.precision != LIPM_PRECISION_F16X3) return launch_strict_rollout(plan, cb, stream);
+    if (plan->desc.precision != LIPM_PRECISION_F16X3)
+        return plan->solver == LIPM_SOLVER_ADMM ? launch_strict_rollout(plan, cb, stream) : launch_strict_rollout_riccati(plan, cb, stream);
     if (plan->N > kMaxReducedHorizon) return launch_strict_rollout_f16s(plan, cb, stream);
     return plan->single_cta_f16 ? launch_strict_rollout_f16(plan, cb, stream) : launch_strict_rollout_f16p(plan, cb, stream);
 }

@@ -81,6 +81,14 @@ class _RolloutIO(ctypes.Structure):
 OPT_KEEP_POOL_MEMORY = 1
 OPT_TICK_RANGES = 2
 OPT_SINGLE_CTA_F16 = 3
+OPT_STRICT_SOLVER = 4
+OPT_RICCATI_LANES = 5
+OPT_MAX_SWEEPS = 6
+# solver of the FP64 strict mode: both return the unique minimiser of the reference's QP
+SOLVER_ACTIVE_SET = 0   # default: primal-dual active set + O(N) Riccati sweeps (csrc/lipm_rollout_riccati.cu)
+SOLVER_ADMM = 1         # ADMM on the condensed QP, FP64 tensor pipe (csrc/lipm_rollout_strict.cu)
+_SOLVERS = {"active_set": SOLVER_ACTIVE_SET, "riccati": SOLVER_ACTIVE_SET, "admm": SOLVER_ADMM,
+            SOLVER_ACTIVE_SET: SOLVER_ACTIVE_SET, SOLVER_ADMM: SOLVER_ADMM}
 OUTCOME_WORDS = 4      # lipm_outcome_t = 4 x 8 bytes: max_violation f64, lean_max f64, (status i32, fell i32), iters i64
 
 _lib = None
@@ -160,6 +168,7 @@ class PlanKey:
     viol_tol: float = -1.0
     device: int = 0
     precision: int = 0
+    solver: int = 0
 
 
 class LipmPlan:
@@ -167,7 +176,10 @@ class LipmPlan:
 
     def __init__(self, horizon: int, h: float, g: float, dt: Optional[float], Q: float, R: float, *,
                  rho: float = 0.0, alpha: float = 0.0, eps: float = 0.0, max_iter: int = 0,
-                 viol_tol: float = -1.0, device: Optional[int] = None, precision: int = PRECISION_FP64):
+                 viol_tol: float = -1.0, device: Optional[int] = None, precision: int = PRECISION_FP64,
+                 solver=SOLVER_ACTIVE_SET):
+        if solver not in _SOLVERS:
+            raise ValueError(f"unknown solver {solver!r}: 'active_set' or 'admm'")
         if not torch.cuda.is_available():
             raise RuntimeError("liblipm_mpc needs a CUDA device (B200 / sm_100a); there is no CPU path")
         self._lib = load_library()
@@ -185,6 +197,9 @@ class LipmPlan:
         _check(self._lib.lipm_plan_create(ctypes.byref(handle), ctypes.byref(desc)))
         self._handle = handle
         self.h, self.g, self.Q, self.R = h, g, Q, R
+        self.solver = _SOLVERS[solver]
+        if self.solver != SOLVER_ACTIVE_SET:
+            _check(self._lib.lipm_set_option(self._handle, OPT_STRICT_SOLVER, self.solver))
 
     def close(self) -> None:
         if getattr(self, "_handle", None):
@@ -282,6 +297,14 @@ class LipmPlan:
         """Force the number of tick ranges of the FP64 strict kernel (0 = automatic); results do not depend on it."""
         _check(self._lib.lipm_set_option(self._handle, OPT_TICK_RANGES, int(ranges)))
 
+    def set_riccati_lanes(self, lanes: int) -> None:
+        """Columns per warp of the active-set kernel (0 = automatic); results do not depend on it."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_RICCATI_LANES, int(lanes)))
+
+    def set_max_sweeps(self, sweeps: int) -> None:
+        """Active-set corrections per QP before the solve is reported as not converged (0 = default 64)."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_MAX_SWEEPS, int(sweeps)))
+
     def set_single_cta_f16(self, on: bool) -> None:
         """Reduced-precision walks (N <= 152) on the single-CTA tcgen05 kernel instead of the CTA-pair one."""
         _check(self._lib.lipm_set_option(self._handle, OPT_SINGLE_CTA_F16, 1 if on else 0))
@@ -354,6 +377,10 @@ def get_plan(horizon: int, h: float, g: float, dt: float, Q: float, R: float, *,
              **solver) -> LipmPlan:
     """Plans are immutable and cheap to keep: cache one per parameter set and device."""
     dev = torch.cuda.current_device() if device is None else int(device)
+    if "solver" in solver:
+        if solver["solver"] not in _SOLVERS:
+            raise ValueError(f"unknown solver {solver['solver']!r}: 'active_set' or 'admm'")
+        solver = dict(solver, solver=_SOLVERS[solver["solver"]])
     key = PlanKey(int(horizon), float(h), float(g), float(dt), float(Q), float(R), device=dev, **solver)
     plan = _plan_cache.get(key)
     if plan is None:

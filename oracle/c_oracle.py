@@ -73,7 +73,8 @@ class COracle:
         flags = np.zeros((B, n_max, 2), np.uint8)
         viol, status, iters = np.zeros((B, 2)), np.zeros((B, 2), np.int32), np.zeros((B, 2), np.int32)
         ptr = lambda a: None if a is None else a.ctypes.data
-        self.lib.lipm_oracle_rollout(self.plan, 1 if strict else 0, B, n_max, ptr(n_steps), ptr(x0), ptr(y0),
+        mode = 2 if strict == "riccati" else (1 if strict else 0)     # "riccati": active-set + Riccati solver
+        self.lib.lipm_oracle_rollout(self.plan, mode, B, n_max, ptr(n_steps), ptr(x0), ptr(y0),
                                      ptr(z_min), ptr(z_max), bounds_batch, ptr(impulse), ptr(force_tick),
                                      ptr(x_hist), ptr(y_hist), ptr(flags), ptr(viol), ptr(status), ptr(iters),
                                      int(threads))

@@ -198,9 +198,127 @@ static int admm_solve(const oracle_plan *p, const double *x, const double *lo, c
     return it;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Third strict solver (cross-check of the ADMM above and blueprint of csrc/lipm_rollout_riccati.cu):
+ * primal-dual active-set iteration whose equality-constrained sub-problems are solved EXACTLY in O(N)
+ * by a Riccati sweep.  The strict QP (zmp_controller.py:173-191) is an LQ tracking problem of the
+ * 3-state model (:15-21): stage i applies jerk J_i, x_{i+1} = A x_i + B J_i, previews z_i = C x_{i+1},
+ * costs Q/2 (z_i - zref_i)^2 + R/2 J_i^2 and must keep zmin_i <= z_i <= zmax_i.  For a guessed active set
+ * (rows pinned to a bound) the backward sweep gives the cost-to-go 1/2 x'P_i x + p_i'x; a pinned row fixes its own
+ * jerk (J_i = (b_i - C A x_i) / (C B)).  The forward sweep returns the plan z and, on pinned rows, the
+ * multiplier mu_i = d cost / d b_i (= the gradient (H z + q)_i of the condensed QP).  Rows that leave the
+ * box are pinned, pinned rows whose multiplier has the wrong sign are released, until nothing changes:
+ * that fixed point satisfies the KKT conditions of the reference's QP, whose minimiser is unique.
+ * act: in = guess (previous tick's set moved up by one sample), out = final set (-1 lower, +1 upper).
+ * Returns Riccati sweeps executed; *converged = 0 if the set still changed after max_sweeps. */
+static uint8_t *g_sweep_log = NULL;   /* debug: [2B, n_max] sweeps per tick (tools only) */
+void lipm_oracle_set_sweep_log(uint8_t *p) { g_sweep_log = p; }
+
+static int riccati_pdas_solve(const oracle_plan *p, const double *x, const double *lo, const double *hi, int8_t *act,
+                              double *gain /* [N,4] */, double *z, double *jerk0, int max_sweeps, int *converged) {
+    const int N = p->N;
+    const double T = p->dt, c2 = p->B[1], c3 = p->B[0], hg = -p->C[2], Q = p->Q, R = p->R;
+    const double cb = c3 - hg * T;                      /* C B = Pu[0][0] */
+    const double ca[3] = {1.0, T, c2 - hg};             /* C A = Px[0]    */
+    const double kv[3] = {-ca[0] / cb, -ca[1] / cb, -ca[2] / cb};
+    const double bc[3] = {c3 / cb, c2 / cb, T / cb};
+    double Ac[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Ac[r * 3 + c] = p->A[r * 3 + c] - p->B[r] * ca[c] / cb;
+    *converged = 0;
+    int sweeps = 0;
+    double mu_scale = 1.0;
+    while (sweeps < max_sweeps) {
+        ++sweeps;
+        /* backward: P symmetric (P00 P01 P02 P11 P12 P22), p */
+        double P00 = 0, P01 = 0, P02 = 0, P11 = 0, P12 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
+        for (int i = N - 1; i >= 0; --i) {
+            double *gi = gain + (size_t)i * 4;
+            if (act[i]) {
+                const double b = act[i] > 0 ? hi[i] : lo[i];
+                const double m0 = P00 * bc[0] + P01 * bc[1] + P02 * bc[2];
+                const double m1 = P01 * bc[0] + P11 * bc[1] + P12 * bc[2];
+                const double m2 = P02 * bc[0] + P12 * bc[1] + P22 * bc[2];
+                gi[0] = m0; gi[1] = m1; gi[2] = m2; gi[3] = bc[0] * p0 + bc[1] * p1 + bc[2] * p2;
+                const double v0 = m0 * b + p0, v1 = m1 * b + p1, v2 = m2 * b + p2;
+                const double rb = R * b / cb;
+                const double n0 = Ac[0] * v0 + Ac[3] * v1 + Ac[6] * v2 + rb * kv[0];
+                const double n1 = Ac[1] * v0 + Ac[4] * v1 + Ac[7] * v2 + rb * kv[1];
+                const double n2 = Ac[2] * v0 + Ac[5] * v1 + Ac[8] * v2 + rb * kv[2];
+                /* Y = P Ac, Pn = Ac' Y + R kv kv' */
+                double Y[9];
+                const double Pm[9] = {P00, P01, P02, P01, P11, P12, P02, P12, P22};
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) Y[r * 3 + c] = Pm[r * 3] * Ac[c] + Pm[r * 3 + 1] * Ac[3 + c] + Pm[r * 3 + 2] * Ac[6 + c];
+#define ACTY(r, c) (Ac[r] * Y[c] + Ac[3 + r] * Y[3 + c] + Ac[6 + r] * Y[6 + c] + R * kv[r] * kv[c])
+                P00 = ACTY(0, 0); P01 = ACTY(0, 1); P02 = ACTY(0, 2); P11 = ACTY(1, 1); P12 = ACTY(1, 2); P22 = ACTY(2, 2);
+#undef ACTY
+                p0 = n0; p1 = n1; p2 = n2;
+            } else {
+                const double r = 0.5 * (lo[i] + hi[i]);
+                const double W00 = P00 + Q, W01 = P01, W02 = P02 - Q * hg, W11 = P11, W12 = P12, W22 = P22 + Q * hg * hg;
+                const double w0 = p0 - Q * r, w1 = p1, w2 = p2 + Q * r * hg;
+                const double b0 = W00 * c3 + W01 * c2 + W02 * T;
+                const double b1 = W01 * c3 + W11 * c2 + W12 * T;
+                const double b2 = W02 * c3 + W12 * c2 + W22 * T;
+                const double s = R + c3 * b0 + c2 * b1 + T * b2;
+                const double bw = c3 * w0 + c2 * w1 + T * w2;
+                const double u0 = b0, u1 = T * b0 + b1, u2 = c2 * b0 + T * b1 + b2;
+                const double is = 1.0 / s;
+                const double k0 = u0 * is, k1 = u1 * is, k2 = u2 * is, kc = bw * is;
+                gi[0] = k0; gi[1] = k1; gi[2] = k2; gi[3] = kc;
+                /* X = A' W A */
+                const double Y00 = W00, Y01 = T * W00 + W01, Y02 = c2 * W00 + T * W01 + W02;
+                const double Y11 = T * W01 + W11, Y12 = c2 * W01 + T * W11 + W12;
+                const double Y22 = c2 * W02 + T * W12 + W22;
+                const double X00 = Y00, X01 = Y01, X02 = Y02;
+                const double X11 = T * Y01 + Y11, X12 = T * Y02 + Y12;
+                const double X22 = c2 * Y02 + T * Y12 + Y22;
+                P00 = X00 - u0 * k0; P01 = X01 - u0 * k1; P02 = X02 - u0 * k2;
+                P11 = X11 - u1 * k1; P12 = X12 - u1 * k2; P22 = X22 - u2 * k2;
+                p0 = w0 - u0 * kc; p1 = T * w0 + w1 - u1 * kc; p2 = c2 * w0 + T * w1 + w2 - u2 * kc;
+            }
+        }
+        /* forward: plan, multipliers, set update */
+        double s0 = x[0], s1 = x[1], s2 = x[2];
+        int changed = 0;
+        double zmag = 1.0;
+        const double tol = 1e-13 * mu_scale;
+        for (int i = 0; i < N; ++i) {
+            const double *gi = gain + (size_t)i * 4;
+            double J, zi;
+            int a = act[i];
+            if (a) {
+                const double b = a > 0 ? hi[i] : lo[i];
+                J = kv[0] * s0 + kv[1] * s1 + kv[2] * s2 + b / cb;
+                const double n0 = s0 + T * s1 + c2 * s2 + c3 * J, n1 = s1 + T * s2 + c2 * J, n2 = s2 + T * J;
+                const double mu = R * J / cb + Q * (b - 0.5 * (lo[i] + hi[i])) + gi[0] * n0 + gi[1] * n1 + gi[2] * n2 + gi[3];
+                if ((a > 0 && mu > tol) || (a < 0 && mu < -tol)) { a = 0; changed = 1; }
+                zi = b;
+                s0 = n0; s1 = n1; s2 = n2;
+            } else {
+                J = -(gi[0] * s0 + gi[1] * s1 + gi[2] * s2 + gi[3]);
+                const double n0 = s0 + T * s1 + c2 * s2 + c3 * J, n1 = s1 + T * s2 + c2 * J, n2 = s2 + T * J;
+                zi = n0 - hg * n2;
+                if (zi > hi[i]) { a = 1; changed = 1; }
+                else if (zi < lo[i]) { a = -1; changed = 1; }
+                s0 = n0; s1 = n1; s2 = n2;
+            }
+            if (i == 0) *jerk0 = J;
+            z[i] = zi;
+            zmag = fmax(zmag, fabs(zi));
+            act[i] = (int8_t)a;
+        }
+        mu_scale = Q * zmag;
+        if (!changed) { *converged = 1; break; }
+    }
+    return sweeps;
+}
+
 /*
  * Walks of B scenarios.  Same argument meaning as lipm_rollout in include/lipm_mpc.h, with host
- * pointers.  mode 0 = non-strict (zmp_controller.py:196-199), 1 = strict.  Returns 0.
+ * pointers.  mode 0 = non-strict (zmp_controller.py:196-199), 1 = strict (ADMM), 2 = strict (active set + Riccati;
+ * iters then counts Riccati sweeps).  Returns 0.
  */
 int lipm_oracle_rollout(const oracle_plan *p, int mode, int B, int n_max, const int32_t *n_steps, const double *x0,
                         const double *y0, const double *z_min, const double *z_max, int bounds_batch,
@@ -214,8 +332,10 @@ int lipm_oracle_rollout(const oracle_plan *p, int mode, int B, int n_max, const 
 #pragma omp parallel
 #endif
     {
-        double *tv = (double *)malloc(sizeof(double) * N * 5);
-        double *lo = tv + N, *hi = tv + 2 * N, *rhs = tv + 3 * N, *q = tv + 4 * N;
+        double *tv = (double *)malloc(sizeof(double) * N * 10);
+        double *lo = tv + N, *hi = tv + 2 * N, *rhs = tv + 3 * N, *q = tv + 4 * N, *gain = tv + 5 * N, *zplan = tv + 9 * N;
+        int8_t *act = (int8_t *)malloc(3 * (size_t)N);
+        int8_t *shifted = act + N, *grown = act + 2 * N;
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
 #endif
@@ -254,6 +374,43 @@ int lipm_oracle_rollout(const oracle_plan *p, int mode, int B, int n_max, const 
                     double acc = 0.0;
                     for (int j = 0; j < N; ++j) acc += p->gain[j] * ((hi[j] + lo[j]) / 2);
                     jerk = acc + p->gain[N] * x[0] + p->gain[N + 1] * x[1] + p->gain[N + 2] * x[2];
+                } else if (mode == 2) {
+                    /* active-set guess: the previous tick's set moved up by one sample, new last row free */
+                    if (i == 0) { memset(act, 0, N); memset(shifted, 0, N); }
+                    else {
+                        /* rows by which a pinned run outgrew the plain shift on the previous tick keep growing */
+                        const int extrapolate = getenv("RIC_GROW") != NULL;
+                        memcpy(grown, act, N);                 /* A_k in window-k coordinates */
+                        memmove(act, act + 1, N - 1); act[N - 1] = 0;      /* S(A_k) */
+                        if (extrapolate) {
+                            int j = 0;
+                            while (j < N) {
+                                if (grown[j] && !shifted[j]) {
+                                    int j2 = j;
+                                    while (j2 + 1 < N && grown[j2 + 1] == grown[j] && !shifted[j2 + 1]) ++j2;
+                                    const int d = j2 - j + 1;
+                                    const int8_t sg = grown[j];
+                                    if (j > 0 && shifted[j - 1] == sg) {          /* run below grew upward: [j..j2] */
+                                        for (int r = j2; r < j2 + d && r < N; ++r) if (!act[r]) act[r] = sg;
+                                    } else if (j2 + 1 < N && shifted[j2 + 1] == sg) {   /* run above grew downward */
+                                        for (int r = j - 2; r > j - 2 - d && r >= 0; --r) if (!act[r]) act[r] = sg;
+                                    }
+                                    j = j2 + 1;
+                                } else ++j;
+                            }
+                        }
+                        memcpy(shifted, grown + 1, N - 1); shifted[N - 1] = 0;   /* plain shift of A_k, for the next tick */
+                    }
+                    int ok;
+                    double j0;
+                    const int sw = riccati_pdas_solve(p, x, lo, hi, act, gain, zplan, &j0, 64, &ok);
+                    total_iters += sw;
+                    if (g_sweep_log) g_sweep_log[(size_t)col * n_max + i] = (uint8_t)sw;
+                    if (!ok) { ++notconv; f |= 16; }
+                    f |= (act[0] < 0 ? 1u : 0u) | (act[0] > 0 ? 2u : 0u);
+                    const double pred = x[0] + T * x[1] + px02 * x[2];
+                    const double z0 = act[0] ? zplan[0] : clip(pred + pu00 * j0, lo[0], hi[0]);
+                    jerk = (z0 - pred) / pu00;
                 } else {
                     if (i == 0) {
                         for (int j = 0; j < N; ++j) tv[j] = 0.5 * (lo[j] + hi[j]);
@@ -285,7 +442,7 @@ int lipm_oracle_rollout(const oracle_plan *p, int mode, int B, int n_max, const 
             if (status) status[b * 2 + axis] = notconv;
             if (iters) iters[b * 2 + axis] = total_iters;
         }
-        free(tv);
+        free(tv); free(act);
     }
     return 0;
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for `ncu --set full` captures: one launch of a chosen kernel on a chosen workload.
-    python tools/ncu_targets.py f16 4096 | fp64 4096 | free 4096 | free 262144 | herdt 8192"""
+    python tools/ncu_targets.py f16 4096 | fp64 4096 (ADMM) | riccati 4096 (active set) | free 4096 | free 262144 | herdt 8192"""
 import os, sys
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +13,7 @@ from bench import sweep_inputs
 what, B = sys.argv[1], int(sys.argv[2])
 cfg, z_max, z_min, F, tick = sweep_inputs(B)
 precision = engine.PRECISION_F16X3 if what == "f16" else engine.PRECISION_FP64
-plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R, precision=precision)
+plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R, precision=precision, solver="admm" if what == "fp64" else "active_set")
 dev = plan.device
 x0 = torch.zeros((B, 3), dtype=torch.float64, device=dev)
 zmin, zmax = torch.as_tensor(z_min).to(dev), torch.as_tensor(z_max).to(dev)
