@@ -68,7 +68,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ double pow2_from_biased(int e) { return __hiloint2double(e << 20, 0); }
 __device__ __forceinline__ int biased_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
 
-constexpr int kGainPrefetch = 8;   // stages of look-ahead of the forward sweep's L1 prefetch
+constexpr int kGainPrefetch = 20;  // stages of look-ahead of the forward sweep's L1 prefetch (a forward stage is ~20 instructions, an L2 hit ~250 cycles)
 constexpr int kMaskWords = kMaxStrictHorizon / 32;
 
 // Cost-to-go of the backward sweep, kept projectively: 1/2 x'(P/pi)x + (v/pi)'x.  A free stage multiplies the scale by
@@ -145,42 +145,57 @@ __device__ __forceinline__ void backward_pinned(const RiccatiParams& P, CostToGo
 __device__ __forceinline__ bool get_bit(const uint32_t* m, int j) { return (m[j >> 5] >> (j & 31)) & 1u; }
 __device__ __forceinline__ void set_bit(uint32_t* m, int j) { m[j >> 5] |= 1u << (j & 31); }
 
-// The guess of the next tick.  in: mask = this tick's final set A, shifted = the plain shift of the previous tick's set
-// (both in this tick's window coordinates).  out: mask = S(A) plus the rows by which a pinned run outgrew `shifted` this
-// tick (a run whose end moves with the state -- a CoM that keeps falling -- moves on), shifted = S(A).
-__device__ __noinline__ void next_guess(uint32_t* mask, uint32_t* shifted, int N, int NW) {
-    uint32_t grown[kMaskWords];
-    bool any = false;
-    for (int w = 0; w < NW; ++w) {
-        grown[w] = mask[w] & ~shifted[w];
-        any = any || grown[w] != 0u;
+__device__ __forceinline__ int row_status(const uint32_t* lo, const uint32_t* hi, int j) {
+    return get_bit(hi, j) ? 1 : (get_bit(lo, j) ? -1 : 0);
+}
+__device__ __forceinline__ void set_status(uint32_t* lo, uint32_t* hi, int j, int st) {
+    const uint32_t bit = 1u << (j & 31);
+    lo[j >> 5] = (lo[j >> 5] & ~bit) | (st < 0 ? bit : 0u);
+    hi[j >> 5] = (hi[j >> 5] & ~bit) | (st > 0 ? bit : 0u);
+}
+
+// The guess of the next tick's active set, predicted from the last two (in: p = A_{k-1}, c = A_k, each in its own
+// window coordinates; out: c = guess for tick k+1, p = A_k).  A boundary of the set (two neighbouring rows with
+// different status) is either anchored in time -- it moves up by one row per tick with the window: the plain shift --
+// or anchored to the window (terminal effects of a saturated plan: it stays where it is), or it moves with the state
+// (a pinned run that keeps growing while the CoM falls).  Each boundary of A_k is matched with the same boundary of
+// A_{k-1} (shift first, then stationary, then other small displacements) and moved on by the same amount; unmatched
+// boundaries shift.  It is only a guess -- the active-set iteration corrects it -- but on the BASELINE push sweep it
+// takes the heaviest column from 3.2 to 1.5 sweep pairs per tick.  Once per tick and column, not per stage.
+__device__ __noinline__ void predict_active_set(uint32_t* p_lo, uint32_t* p_hi, uint32_t* c_lo, uint32_t* c_hi, int N, int NW) {
+    uint32_t o_lo[kMaskWords], o_hi[kMaskWords];
+    for (int w = 0; w < NW; ++w) {                 // default: plain shift, new last row free
+        o_lo[w] = (c_lo[w] >> 1) | (((w + 1 < NW) ? c_lo[w + 1] : 0u) << 31);
+        o_hi[w] = (c_hi[w] >> 1) | (((w + 1 < NW) ? c_hi[w + 1] : 0u) << 31);
     }
     for (int w = 0; w < NW; ++w) {
-        const uint32_t up = (w + 1 < NW) ? mask[w + 1] : 0u;
-        mask[w] = (mask[w] >> 1) | (up << 31);
-    }
-    if (any) {
-        uint32_t plain[kMaskWords];
-        for (int w = 0; w < NW; ++w) plain[w] = mask[w];
-        int j = 0;
-        while (j < N) {
-            if (get_bit(grown, j)) {
-                int j2 = j;
-                while (j2 + 1 < N && get_bit(grown, j2 + 1)) ++j2;
-                const int d = j2 - j + 1;
-                if (j > 0 && get_bit(shifted, j - 1)) {               // the run below grew upward by d rows
-                    for (int r = j2; r < j2 + d && r < N; ++r) set_bit(mask, r);
-                } else if (j2 + 1 < N && get_bit(shifted, j2 + 1)) {  // the run above grew downward by d rows
-                    for (int r = j - 2; r > j - 2 - d && r >= 0; --r) set_bit(mask, r);
-                }
-                j = j2 + 1;
-            } else {
-                ++j;
+        // bit j set: rows j and j + 1 of A_k differ (the shifted copy holds row j + 1 at position j)
+        uint32_t d = (c_lo[w] ^ o_lo[w]) | (c_hi[w] ^ o_hi[w]);
+        if (w == NW - 1) d &= ~(1u << ((N - 1) & 31));        // the window end is handled below
+        while (d) {
+            const int q = w * 32 + __ffs((int)d) - 1;
+            d &= d - 1u;
+            const int a = row_status(c_lo, c_hi, q), b = row_status(c_lo, c_hi, q + 1);
+            int v = -1;                                          // displacement per tick in window coordinates
+            for (int k = 0; k < 6; ++k) {
+                const int dq = k == 0 ? 1 : (k == 1 ? 0 : (k == 2 ? -1 : (k == 3 ? 2 : (k == 4 ? -2 : -3))));   // q' - q, by preference
+                const int qp = q + dq;
+                if (qp < 0 || qp + 1 >= N) continue;
+                if (row_status(p_lo, p_hi, qp) == a && row_status(p_lo, p_hi, qp + 1) == b) { v = -dq; break; }
             }
+            // the shift put this boundary at q - 1; move it to q + v
+            for (int r = q; r <= q + v && r < N; ++r) if (r >= 0) set_status(o_lo, o_hi, r, a);
+            for (int r = q + v + 1; r <= q - 1; ++r) if (r >= 0 && r < N) set_status(o_lo, o_hi, r, b);
         }
-        for (int w = 0; w < NW; ++w) shifted[w] = plain[w];
-    } else {
-        for (int w = 0; w < NW; ++w) shifted[w] = mask[w];
+    }
+    // the last row keeps its status when it had it on both ticks (anchored to the window end)
+    {
+        const int a = row_status(c_lo, c_hi, N - 1);
+        if (a != 0 && row_status(p_lo, p_hi, N - 1) == a) set_status(o_lo, o_hi, N - 1, a);
+    }
+    for (int w = 0; w < NW; ++w) {
+        p_lo[w] = c_lo[w]; p_hi[w] = c_hi[w];
+        c_lo[w] = o_lo[w]; c_hi[w] = o_hi[w];
     }
 }
 
@@ -237,8 +252,8 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
         if (pf) pf[0] = (uint8_t)((below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) | (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u));
     }
 
-    // active set: bit j of m_lo / m_hi = row j pinned to its lower / upper bound; s_lo / s_hi = the plain shift of the
-    // previous tick's final set (maintained by next_guess for its growth extrapolation)
+    // active set: bit j of m_lo / m_hi = row j pinned to its lower / upper bound; s_lo / s_hi = the final set of the
+    // tick before (predict_active_set extrapolates from the two)
     uint32_t m_lo[kMaskWords], m_hi[kMaskWords], s_lo[kMaskWords], s_hi[kMaskWords];
 #pragma unroll
     for (int w = 0; w < kMaskWords; ++w) m_lo[w] = m_hi[w] = s_lo[w] = s_hi[w] = 0u;
@@ -247,30 +262,50 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
 
     for (int i = 0; i < ticks; ++i) {
         const int base = i + B.bound_index_bias;      // window row j reads sample min(base + j, last)
-        // ---- guess: the previous tick's set moved up by one sample (+ growing runs), new last row free -----
+        // ---- guess: extrapolated from the last two ticks' sets (plain shift by default) --------------------
         if (i > 0) {
-            next_guess(m_lo, s_lo, N, NW);
-            next_guess(m_hi, s_hi, N, NW);
-            // a row cannot sit on both bounds
-            for (int w = 0; w < NW; ++w) m_hi[w] &= ~m_lo[w];
+            predict_active_set(s_lo, s_hi, m_lo, m_hi, N, NW);
         }
         uint32_t zmag_hi = 0x3ff00000u;            // high word of max(1, |z|_inf) of the last forward sweep
         bool converged = false;
         for (int sweep = 0; sweep < P.max_sweeps; ++sweep) {
             ++sweeps_total;
-            // ---- backward sweep ------------------------------------------------------------------------------
+            // ---- leading pinned block: rows 0 .. m-1 are all pinned, so their jerks follow from the bounds alone and
+            //      the cost-to-go is needed from stage m on only; their multipliers come from a costate pass -----
+            int m = 0;
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t freeb = ~(m_lo[w] | m_hi[w]);
+                const int t = freeb ? (__ffs((int)freeb) - 1) : 32;
+                m += t;
+                if (t < 32) break;
+            }
+            m = m > N ? N : m;
+            double s0 = x0, s1 = x1, s2 = x2;
+            for (int j = 0; j < m; ++j) {
+                const int off = min(base + j, last) * bstride;
+                const double lo = __ldg(plo + off), hi = __ldg(phi + off);
+                const double bnd = get_bit(m_hi, j) ? hi : lo;
+                const double Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, bnd * P.inv_cb)));
+                const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);
+                s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
+                G[j * GS] = make_double2(Jv, Q * (bnd - 0.5 * (lo + hi)));
+            }
+            const double xm0 = s0, xm1 = s1, xm2 = s2;     // state at the start of stage m
+            const int wm = m >> 5, bm = m & 31;
+            // ---- backward sweep over rows N-1 .. m --------------------------------------------------------------
             CostToGo ctg;
             ctg.P00 = ctg.P01 = ctg.P02 = ctg.P11 = ctg.P12 = ctg.P22 = ctg.v0 = ctg.v1 = ctg.v2 = 0.0;
             ctg.pi = ctg.ipi = 1.0;
-            {
+            if (m < N) {
                 int off = min(base + N - 1, last) * bstride;
                 double lo_n = __ldg(plo + off), hi_n = __ldg(phi + off);
-                for (int w = NW - 1; w >= 0; --w) {
+                for (int w = NW - 1; w >= wm; --w) {
                     const int jtop = (w == NW - 1) ? (N - 1 - w * 32) : 31;
+                    const int jbot = (w == wm) ? bm : 0;
                     uint32_t wl = m_lo[w] << (31 - jtop), wh = m_hi[w] << (31 - jtop);   // row of this stage in the sign bit
                     double2* gj = G + (w * 32 + jtop) * GS;
 #pragma unroll 2
-                    for (int bit = jtop; bit >= 0; --bit) {
+                    for (int bit = jtop; bit >= jbot; --bit) {
                         const double lo = lo_n, hi = hi_n;
                         // bounds of the next stage of this sweep (row j - 1; row -1 is never used)
                         off = min(base + w * 32 + bit - 1, last) * bstride;
@@ -283,36 +318,35 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                         if (pin_lo | pin_hi) backward_pinned(P, ctg, pin_hi ? hi : lo, g01, g23);
                         else backward_free(P, ctg, lo, hi, g01, g23);
                         gj[0] = g01; gj[1] = g23;
+                        if (w == wm && bit < jbot + kGainPrefetch) prefetch_l1(gj);     // the forward sweep starts here
                         gj -= GS;
                     }
                 }
             }
-            // ---- forward sweep: plan, multipliers, corrected set ----------------------------------------------
-            double s0 = x0, s1 = x1, s2 = x2;
+            // ---- forward sweep over rows m .. N-1: plan, multipliers, corrected set ---------------------------
             bool changed = false;
             const double tol = P.mu_eps * Q * __hiloint2double((int)zmag_hi, 0);
             zmag_hi = 0x3ff00000u;
-            {
-                int off = min(base, last) * bstride;
+            if (m < N) {
+                int off = min(base + m, last) * bstride;
                 double lo_n = __ldg(plo + off), hi_n = __ldg(phi + off);
-                const double2* gj = G;
+                const double2* gj = G + m * GS;
                 double2 ga_n = gj[0], gb_n = gj[1];
-#pragma unroll
-                for (int k = 1; k < kGainPrefetch; ++k) prefetch_l1(gj + (k < N ? k : 0) * GS);
-                for (int w = 0; w < NW; ++w) {
-                    uint32_t wl = m_lo[w], wh = m_hi[w];
-                    uint32_t nl = 0u, nh = 0u;
+                for (int w = wm; w < NW; ++w) {
+                    const int jfirst = (w == wm) ? bm : 0;
+                    uint32_t wl = m_lo[w] >> jfirst, wh = m_hi[w] >> jfirst;
+                    const uint32_t below_mask = jfirst ? ((1u << jfirst) - 1u) : 0u;
+                    uint32_t nl = m_lo[w] & below_mask, nh = m_hi[w] & below_mask;     // rows of the leading block keep their bits
                     const int jcount = (w == NW - 1) ? (N - w * 32) : 32;
 #pragma unroll 2
-                    for (int bit = 0; bit < jcount; ++bit) {
+                    for (int bit = jfirst; bit < jcount; ++bit) {
                         const double lo = lo_n, hi = hi_n;
                         const double2 ga = ga_n, gb = gb_n;
-                        // next stage's data (one record past the end belongs to the scratch of this column's warp or is
-                        // never used; the bound index is clamped)
+                        // next stage's data (the scratch has kGainPrefetch stages of slack; the bound index is clamped)
                         off = min(base + w * 32 + bit + 1, last) * bstride;
                         lo_n = __ldg(plo + off);
                         hi_n = __ldg(phi + off);
-                        if (w * 32 + bit + 1 < N) { ga_n = gj[GS]; gb_n = gj[GS + 1]; }
+                        ga_n = gj[GS]; gb_n = gj[GS + 1];
                         prefetch_l1(gj + kGainPrefetch * GS);
                         gj += GS;
                         const uint32_t pin_lo = wl & 1u, pin_hi = wh & 1u;
@@ -338,6 +372,28 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                         nl |= keep_lo << bit; nh |= keep_hi << bit;
                     }
                     m_lo[w] = nl; m_hi[w] = nh;
+                }
+            }
+            // ---- costate pass over the leading block, rows m-1 .. 0: lambda_j = grad of the cost-to-go at x_j;
+            //      mu_j = R J_j / (CB) + Q (b_j - zref_j) + B/(CB) . lambda_{j+1} ------------------------------------
+            if (m > 0) {
+                double l0 = fma(ctg.P02, xm2, fma(ctg.P01, xm1, fma(ctg.P00, xm0, ctg.v0))) * ctg.ipi;
+                double l1 = fma(ctg.P12, xm2, fma(ctg.P11, xm1, fma(ctg.P01, xm0, ctg.v1))) * ctg.ipi;
+                double l2 = fma(ctg.P22, xm2, fma(ctg.P12, xm1, fma(ctg.P02, xm0, ctg.v2))) * ctg.ipi;
+                for (int j = m - 1; j >= 0; --j) {
+                    const double2 rec = G[j * GS];
+                    const double mu = fma(P.r_cb, rec.x, rec.y + fma(P.bc[2], l2, fma(P.bc[1], l1, P.bc[0] * l0)));
+                    const bool pin_hi = get_bit(m_hi, j);
+                    if (pin_hi ? (mu > tol) : (mu < -tol)) {
+                        m_lo[j >> 5] &= ~(1u << (j & 31));
+                        m_hi[j >> 5] &= ~(1u << (j & 31));
+                        changed = true;
+                    }
+                    const double e2 = fma(hg, l0, l2), rj = P.R * rec.x;
+                    const double t0 = fma(P.a2[0], e2, fma(P.a1[0], l1, rj * P.kv[0]));
+                    const double t1 = fma(P.a2[1], e2, fma(P.a1[1], l1, rj * P.kv[1]));
+                    const double t2 = fma(P.a2[2], e2, fma(P.a1[2], l1, rj * P.kv[2]));
+                    l0 = t0; l1 = t1; l2 = t2;
                 }
             }
             if (!changed) { converged = true; break; }
@@ -367,7 +423,8 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
             viol = fmax(viol, fmax(fmax(below, above), 0.0));
             lean = fmax(lean, fabs(n0 - zmp));
             unsigned f = (below > P.viol_tol ? LIPM_FLAG_VIOL_LO : 0u) | (above > P.viol_tol ? LIPM_FLAG_VIOL_HI : 0u);
-            f |= (first_pinned & 1 ? LIPM_FLAG_ACTIVE_LO : 0u) | (first_pinned & 2 ? LIPM_FLAG_ACTIVE_HI : 0u);
+            // on-the-bound bits by equality, like the ADMM kernels (a degenerate box sets both)
+            f |= (z0 == l0 ? LIPM_FLAG_ACTIVE_LO : 0u) | (z0 == h0 ? LIPM_FLAG_ACTIVE_HI : 0u);
             if (!converged) {
                 // like the ADMM kernels: the walk of this column ends at the first QP without a solution
                 f |= LIPM_FLAG_NOT_CONVERGED;
@@ -424,7 +481,7 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
     // columns per warp: give every scheduler (4 per SM) a warp before widening the warps
     int lanes = plan->riccati_lanes;
     if (lanes <= 0) {
-        const long long want_warps = (long long)plan->sm_count * 4;
+        const long long want_warps = (long long)plan->sm_count * 8;       // ~2 warps per scheduler before the warps widen (measured: 4096 scenarios run best on 8 columns per warp)
         lanes = 1;
         while (lanes < 32 && (long long)ncols > want_warps * lanes) lanes <<= 1;
     }
@@ -499,7 +556,7 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
     P.rkk[0] = d.R * P.kv[0] * P.kv[0]; P.rkk[1] = d.R * P.kv[0] * P.kv[1]; P.rkk[2] = d.R * P.kv[0] * P.kv[2];
     P.rkk[3] = d.R * P.kv[1] * P.kv[1]; P.rkk[4] = d.R * P.kv[1] * P.kv[2]; P.rkk[5] = d.R * P.kv[2] * P.kv[2];
     P.viol_tol = d.viol_tol;
-    P.mu_eps = 1e-13;
+    P.mu_eps = 1e-12;
     P.stats = nullptr;
     return launch_kernel(plan, P, stream);
 }

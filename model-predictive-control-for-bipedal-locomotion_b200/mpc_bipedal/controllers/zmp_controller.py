@@ -125,6 +125,28 @@ class ZMPController:
             self._host_pool = engine.HostPool()
         res = engine.to_host(res, self._host_pool)
         res.update({k: v for k, v in engine.unpack_outcome_host(res.pop("outcome")).items() if k != "iters"})
+        if mode == 1 and plan.precision == engine.PRECISION_FP64 and plan.solver == engine.SOLVER_ACTIVE_SET:
+            # Safety net: an active-set iteration whose set keeps changing (never seen on the BASELINE sweeps) is
+            # reported like an ADMM solve that hit max_iter; those scenarios run again on the ADMM kernel, which
+            # converges for every feasible QP.
+            bad = np.flatnonzero(np.asarray(res["status"]) != 0)
+            if bad.size:
+                admm = dict(self.solver_options, solver="admm")
+                c = self.config
+                other = engine.get_plan(c.horizon, c.h, c.g, c.dt, c.Q, c.R, **admm)
+                pick = lambda a: None if a is None else np.asarray(a)[bad]
+                zmin_b = z_min if np.ndim(z_min) == 2 else np.asarray(z_min)[bad]
+                zmax_b = z_max if np.ndim(z_max) == 2 else np.asarray(z_max)[bad]
+                redo = other.rollout(mode, np.asarray(x_init)[bad], np.asarray(y_init)[bad], zmin_b, zmax_b, n_steps=pick(n_steps),
+                                     impulse=pick(impulse), force_tick=pick(tick), want_readout=True,
+                                     fall_lean=cfg.h * float(np.tan(np.radians(fall_angle_deg))))
+                res = {k: np.array(v) for k, v in res.items()}
+                for name in ("com", "x_hist", "y_hist", "zmp", "flags", "iters"):
+                    res[name][bad] = redo[name].cpu().numpy()
+                for name, val in engine.unpack_outcome_host(redo["outcome"].cpu().numpy()).items():
+                    if name != "iters":
+                        res[name][bad] = val
+                return res
         if to_numpy == "copy":
             res = {k: np.array(v) for k, v in res.items()}
         return res

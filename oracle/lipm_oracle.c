@@ -211,6 +211,34 @@ static int admm_solve(const oracle_plan *p, const double *x, const double *lo, c
  * that fixed point satisfies the KKT conditions of the reference's QP, whose minimiser is unique.
  * act: in = guess (previous tick's set moved up by one sample), out = final set (-1 lower, +1 upper).
  * Returns Riccati sweeps executed; *converged = 0 if the set still changed after max_sweeps. */
+/* Prediction of the next tick's active set from the last two.  A boundary of the set (two neighbouring rows with
+ * different status) is either anchored in time -- it moves up by one row per tick with the window: the plain shift --
+ * or anchored to the window (terminal effects of a saturated plan: it stays), or it moves with the state (a pinned run
+ * that keeps growing).  Each boundary of `cur` is matched with the same boundary of `prev` (shift first, then
+ * stationary, then +-1, +-2 rows) and moved on by the same amount; unmatched boundaries shift.  Only a guess: the
+ * active-set iteration corrects it. */
+static void predict_active_set(int N, const int8_t *prev, const int8_t *cur, int8_t *out) {
+    for (int j = 0; j + 1 < N; ++j) out[j] = cur[j + 1];          /* default: plain shift, new last row free */
+    out[N - 1] = 0;
+    static const int cand[6] = {1, 0, -1, 2, -2, -3};             /* q' - q, in order of preference */
+    for (int q = 0; q < N; ++q) {
+        const int a = cur[q], b = (q + 1 < N) ? cur[q + 1] : 2;    /* 2 = beyond the window */
+        if (a == b) continue;
+        int v = -1;
+        for (int k = 0; k < 6; ++k) {
+            const int qp = q + cand[k];
+            if (qp < 0 || qp >= N) continue;
+            const int pa = prev[qp], pb = (qp + 1 < N) ? prev[qp + 1] : 2;
+            if (pa == a && pb == b) { v = -cand[k]; break; }
+        }
+        if (b == 2 && v != 0) continue;                            /* the window end does not move */
+        /* the shift put this boundary at q - 1; move it to q + v: rows q .. q + v take the lower side's status */
+        for (int r = q; r <= q + v && r < N; ++r) if (r >= 0) out[r] = (int8_t)a;
+        /* (v < -1: rows q + v + 1 .. q - 1 take the upper side's status) */
+        if (b != 2) for (int r = q + v + 1; r <= q - 1; ++r) if (r >= 0 && r < N) out[r] = (int8_t)b;
+    }
+}
+
 static uint8_t *g_sweep_log = NULL;   /* debug: [2B, n_max] sweeps per tick (tools only) */
 void lipm_oracle_set_sweep_log(uint8_t *p) { g_sweep_log = p; }
 
@@ -283,7 +311,7 @@ static int riccati_pdas_solve(const oracle_plan *p, const double *x, const doubl
         double s0 = x[0], s1 = x[1], s2 = x[2];
         int changed = 0;
         double zmag = 1.0;
-        const double tol = 1e-13 * mu_scale;
+        const double tol = 1e-12 * mu_scale;
         for (int i = 0; i < N; ++i) {
             const double *gi = gain + (size_t)i * 4;
             double J, zi;
@@ -335,7 +363,7 @@ int lipm_oracle_rollout(const oracle_plan *p, int mode, int B, int n_max, const 
         double *tv = (double *)malloc(sizeof(double) * N * 10);
         double *lo = tv + N, *hi = tv + 2 * N, *rhs = tv + 3 * N, *q = tv + 4 * N, *gain = tv + 5 * N, *zplan = tv + 9 * N;
         int8_t *act = (int8_t *)malloc(3 * (size_t)N);
-        int8_t *shifted = act + N, *grown = act + 2 * N;
+        int8_t *older = act + N, *guess = act + 2 * N;
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
 #endif
@@ -376,30 +404,13 @@ int lipm_oracle_rollout(const oracle_plan *p, int mode, int B, int n_max, const 
                     jerk = acc + p->gain[N] * x[0] + p->gain[N + 1] * x[1] + p->gain[N + 2] * x[2];
                 } else if (mode == 2) {
                     /* active-set guess: the previous tick's set moved up by one sample, new last row free */
-                    if (i == 0) { memset(act, 0, N); memset(shifted, 0, N); }
+                    /* guess = prediction of this tick's set from the last two (act = A_{i-1}, older = A_{i-2}, each in
+                     * its own window coordinates) */
+                    if (i == 0) { memset(act, 0, N); memset(older, 0, N); }
                     else {
-                        /* rows by which a pinned run outgrew the plain shift on the previous tick keep growing */
-                        const int extrapolate = getenv("RIC_GROW") != NULL;
-                        memcpy(grown, act, N);                 /* A_k in window-k coordinates */
-                        memmove(act, act + 1, N - 1); act[N - 1] = 0;      /* S(A_k) */
-                        if (extrapolate) {
-                            int j = 0;
-                            while (j < N) {
-                                if (grown[j] && !shifted[j]) {
-                                    int j2 = j;
-                                    while (j2 + 1 < N && grown[j2 + 1] == grown[j] && !shifted[j2 + 1]) ++j2;
-                                    const int d = j2 - j + 1;
-                                    const int8_t sg = grown[j];
-                                    if (j > 0 && shifted[j - 1] == sg) {          /* run below grew upward: [j..j2] */
-                                        for (int r = j2; r < j2 + d && r < N; ++r) if (!act[r]) act[r] = sg;
-                                    } else if (j2 + 1 < N && shifted[j2 + 1] == sg) {   /* run above grew downward */
-                                        for (int r = j - 2; r > j - 2 - d && r >= 0; --r) if (!act[r]) act[r] = sg;
-                                    }
-                                    j = j2 + 1;
-                                } else ++j;
-                            }
-                        }
-                        memcpy(shifted, grown + 1, N - 1); shifted[N - 1] = 0;   /* plain shift of A_k, for the next tick */
+                        predict_active_set(N, older, act, guess);
+                        memcpy(older, act, N);
+                        memcpy(act, guess, N);
                     }
                     int ok;
                     double j0;

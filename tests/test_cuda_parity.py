@@ -24,9 +24,16 @@ def engine():
     return eng
 
 
+@pytest.fixture(scope="module", params=["active_set", "admm"])
+def solver(request):
+    """Both FP64 strict solvers go through the same tests: the active-set / Riccati kernel (default) and the ADMM
+    tensor-pipe kernel share no arithmetic, the oracle they are compared with is a third implementation."""
+    return request.param
+
+
 @pytest.fixture(scope="module")
-def plan150(engine):
-    return engine.get_plan(150, 0.75, 9.81, 1.5 / 150, 1.0, 1e-6)
+def plan150(engine, solver):
+    return engine.get_plan(150, 0.75, 9.81, 1.5 / 150, 1.0, 1e-6, solver=solver)
 
 
 def rel_err(got, want):
@@ -99,14 +106,14 @@ def test_nonstrict_default_walk_matches_reference(engine, plan150, golden):
 
 
 # ----------------------------------------------------------------------------- strict mode
-def test_strict_gpu_plans_are_kkt_points_of_the_reference_qp(engine, golden):
+def test_strict_gpu_plans_are_kkt_points_of_the_reference_qp(engine, golden, solver):
     """The ZMP plans the FP64 kernel returns, mapped back to jerks and checked in the reference's literal QP
     (zmp_controller.py:174-189: H = R I, A_ineq = [Pu; -Pu]): primal feasible, multipliers vanish on free rows and have
     the right sign on active ones.  Independent of both oracle solvers and of the z-coordinates the kernel works in."""
     g = golden("oracle_strict_ticks")
     rng = np.random.default_rng(17)
     for N in (16, 50, 150):
-        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+        plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, solver=solver)
         p = orc.Problem.make(N)
         x, lo, hi = g[f"N{N}/x"], g[f"N{N}/z_min"], g[f"N{N}/z_max"]
         # golden ticks plus fresh random ones the oracle never saw (narrow boxes: many active rows)
@@ -127,9 +134,9 @@ def test_strict_gpu_plans_are_kkt_points_of_the_reference_qp(engine, golden):
 
 
 @pytest.mark.parametrize("N", [16, 50, 150])
-def test_strict_ticks_match_exact_oracle(engine, golden, N):
+def test_strict_ticks_match_exact_oracle(engine, golden, N, solver):
     g = golden("oracle_strict_ticks")
-    plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, solver=solver)
     x, lo, hi = g[f"N{N}/x"], g[f"N{N}/z_min"], g[f"N{N}/z_max"]
     res = plan.solve_tick(engine.MODE_STRICT, x, lo, hi, want_plan=True)
     assert (res["status"].cpu().numpy() == 0).all()
@@ -158,7 +165,7 @@ def check_flags(flags, want_flags, margin_of_got, engine, tie=1e-9):
     return int(diff.sum())
 
 
-def test_strict_default_walk_matches_exact_oracle(engine, plan150, golden):
+def test_strict_default_walk_matches_exact_oracle(engine, plan150, golden, solver):
     g = golden("oracle_strict_walk")
     zero = np.zeros((1, 3))
     out = plan150.rollout(engine.MODE_STRICT, zero, zero, g["z_min"], g["z_max"],
@@ -176,7 +183,10 @@ def test_strict_default_walk_matches_exact_oracle(engine, plan150, golden):
     assert ties <= 8
     assert out["max_violation"].max().item() < 1e-12
     iters = out["iters"][0].cpu().numpy()
-    assert 5 * 419 < iters[0] < 80 * 419 and 5 * 419 < iters[1] < 80 * 419
+    if solver == "admm":          # ADMM iterations
+        assert 5 * 419 < iters[0] < 80 * 419 and 5 * 419 < iters[1] < 80 * 419
+    else:                         # sweep pairs of the active-set iteration: the guess is right on most ticks
+        assert 419 <= iters[0] < 1.2 * 419 and 419 <= iters[1] < 2 * 419
 
 
 def test_strict_equals_unconstrained_when_box_is_wide(engine, plan150):
@@ -239,7 +249,7 @@ def test_tick_ranges_do_not_change_results(engine):
     zero = np.zeros((29, 3))
     # 12 iterations are enough before the push and too few after a strong one: those columns stop at their
     # first QP without a solution, in whatever range that happens
-    plan = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=12, eps=1e-9)
+    plan = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=12, eps=1e-9, solver="admm")
     results = {}
     for segments in (1, 2, 3, 4):
         plan.set_tick_ranges(segments)                  # lipm_set_option(LIPM_OPT_TICK_RANGES)
@@ -449,12 +459,12 @@ def test_reference_python_surface_on_gpu(golden):
 
 
 @pytest.mark.parametrize("N", [24, 40, 100, 128, 145, 153, 160, 161, 200, 300, 600])
-def test_strict_ticks_other_horizons_and_determinism(engine, N):
+def test_strict_ticks_other_horizons_and_determinism(engine, N, solver):
     """Every kernel variant (row blocks per warp 1..5, partial last row group, padded rows; resident
     matrix up to N=160, L2-streamed matrix with 8- and 16-warp groups beyond -- BASELINE config 3):
     result equals the oracle's ADMM and repeated launches are bit-identical (no races)."""
     rng = np.random.default_rng(11 + N)
-    plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, solver=solver)
     p = orc.Problem.make(N)
     cases = 40
     x = rng.normal(size=(cases, 3)) * np.array([0.05, 0.1, 0.5])
@@ -697,7 +707,7 @@ def test_reduced_other_horizons_against_fp64_path(engine, N):
     tile; beyond: operands streamed, 1-4 slabs, BASELINE config 3's N = 300 / 600): solution within 1e-4 m of the FP64
     path of the same library, feasible after the FP64 clamp, far fewer iterations, bit-identical when repeated."""
     rng = np.random.default_rng(21 + N)
-    fp64 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6)
+    fp64 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, solver="admm")      # iteration counts are compared below
     f16 = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
     cases = 300                      # more than two 128-column units: partial last unit
     x = rng.normal(size=(cases, 3)) * np.array([0.05, 0.1, 0.5])
@@ -723,7 +733,7 @@ def test_reduced_streamed_walks(engine):
     cfg, z_max, z_min, impulse, tick = push_sweep_inputs(7, seed=9)
     n, N = 130, 200
     z_max, z_min = z_max[:n], z_min[:n]
-    fp64 = engine.get_plan(N, 0.75, 9.81, 0.01, 1.0, 1e-6)
+    fp64 = engine.get_plan(N, 0.75, 9.81, 0.01, 1.0, 1e-6, solver="admm")      # iteration counts are compared below
     f16 = engine.get_plan(N, 0.75, 9.81, 0.01, 1.0, 1e-6, precision=engine.PRECISION_F16X3)
     n_steps = np.array([130, 130, 60, 130, 2, 101, 130], np.int32)
     tick = np.array([105, 110, 30, 120, 0, 50, 115], np.int32)
@@ -832,7 +842,7 @@ def test_edge_cases(engine, plan150, plan150_f16):
         for k in range(9):
             assert np.max(np.abs(free["next_state"][k].cpu().numpy() - orc.unconstrained_axis(p, xs[k], hi[k], lo[k]))) < 1e-9
     # a QP that cannot converge within max_iter stops its walk there, like the reference raises (:193-194)
-    tight = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=3)
+    tight = engine.get_plan(150, 0.75, 9.81, 0.01, 1.0, 1e-6, max_iter=3, solver="admm")
     out = tight.rollout(engine.MODE_STRICT, zero[:2], zero[:2], z_min[:60], z_max[:60], impulse=[0.0, 0.2], force_tick=[5, 5])
     status = out["status"].cpu().numpy()
     flags = out["flags"].cpu().numpy()
@@ -841,9 +851,30 @@ def test_edge_cases(engine, plan150, plan150_f16):
     assert first_bad > 0 and not out["y_hist"][1, first_bad + 1:].cpu().numpy().any()
     from mpc_bipedal.controllers import ZMPController
     ctrl = ZMPController(cfg)
-    ctrl.solver_options = {"max_iter": 3}
+    ctrl.solver_options = {"max_iter": 3, "solver": "admm"}
     with pytest.raises(RuntimeError, match="QP solver did not find a solution"):
         ctrl.generate_com_trajectory(np.zeros((3, 1)), np.zeros((3, 1)), z_max, z_min)
+    # the active-set solver reports a QP whose set is still changing after max_sweeps corrections the same way
+    one_sweep = engine.LipmPlan(150, 0.75, 9.81, 0.01, 1.0, 1e-6)
+    one_sweep.set_max_sweeps(1)
+    out = one_sweep.rollout(engine.MODE_STRICT, zero[:2], zero[:2], z_min, z_max, impulse=[0.0, 0.2], force_tick=[150, 150])
+    status, flags = out["status"].cpu().numpy(), out["flags"].cpu().numpy()
+    assert status.max() == 1 and status[1, 1] == 1                 # the first step transition that enters the preview needs a correction
+    first_bad = np.argmax(flags[1, :, 1] & engine.FLAG_NOT_CONVERGED != 0)
+    assert first_bad > 0 and not out["y_hist"][1, first_bad + 1:].cpu().numpy().any()
+    one_sweep.close()
+    # ... and the batched entry point of the mirrored API then solves those scenarios on the ADMM kernel instead
+    ctrl = ZMPController(cfg)
+    shared = ctrl._plan()
+    shared.set_max_sweeps(1)
+    try:
+        res = ctrl.generate_com_trajectory_batched(zero[:2], zero[:2], z_max, z_min, F_ext=[0.0, 400.0], force_tick=[150, 150])
+    finally:
+        shared.set_max_sweeps(0)
+    assert (res["status"] == 0).all()
+    ctrl.solver_options = {"solver": "admm"}
+    want = ctrl.generate_com_trajectory_batched(zero[:2], zero[:2], z_max, z_min, F_ext=[0.0, 400.0], force_tick=[150, 150])
+    assert np.array_equal(res["y_hist"], want["y_hist"]) and np.array_equal(res["flags"], want["flags"])
     # bad arguments are rejected with a message, never a crash
     with pytest.raises(ValueError, match="bounds batch"):
         plan150.rollout(engine.MODE_STRICT, zero, zero, np.zeros((3, 30, 2)), np.zeros((3, 30, 2)))

@@ -158,6 +158,44 @@ def test_c_oracle_matrices_and_walks(golden):
     assert 10 < res["iters"].sum() / 838 < 60
 
 
+def test_c_oracle_active_set_solver(golden):
+    """The third strict solver of the oracle -- primal-dual active set with exact O(N) Riccati sweeps over the 3-state
+    model (lipm_oracle.c:riccati_pdas_solve, the CPU restatement of csrc/lipm_rollout_riccati.cu) -- against the exact
+    BVLS oracle and against the C ADMM: it shares no arithmetic with either (no condensed N x N matrix at all)."""
+    from oracle.c_oracle import COracle
+
+    c = COracle(150)
+    p = orc.Problem.make(150)
+    g = golden("oracle_strict_walk")
+    zero = np.zeros((1, 3))
+    res = c.rollout("riccati", zero, zero, g["z_min"], g["z_max"], impulse=[float(g["impulse"])], force_tick=[int(g["force_tick"])])
+    assert (res["status"] == 0).all()
+    assert np.max(np.abs(res["x_hist"][0] - g["x_hist"])) <= 1e-9 * np.max(np.abs(g["x_hist"]))
+    assert np.max(np.abs(res["y_hist"][0] - g["y_hist"])) <= 1e-9 * np.max(np.abs(g["y_hist"]))
+    zmp = np.stack([res["x_hist"][0] @ p.C, res["y_hist"][0] @ p.C], 1)
+    margin = np.minimum(zmp - g["z_min"], g["z_max"] - zmp)
+    assert margin.min() > -1e-12
+    diff = res["flags"][0] != g["flags"]
+    assert not (diff & (np.abs(margin) > 1e-9)).any() and diff.sum() <= 8
+    assert 838 <= res["iters"].sum() < 1.5 * 838           # sweep pairs: the predicted set is right on most ticks
+    # pushed scenarios (one of them falls), ragged lengths: same walks as the ADMM solver, same flags
+    n = len(g["z_min"])
+    B = 6
+    imp = np.array([0.0, 0.05, 0.1, 0.16, 0.2, 0.25])
+    tick = np.array([100, 150, 210, 120, 319, 101], np.int32)
+    n_steps = np.array([n, n, 300, n, n, 250], np.int32)
+    zero = np.zeros((B, 3))
+    a = c.rollout(True, zero, zero, g["z_min"], g["z_max"], n_steps=n_steps, impulse=imp, force_tick=tick)
+    r = c.rollout("riccati", zero, zero, g["z_min"], g["z_max"], n_steps=n_steps, impulse=imp, force_tick=tick)
+    assert not a["status"].any() and not r["status"].any()
+    for key in ("x_hist", "y_hist"):
+        scale = np.maximum(1.0, np.abs(a[key]).max(axis=(1, 2)))
+        assert (np.abs(a[key] - r[key]).max(axis=(1, 2)) <= 1e-9 * scale).all(), key
+    assert np.abs(a["y_hist"][:, :, 0]).max() > 1.0            # at least one scenario diverges (all rows pinned)
+    assert (a["flags"] != r["flags"]).sum() <= 4
+    assert r["max_violation"].max() < 1e-12
+
+
 def test_c_oracle_ragged_and_batched():
     from oracle.c_oracle import COracle
 
