@@ -33,6 +33,7 @@ for _p in (REPO, PACKAGE_DIR):
 METRIC = "QP solves/sec (N=150 LIPM MPC, strict, batched push sweep)"
 UNIT = "solves/s"
 SCENARIOS_PER_GPU = 4096
+RICCATI_FLOPS_PER_STAGE = 184      # one stage of a sweep pair: backward 75 + forward 17 FP64 multiply-adds
 WORKLOAD = "push-sweep-4096 (BASELINE configs[1]): default.json walk n=420, N=150, strict, F_ext~U(0,1000)N, tick~U{100..319}"
 
 
@@ -41,7 +42,7 @@ def bench_config(B, n, N, mode):
     return {"workload": WORKLOAD, "scenarios_per_gpu": B, "horizon": N, "samples_per_walk": n, "mode": mode,
             "solves_per_step_per_gpu": B * 2 * (n - 1),
             "l2": "flushed between timed steps (256 MiB write, untimed)",
-            "admm": {"rho": 2.0, "alpha": 1.75, "eps": 1e-12}}
+            "qp": "box-constrained preview QP of zmp_controller.py:173-191, both axes, solved to its unique minimiser in FP64"}
 
 
 def sweep_inputs(B, seed=0):
@@ -155,7 +156,20 @@ def cpu_baseline(steps=1, warmup=1, budget_s=25.0, batch=SCENARIOS_PER_GPU):
         times.append(dt)
     assert (res["status"] == 0).all()
     solves = walks * 2 * (len(z_min) - 1)
+    # the GPU arm's own algorithm (active set + Riccati sweeps) restated in C on the same cores, same sample: separates
+    # what the algorithm buys from what the hardware buys
+    t0 = time.perf_counter()
+    res_as = oracle.rollout("riccati", zero[:walks], zero[:walks], z_min, z_max, impulse=impulse[:walks],
+                            force_tick=tick[:walks], threads=threads)
+    t_as = time.perf_counter() - t0
+    same_algorithm = {"value": solves / t_as, "unit": UNIT, "cores": threads, "seconds": t_as,
+                      "mean_sweep_pairs_per_solve": float(res_as["iters"].sum()) / solves,
+                      "not_converged": int((res_as["status"] != 0).sum()),
+                      "note": "oracle/lipm_oracle.c mode 2: primal-dual active set with O(N) Riccati sweeps, the CPU "
+                              "restatement of csrc/lipm_rollout_riccati.cu (not the reference's algorithm: the reference "
+                              "calls OSQP, an ADMM method, cold-started on every solve)"}
     return {"value": solves / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
+            "active_set_port": same_algorithm,
             "sample": f"first {walks} of the {batch} scenarios of the push sweep (seed 0), full default.json strict walks "
                       f"({solves} solves) per step; C restatement (oracle/lipm_oracle.c), FP64 ADMM rho=2 alpha=1.75 "
                       f"eps=1e-12, matrices cached, warm start, OpenMP over scenarios on {threads} threads",
@@ -284,8 +298,9 @@ def other_configs(torch, engine, device):
     out = {}
     B = 16384
     for N in (300, 600):
-        for precision, tag in ((engine.PRECISION_FP64, "fp64"), (engine.PRECISION_F16X3, "f16x3")):
-            plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=precision)
+        for precision, tag, solver in ((engine.PRECISION_FP64, "fp64", "active_set"), (engine.PRECISION_FP64, "fp64_admm", "admm"),
+                                       (engine.PRECISION_F16X3, "f16x3", "admm")):
+            plan = engine.get_plan(N, 0.75, 9.81, 1.5 / N, 1.0, 1e-6, precision=precision, solver=solver)
             x, lo, hi = horizon_scaling.tick_inputs(N, B)
             xd, lod, hid = (torch.as_tensor(a).to(device) for a in (x, lo, hi))
             plan.solve_tick(engine.MODE_STRICT, xd, lod, hid)
@@ -298,10 +313,14 @@ def other_configs(torch, engine, device):
             torch.cuda.synchronize(device)
             ms = e0.elapsed_time(e1) / 3
             iters = int(res["iters"].sum().item())
-            out[f"strict_tick_N{N}_{tag}"] = {"batch": B, "ms_per_tick": ms, "solves_per_s": B / (ms * 1e-3),
-                                              "algorithmic_tflops": 2.0 * N * N * iters / (ms * 1e-3) / 1e12,
-                                              "mean_iters_per_solve": iters / B, "start": "cold",
-                                              "not_converged": int((res["status"] != 0).sum().item())}
+            rec = {"batch": B, "ms_per_tick": ms, "solves_per_s": B / (ms * 1e-3), "start": "cold",
+                   "not_converged": int((res["status"] != 0).sum().item())}
+            if tag == "fp64":
+                rec.update({"solver": "active set + Riccati sweeps", "mean_sweep_pairs_per_solve": iters / B})
+            else:
+                rec.update({"solver": "ADMM", "algorithmic_tflops": 2.0 * N * N * iters / (ms * 1e-3) / 1e12,
+                            "mean_iters_per_solve": iters / B})
+            out[f"strict_tick_N{N}_{tag}"] = rec
     out["herdt_randomized_plans_fp64"] = herdt_plans_leg(torch, engine, device)
     return out
 
@@ -424,8 +443,9 @@ def run_ours(args, rank, world, local_rank):
     n = len(z_min)
     solves_per_step = B * 2 * (n - 1)
     precision = engine.PRECISION_F16X3 if args.precision == "f16x3" else engine.PRECISION_FP64
-    plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R, precision=precision)
+    plan = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R, precision=precision, solver=args.solver)
     mode = engine.MODE_STRICT if args.mode == "strict" else engine.MODE_UNCONSTRAINED
+    active_set = precision == engine.PRECISION_FP64 and args.solver == "active_set"
 
     # device-resident inputs for `value`
     d = lambda a, dt: torch.as_tensor(a, dtype=dt).to(device)
@@ -473,6 +493,44 @@ def run_ours(args, rank, world, local_rank):
     stats = plan.stats() if mode == engine.MODE_STRICT else {"group_iterations": 0, "units": 0}
     status_bad = int((out["status"] != 0).sum().item())
     max_viol = out["max_violation"].max().item()
+
+    # ---- the same sweep on the ADMM / FP64 tensor-pipe kernel (the headline solver of round 1): its own roofline and
+    #      the agreement of the two solvers, which share no arithmetic ---------------------------------------------
+    admm_leg = None
+    if mode == engine.MODE_STRICT and active_set and not args.no_reduced:
+        plan_admm = engine.get_plan(cfg.horizon, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R, solver="admm")
+        out_a = {}
+        for _ in range(2):
+            plan_admm.rollout(mode, x0, y0, zmin_d, zmax_d, impulse=imp_d, force_tick=tick_d, out=out_a)
+        torch.cuda.synchronize(device)
+        ev_a = []
+        for _ in range(min(args.steps, 3)):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); plan_admm.rollout(mode, x0, y0, zmin_d, zmax_d, impulse=imp_d, force_tick=tick_d, out=out_a); e1.record()
+            ev_a.append((e0, e1))
+        torch.cuda.synchronize(device)
+        ms_a = float(np.mean([a.elapsed_time(b) for a, b in ev_a]))
+        it_a = out_a["iters"].sum().item()
+        st_a = plan_admm.stats()
+        peak_a = measure_fp64_peak(torch, device)
+        tf_a = 2.0 * cfg.horizon ** 2 * it_a / (ms_a * 1e-3) / 1e12
+        scale = torch.clamp(out_a["y_hist"].abs().amax(dim=(1, 2)), min=1.0)
+        dxy = torch.maximum((out["x_hist"] - out_a["x_hist"]).abs().amax(dim=(1, 2)), (out["y_hist"] - out_a["y_hist"]).abs().amax(dim=(1, 2)))
+        admm_leg = {
+            "value_per_gpu": solves_per_step / (ms_a * 1e-3), "unit": UNIT, "ms_per_step": ms_a,
+            "kernel": "k_strict_rollout (FP64 DMMA.8x8x4 ADMM, rho=2 alpha=1.75 eps=1e-12)",
+            "mean_iters_per_solve": it_a / max(solves_per_step, 1),
+            "useful_column_slot_fraction": it_a / max(8 * st_a["group_iterations"], 1),
+            "roofline": {"bound": "tensor", "achieved": tf_a, "peak": peak_a, "unit": "TFLOP/s", "frac": tf_a / peak_a,
+                         "traffic": ncu_traffic("k_strict_rollout<", B),
+                         "note": "algorithmic K_exec * 2 N^2 flops per solve (SURVEY 8(d)); peak = cuBLAS DGEMM measured in this run"},
+            "agreement_with_headline_solver": {
+                "max_rel_diff_trajectories": float((dxy / scale).max().item()),
+                "median_abs_diff_m": float(dxy.median().item()),
+                "flag_bytes_that_differ": int((out["flags"] != out_a["flags"]).sum().item()),
+                "fall_verdict_mismatches": int((engine.unpack_outcome(out["outcome"])["fell"] != engine.unpack_outcome(out_a["outcome"])["fell"]).sum().item())},
+        }
 
     # ---- the same sweep on the reduced-precision (tcgen05) strict path -------------------------------
     reduced = None
@@ -546,7 +604,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the public API with host buffers ---------------------------------------
     ctrl = ZMPController(cfg)
     ctrl.config.strict = (args.mode == "strict")
-    ctrl.solver_options = {"precision": precision}
+    ctrl.solver_options = {"precision": precision, "solver": args.solver}
     hx0 = np.zeros((B, 3)); hy0 = np.zeros((B, 3))
     e2e_steps = max(1, args.steps)
     for _ in range(3):   # warm-up: the page-locked staging buffers are allocated on the first calls
@@ -600,19 +658,44 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         N = cfg.horizon
         kernel_s = np.mean(step_ms) * 1e-3
-        flops = 2.0 * N * N * iters                      # K_exec * 2 N^2 per solve
         peak = measure_fp64_peak(torch, device)
-        traffic = ncu_traffic("k_strict_rollout_f16" if precision == engine.PRECISION_F16X3 else "k_strict_rollout<", B)
+        if active_set:
+            # one sweep pair = N stages x (backward 75 + forward 17 FP64 multiply-adds) ~ 184 N flops
+            flops = RICCATI_FLOPS_PER_STAGE * N * iters
+            traffic = ncu_traffic("k_riccati_rollout", B)
+            roofline = {"bound": "fp64 pipe (not tensor, not hbm: scalar FP64 recursions, one dependent chain per column; latency "
+                                 "bound at this batch)",
+                        "kernel": "k_riccati_rollout (active set + Riccati sweeps, one thread per column)",
+                        "note": "achieved = sweep pairs x N x %d flops (the active-set algorithm's own work; the ADMM formulation "
+                                "needs ~150x more flops per solve, see admm_tensor_path); peak = cuBLAS DGEMM measured in this run "
+                                "(B200's FP64 FMA pipe and DMMA have the same nominal rate)" % RICCATI_FLOPS_PER_STAGE}
+        else:
+            flops = 2.0 * N * N * iters                      # K_exec * 2 N^2 per solve
+            traffic = ncu_traffic("k_strict_rollout_f16" if precision == engine.PRECISION_F16X3 else "k_strict_rollout<", B)
+            roofline = {"bound": "tensor", "kernel": "k_strict_rollout (FP64 DMMA.8x8x4 ADMM)"}
         achieved = flops / kernel_s / 1e12
+        roofline.update({"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run "
+                                        "(MEASURED_PEAKS.json has no FP64 entry)",
+                         "algorithmic_flops_per_step": flops})
+        if active_set:
+            solver_block = {"name": "active set + Riccati sweeps (LIPM_SOLVER_ACTIVE_SET)",
+                            "mean_sweep_pairs_per_solve": iters / max(solves_per_step, 1),
+                            "mean_sweep_pairs_per_solve_x_axis": out["iters"][:, 0].sum().item() / max(B * (n - 1), 1),
+                            "mean_sweep_pairs_per_solve_y_axis": out["iters"][:, 1].sum().item() / max(B * (n - 1), 1),
+                            "max_sweep_pairs_of_one_column": int(out["iters"].max().item())}
+        else:
+            solver_block = {"name": "ADMM (rho=2, alpha=1.75, eps=1e-12)" if precision == engine.PRECISION_FP64 else "ADMM f16x3 (eps=1e-5)",
+                            "mean_iters_per_solve": iters / max(solves_per_step, 1),
+                            "useful_column_slot_fraction": iters / max(slots * stats["group_iterations"], 1),
+                            "mean_iters_per_solve_x_axis": out["iters"][:, 0].sum().item() / max(B * (n - 1), 1),
+                            "mean_iters_per_solve_y_axis": out["iters"][:, 1].sum().item() / max(B * (n - 1), 1)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(B, n, N, args.mode),
-            "solver": {"mean_iters_per_solve": iters / max(solves_per_step, 1),
-                       "useful_column_slot_fraction": iters / max(slots * stats["group_iterations"], 1),
-                       "mean_iters_per_solve_x_axis": out["iters"][:, 0].sum().item() / max(B * (n - 1), 1),
-                       "mean_iters_per_solve_y_axis": out["iters"][:, 1].sum().item() / max(B * (n - 1), 1)},
+            "solver": solver_block,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "api": "ZMPController.generate_com_trajectory_batched (NumPy in, NumPy out)",
                     "ms_per_call": [round(1e3 * c, 2) for c in e2e_calls],
@@ -621,19 +704,16 @@ def run_ours(args, rank, world, local_rank):
                     "note": "value = mean over the calls (wall clock, NumPy in / NumPy out, all histories copied back)"},
             # per timed step: k_tick_span + k_order_keys + k_unit_work + the rollout kernel + k_pack_outcomes (the CUB
             # sort passes between them are library kernels and not counted); unconstrained: preview + rollout + pack
-            "gpu_launches": (5 if mode == engine.MODE_STRICT else 3) * args.steps,
+            "gpu_launches": ((4 if active_set else 5) if mode == engine.MODE_STRICT else 3) * args.steps,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_strict_rollout (FP64 DMMA.8x8x4 ADMM)",
-                         "peak_source": "cuBLAS DGEMM 4096^3 via torch.matmul, best of 5, measured in this run "
-                                        "(MEASURED_PEAKS.json has no FP64 entry)",
-                         "algorithmic_flops_per_step": flops},
+            "roofline": roofline,
             "checks": {"not_converged_columns": status_bad, "max_zmp_violation_m": max_viol},
             "latency": {"p50_step_ms": float(np.median(step_ms)),
                         "p50_tick_ms_amortised": float(np.median(step_ms)) / (n - 1),
                         "single_tick": tick_latency},
         }
+        if admm_leg is not None:
+            line["admm_tensor_path"] = admm_leg
         if reduced is not None:
             line["reduced_precision"] = reduced
         if extras is not None or sweep is not None:
@@ -683,6 +763,8 @@ def main():
     ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-precision leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the one-number summaries of the other BASELINE configs")
     ap.add_argument("--precision", choices=["fp64", "f16x3"], default="fp64")
+    ap.add_argument("--solver", choices=["active_set", "admm"], default="active_set",
+                    help="solver of the FP64 strict path (library default: active_set)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
