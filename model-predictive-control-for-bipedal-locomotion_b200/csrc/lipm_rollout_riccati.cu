@@ -68,7 +68,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ double pow2_from_biased(int e) { return __hiloint2double(e << 20, 0); }
 __device__ __forceinline__ int biased_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
 
-constexpr int kGainPrefetch = 20;  // stages of look-ahead of the forward sweep's L1 prefetch (a forward stage is ~20 instructions, an L2 hit ~250 cycles)
+constexpr int kGainPrefetch = 16;  // stages of look-ahead of the forward sweep's L1 prefetch (a forward stage is ~20 instructions, an L2 hit ~250 cycles)
 constexpr int kMaskWords = kMaxStrictHorizon / 32;
 
 // Cost-to-go of the backward sweep, kept projectively: 1/2 x'(P/pi)x + (v/pi)'x.  A free stage multiplies the scale by
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                 if (t < 32) break;
             }
             m = m > N ? N : m;
+            m &= ~3;                // the sweeps below work in aligned chunks of four stages (a shorter block is only less of a shortcut)
             double s0 = x0, s1 = x1, s2 = x2;
             for (int j = 0; j < m; ++j) {
                 const int off = min(base + j, last) * bstride;
@@ -291,88 +292,125 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                 G[j * GS] = make_double2(Jv, Q * (bnd - 0.5 * (lo + hi)));
             }
             const double xm0 = s0, xm1 = s1, xm2 = s2;     // state at the start of stage m
-            const int wm = m >> 5, bm = m & 31;
+            const int N4 = N & ~3;                          // rows N4 .. N-1: a tail of up to three stages
             // ---- backward sweep over rows N-1 .. m --------------------------------------------------------------
             CostToGo ctg;
             ctg.P00 = ctg.P01 = ctg.P02 = ctg.P11 = ctg.P12 = ctg.P22 = ctg.v0 = ctg.v1 = ctg.v2 = 0.0;
             ctg.pi = ctg.ipi = 1.0;
-            if (m < N) {
-                int off = min(base + N - 1, last) * bstride;
-                double lo_n = __ldg(plo + off), hi_n = __ldg(phi + off);
-                for (int w = NW - 1; w >= wm; --w) {
-                    const int jtop = (w == NW - 1) ? (N - 1 - w * 32) : 31;
-                    const int jbot = (w == wm) ? bm : 0;
-                    uint32_t wl = m_lo[w] << (31 - jtop), wh = m_hi[w] << (31 - jtop);   // row of this stage in the sign bit
-                    double2* gj = G + (w * 32 + jtop) * GS;
-#pragma unroll 2
-                    for (int bit = jtop; bit >= jbot; --bit) {
-                        const double lo = lo_n, hi = hi_n;
-                        // bounds of the next stage of this sweep (row j - 1; row -1 is never used)
-                        off = min(base + w * 32 + bit - 1, last) * bstride;
-                        off = off < 0 ? 0 : off;
-                        lo_n = __ldg(plo + off);
-                        hi_n = __ldg(phi + off);
-                        const bool pin_lo = (int)wl < 0, pin_hi = (int)wh < 0;
-                        wl <<= 1; wh <<= 1;
-                        double2 g01, g23;
-                        if (pin_lo | pin_hi) backward_pinned(P, ctg, pin_hi ? hi : lo, g01, g23);
-                        else backward_free(P, ctg, lo, hi, g01, g23);
-                        gj[0] = g01; gj[1] = g23;
-                        if (w == wm && bit < jbot + kGainPrefetch) prefetch_l1(gj);     // the forward sweep starts here
-                        gj -= GS;
+            for (int j = N - 1; j >= N4 && j >= m; --j) {            // tail
+                const int off = min(base + j, last) * bstride;
+                const double lo = __ldg(plo + off), hi = __ldg(phi + off);
+                const bool pin_lo = get_bit(m_lo, j), pin_hi = get_bit(m_hi, j);
+                double2 g01, g23;
+                if (pin_lo | pin_hi) backward_pinned(P, ctg, pin_hi ? hi : lo, g01, g23);
+                else backward_free(P, ctg, lo, hi, g01, g23);
+                G[j * GS] = g01; G[j * GS + 1] = g23;
+            }
+            if (m < N4) {
+                // chunks of four stages, highest first; the bounds of a chunk are fetched while the chunk before it is computed
+                double blo[4], bhi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int off = min(base + N4 - 4 + k, last) * bstride;
+                    blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                }
+                double2* gj = G + (N4 - 4) * GS;
+                for (int j = N4 - 4; j >= m; j -= 4) {
+                    double clo[4], chi[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { clo[k] = blo[k]; chi[k] = bhi[k]; }
+                    if (j > m) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int off = min(base + j - 4 + k, last) * bstride;
+                            blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                        }
                     }
+                    const uint32_t nib_lo = (m_lo[j >> 5] >> (j & 31)) & 15u, nib_hi = (m_hi[j >> 5] >> (j & 31)) & 15u;
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) {
+                        const bool pin_lo = (nib_lo >> k) & 1u, pin_hi = (nib_hi >> k) & 1u;
+                        double2 g01, g23;
+                        if (pin_lo | pin_hi) backward_pinned(P, ctg, pin_hi ? chi[k] : clo[k], g01, g23);
+                        else backward_free(P, ctg, clo[k], chi[k], g01, g23);
+                        gj[k * GS] = g01; gj[k * GS + 1] = g23;
+                    }
+                    gj -= 4 * GS;
                 }
             }
             // ---- forward sweep over rows m .. N-1: plan, multipliers, corrected set ---------------------------
             bool changed = false;
             const double tol = P.mu_eps * Q * __hiloint2double((int)zmag_hi, 0);
             zmag_hi = 0x3ff00000u;
-            if (m < N) {
-                int off = min(base + m, last) * bstride;
-                double lo_n = __ldg(plo + off), hi_n = __ldg(phi + off);
-                const double2* gj = G + m * GS;
-                double2 ga_n = gj[0], gb_n = gj[1];
-                for (int w = wm; w < NW; ++w) {
-                    const int jfirst = (w == wm) ? bm : 0;
-                    uint32_t wl = m_lo[w] >> jfirst, wh = m_hi[w] >> jfirst;
-                    const uint32_t below_mask = jfirst ? ((1u << jfirst) - 1u) : 0u;
-                    uint32_t nl = m_lo[w] & below_mask, nh = m_hi[w] & below_mask;     // rows of the leading block keep their bits
-                    const int jcount = (w == NW - 1) ? (N - w * 32) : 32;
-#pragma unroll 2
-                    for (int bit = jfirst; bit < jcount; ++bit) {
-                        const double lo = lo_n, hi = hi_n;
-                        const double2 ga = ga_n, gb = gb_n;
-                        // next stage's data (the scratch has kGainPrefetch stages of slack; the bound index is clamped)
-                        off = min(base + w * 32 + bit + 1, last) * bstride;
-                        lo_n = __ldg(plo + off);
-                        hi_n = __ldg(phi + off);
-                        ga_n = gj[GS]; gb_n = gj[GS + 1];
-                        prefetch_l1(gj + kGainPrefetch * GS);
-                        gj += GS;
-                        const uint32_t pin_lo = wl & 1u, pin_hi = wh & 1u;
-                        wl >>= 1; wh >>= 1;
-                        const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);     // A s, independent of the jerk
-                        double zi;
-                        uint32_t keep_lo = pin_lo, keep_hi = pin_hi;
-                        if (pin_lo | pin_hi) {
-                            const double bnd = pin_hi ? hi : lo;
-                            const double Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, bnd * P.inv_cb)));
-                            s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
-                            const double mu = fma(P.r_cb, Jv, fma(Q, bnd - 0.5 * (lo + hi), fma(ga.x, s0, fma(ga.y, s1, fma(gb.x, s2, gb.y)))));
-                            if (pin_hi ? (mu > tol) : (mu < -tol)) { keep_lo = keep_hi = 0u; changed = true; }
-                            zi = bnd;
-                        } else {
-                            const double Jv = fma(ga.x, s0, fma(ga.y, s1, fma(gb.x, s2, gb.y)));
-                            s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
-                            zi = fma(-hg, s2, s0);
-                            if (zi > hi) { keep_hi = 1u; changed = true; }
-                            else if (zi < lo) { keep_lo = 1u; changed = true; }
-                        }
-                        zmag_hi = max(zmag_hi, (uint32_t)__double2hiint(zi) & 0x7fffffffu);
-                        nl |= keep_lo << bit; nh |= keep_hi << bit;
-                    }
-                    m_lo[w] = nl; m_hi[w] = nh;
+            // one stage of the forward sweep (returns the corrected pin bits of the row)
+            auto forward_stage = [&](double lo, double hi, double2 ga, double2 gb, uint32_t pin_lo, uint32_t pin_hi,
+                                     uint32_t& keep_lo, uint32_t& keep_hi) {
+                const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);     // A s, independent of the jerk
+                double zi;
+                keep_lo = pin_lo; keep_hi = pin_hi;
+                if (pin_lo | pin_hi) {
+                    const double bnd = pin_hi ? hi : lo;
+                    const double Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, bnd * P.inv_cb)));
+                    s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
+                    const double mu = fma(P.r_cb, Jv, fma(Q, bnd - 0.5 * (lo + hi), fma(ga.x, s0, fma(ga.y, s1, fma(gb.x, s2, gb.y)))));
+                    if (pin_hi ? (mu > tol) : (mu < -tol)) { keep_lo = keep_hi = 0u; changed = true; }
+                    zi = bnd;
+                } else {
+                    const double Jv = fma(ga.x, s0, fma(ga.y, s1, fma(gb.x, s2, gb.y)));
+                    s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
+                    zi = fma(-hg, s2, s0);
+                    if (zi > hi) { keep_hi = 1u; changed = true; }
+                    else if (zi < lo) { keep_lo = 1u; changed = true; }
                 }
+                zmag_hi = max(zmag_hi, (uint32_t)__double2hiint(zi) & 0x7fffffffu);
+            };
+            if (m < N4) {
+                // chunks of four stages; gains and bounds of a chunk are fetched while the chunk before it is computed
+                // (an L2 hit is ~250 cycles, a forward stage ~60), and prefetched into L1 kGainPrefetch stages ahead
+                const double2* gj = G + m * GS;
+                double2 na[4], nb[4];
+                double blo[4], bhi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    na[k] = gj[k * GS]; nb[k] = gj[k * GS + 1];
+                    const int off = min(base + m + k, last) * bstride;
+                    blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                }
+                for (int j = m; j < N4; j += 4) {
+                    double2 ga[4], gb[4];
+                    double clo[4], chi[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { ga[k] = na[k]; gb[k] = nb[k]; clo[k] = blo[k]; chi[k] = bhi[k]; }
+                    gj += 4 * GS;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {            // next chunk (the scratch has slack past the last stage)
+                        na[k] = gj[k * GS]; nb[k] = gj[k * GS + 1];
+                        const int off = min(base + j + 4 + k, last) * bstride;
+                        blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                    }
+                    prefetch_l1(gj + (kGainPrefetch - 4) * GS);
+                    prefetch_l1(gj + (kGainPrefetch - 2) * GS);
+                    const int w = j >> 5, sh = j & 31;
+                    const uint32_t nib_lo = (m_lo[w] >> sh) & 15u, nib_hi = (m_hi[w] >> sh) & 15u;
+                    uint32_t new_lo = 0u, new_hi = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t kl, kh;
+                        forward_stage(clo[k], chi[k], ga[k], gb[k], (nib_lo >> k) & 1u, (nib_hi >> k) & 1u, kl, kh);
+                        new_lo |= kl << k; new_hi |= kh << k;
+                    }
+                    if ((new_lo ^ nib_lo) | (new_hi ^ nib_hi)) {
+                        m_lo[w] = (m_lo[w] & ~(15u << sh)) | (new_lo << sh);
+                        m_hi[w] = (m_hi[w] & ~(15u << sh)) | (new_hi << sh);
+                    }
+                }
+            }
+            for (int j = (m > N4 ? m : N4); j < N; ++j) {              // tail
+                const int off = min(base + j, last) * bstride;
+                uint32_t kl, kh;
+                forward_stage(__ldg(plo + off), __ldg(phi + off), G[j * GS], G[j * GS + 1], get_bit(m_lo, j) ? 1u : 0u,
+                              get_bit(m_hi, j) ? 1u : 0u, kl, kh);
+                set_status(m_lo, m_hi, j, kh ? 1 : (kl ? -1 : 0));
             }
             // ---- costate pass over the leading block, rows m-1 .. 0: lambda_j = grad of the cost-to-go at x_j;
             //      mu_j = R J_j / (CB) + Q (b_j - zref_j) + B/(CB) . lambda_{j+1} ------------------------------------
@@ -497,7 +535,7 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
     if (cols_per_launch > ncols) cols_per_launch = ((long long)ncols + lanes - 1) / lanes * lanes;
     StreamBuffer scratch;
     // (+ kGainPrefetch stages of slack: the forward sweep looks ahead without range checks)
-    LIPM_CUDA_TRY(scratch.alloc((size_t)cols_per_launch * per_col + (size_t)(kGainPrefetch + 1) * 32 * 32, stream));
+    LIPM_CUDA_TRY(scratch.alloc((size_t)cols_per_launch * per_col + (size_t)(kGainPrefetch + 8) * 32 * 32, stream));
     P.gains = scratch.as<double2>();
     const int warps_per_block = 2;
     for (long long c0 = 0; c0 < ncols; c0 += cols_per_launch) {
