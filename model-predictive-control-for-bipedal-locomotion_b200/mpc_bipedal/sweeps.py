@@ -130,23 +130,38 @@ def run_shard(config: MPCConfig, table: SweepTable, rank: int = 0, world: int = 
     index = torch.empty((total,), dtype=torch.int64, device=device)
     n_all = np.zeros(total, np.int64)
     pos = 0
+    # Reduced precision: one stream per CoM-height bucket -- a launch is as long as its slowest unit, and the other buckets'
+    # launches fill that tail (0.83 -> 0.65 s for 131,072 scenarios).  The FP64 active-set kernel keeps per-stage feedback
+    # data of every resident column in scratch memory; eight buckets in flight push it out of the L2 (measured: 0.90 ->
+    # 1.20 s), so its buckets run one after the other.
+    concurrent = precision == engine.PRECISION_F16X3
+    main = torch.cuda.current_stream(device)
+    streams = []
     for h_idx, idx in shares:
         count = len(idx)
         if count == 0:
             continue
         h = float(table.h_values[h_idx])
         plan = engine.get_plan(config.horizon, h, config.g, config.dt, config.Q, config.R, precision=precision)
-        zero = torch.zeros((count, 3), dtype=torch.float64, device=device)
         variant = table.variant[idx]
         n_steps = lengths[variant]
-        out = plan.rollout(mode, zero, zero, z_min_d, z_max_d, n_steps=n_steps, bounds_index=variant,
-                           impulse=config.dt * table.F_ext[idx] / table.mass[idx],
-                           force_tick=push_ticks(table, idx, lengths, first, last), want_flags=False, want_hist=False,
-                           fall_lean=h * float(np.tan(np.radians(fall_angle_deg))))
-        record[pos:pos + count] = out["outcome"]
-        index[pos:pos + count] = torch.as_tensor(idx).to(device, non_blocking=True)
+        side = torch.cuda.Stream(device) if concurrent else main
+        if concurrent:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            zero = torch.zeros((count, 3), dtype=torch.float64, device=device)
+            out = plan.rollout(mode, zero, zero, z_min_d, z_max_d, n_steps=n_steps, bounds_index=variant,
+                               impulse=config.dt * table.F_ext[idx] / table.mass[idx],
+                               force_tick=push_ticks(table, idx, lengths, first, last), want_flags=False, want_hist=False,
+                               fall_lean=h * float(np.tan(np.radians(fall_angle_deg))))
+            record[pos:pos + count] = out["outcome"]
+            index[pos:pos + count] = torch.as_tensor(idx).to(device, non_blocking=True)
+        streams.append((side, out, zero))
         n_all[pos:pos + count] = n_steps
         pos += count
+    for side, _, _ in streams:
+        if concurrent:
+            main.wait_stream(side)
     status = (record[:, 2] & 0xFFFFFFFF).cpu().numpy()
     solves = int((2 * (n_all - 1))[status == 0].sum())
     return {"record": record, "index": index, "solves": solves, "launched": total}
