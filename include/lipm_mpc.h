@@ -198,6 +198,13 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
 #define LIPM_OPT_STRICT_SOLVER 4   /* plan required; LIPM_SOLVER_* of the FP64 strict mode                        */
 #define LIPM_OPT_RICCATI_LANES 5   /* plan required; columns per warp of the active-set kernel (0 automatic,
                                       else a power of two <= 32); results do not depend on it                    */
+#define LIPM_OPT_RICCATI_SCRATCH 7  /* plan required; where the active-set kernel keeps the feed-forward terms of its
+                                      table stages: 0 automatic, 1 shared memory, 2 global scratch; results do not
+                                      depend on it                                                               */
+#define LIPM_OPT_FEW_PIN_ROWS 8     /* plan required; active-set kernel: sweeps with at most this many pinned rows solve
+                                      the unconstrained problem with the per-plan tables and correct it with the dense
+                                      inverse Hessian (0 = never, the default: in the one-thread-per-column kernel the
+                                      Riccati recursion is faster; up to 16); both give the same optimum           */
 #define LIPM_OPT_MAX_SWEEPS 6      /* plan required; active-set corrections per QP before it is reported as
                                       not converged (0 -> 64)                                                    */
 

@@ -34,7 +34,7 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s, p->d_ric_tab, p->d_ric_aux};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }
@@ -214,6 +214,14 @@ int lipm_set_option(lipm_plan_t* plan, int option, long long value) {
         case LIPM_OPT_RICCATI_LANES:
             if (!plan || value < 0 || value > 32 || (value & (value - 1)) != 0) { set_error("lipm_set_option(RICCATI_LANES): need a plan and 0 or a power of two <= 32"); return LIPM_E_INVALID; }
             plan->riccati_lanes = (int)value;
+            return LIPM_OK;
+        case LIPM_OPT_FEW_PIN_ROWS:
+            if (!plan || value < 0 || value > 16) { set_error("lipm_set_option(FEW_PIN_ROWS): need a plan and a value in [0, 16]"); return LIPM_E_INVALID; }
+            plan->riccati_few_pins = (int)value;
+            return LIPM_OK;
+        case LIPM_OPT_RICCATI_SCRATCH:
+            if (!plan || value < 0 || value > 2) { set_error("lipm_set_option(RICCATI_SCRATCH): need a plan and 0 (automatic), 1 (shared memory) or 2 (global)"); return LIPM_E_INVALID; }
+            plan->riccati_scratch = (int)value;
             return LIPM_OK;
         case LIPM_OPT_MAX_SWEEPS:
             if (!plan || value < 0 || value > 100000) { set_error("lipm_set_option(MAX_SWEEPS): need a plan and a value in [0, 100000]"); return LIPM_E_INVALID; }

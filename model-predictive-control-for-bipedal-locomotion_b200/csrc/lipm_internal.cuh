@@ -124,6 +124,10 @@ struct lipm_plan {
     int solver;           // LIPM_SOLVER_* of the FP64 strict mode (lipm_set_option; 0 = active set + Riccati sweeps)
     int riccati_lanes;    // columns per warp of the active-set kernel (0 = automatic)
     int riccati_max_sweeps;   // active-set corrections per QP (0 -> 64)
+    int riccati_few_pins; // pinned rows up to which a sweep uses table solve + dense correction (0 = never, the default: measured slower in a one-thread-per-column kernel)
+    int riccati_scratch;  // feed-forward terms of the table stages: 0 automatic, 1 shared memory, 2 global scratch
+    double* d_ric_tab;    // [N + 4][16] per-stage tables of the active-set kernel's free tail (build_riccati_tables)
+    double* d_ric_aux;    // [N + 1][12] K_j, P_j of the same stages
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch (copied from the launch's own state)
@@ -133,6 +137,7 @@ namespace lipm {
 
 // plan construction (lipm_plan.cu)
 int build_plan_matrices(lipm_plan* plan);
+int build_riccati_tables(lipm_plan* plan);        // lipm_rollout_riccati.cu
 
 // One "column" = one axis of one scenario.  The rollout kernels receive this flat description.
 struct ColumnBatch {

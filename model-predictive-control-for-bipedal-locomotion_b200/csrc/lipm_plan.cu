@@ -359,6 +359,9 @@ int build_plan_matrices(lipm_plan* plan) {
     LIPM_CUDA_TRY(cudaGetLastError());
     LIPM_CUDA_TRY(cudaDeviceSynchronize());
 
+    rc = build_riccati_tables(plan);
+    if (rc != LIPM_OK) return rc;
+
     int info[4];
     LIPM_CUDA_TRY(cudaMemcpy(info, plan->d_info, sizeof(info), cudaMemcpyDeviceToHost));
     if (info[0] != 0) {

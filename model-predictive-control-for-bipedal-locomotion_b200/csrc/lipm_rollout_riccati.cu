@@ -28,11 +28,22 @@
 // HBM: bounds read through L1 (the window slides by one sample per tick), 24 B of state + flag / com / zmp per
 // solve written once.
 //
+// Free tail from per-plan tables: the quadratic part P_j of the cost-to-go does not depend on the bounds, only on which
+// of the rows j .. N-1 are pinned.  Above the highest pinned row (on most ticks: everywhere, or everywhere past a leading
+// pinned block) it is therefore the same for every column and every tick: P_j, the feedback row K_j, the closed-loop
+// matrix Acl_j = A - B K_j and B / sigma_j are computed once per plan (build_riccati_tables) and staged in shared memory.
+// There a backward stage is only the linear part  v_j = Acl_j'(v_{j+1} - Q zref_j C')  plus the feed-forward
+// -kc_j = -(B / sigma_j) . w  (16 multiply-adds, chain depth 3), a forward stage is  s_{j+1} = Acl_j s_j - B kc_j
+// (12 multiply-adds, chain depth 3) and the box test; the general recursion (~100 multiply-adds per stage pair) runs
+// only from the highest pinned row down to the leading block.
+//
 // Determinism: a column's arithmetic does not depend on its neighbours, so results are bit-identical whatever
 // batch, warp shape or GPU a scenario lands in.
 #include "lipm_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace lipm {
 
@@ -58,8 +69,15 @@ struct RiccatiParams {
     double hg2x, hgsq;      // 2 h/g, (h/g)^2
     double rkk[6];          // R kv_i kv_j (00 01 02 11 12 22)
     double viol_tol, mu_eps;
-    double2* gains;         // [warp][stage][lane] x 2: per-stage feedback data of the backward sweep
-    unsigned long long* stats;   // [0] sweep pairs, [1] columns
+    double2* gains;         // [warp][stage][lane] x 2: per-stage feedback data of the backward sweep (general recursion)
+    double* nkc;            // [warp][stage][lane]: feed-forward -kc of the table stages (nullptr: kept in shared memory)
+    const double* tab;      // [N + 4][16] per-plan stage tables (kTab* below)
+    const double* aux;      // [N + 1][12]: K_j (3), pad, P_j (00 01 02 11 12 22), pad 2
+    const double2* pk;      // bound series repacked as (lo, hi) pairs (k_pack_bounds)
+    const double* hinv;     // [N][N] inverse Hessian in ZMP coordinates (plan->d_hinv, symmetric): few-pin solves
+    int schur_max;          // pinned rows up to which a sweep uses the table solve + dense correction (0: never)
+    int pk_by_column;       // 1: one run of pairs per column of the launch; 0: one per (series, axis)
+    unsigned long long* stats;   // [0] sweep pairs, [1] columns, [2] stages of the general recursion, [3] table stages
 };
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -70,6 +88,9 @@ __device__ __forceinline__ int biased_exponent(double x) { return (__double2hiin
 
 constexpr int kGainPrefetch = 16;  // stages of look-ahead of the forward sweep's L1 prefetch (a forward stage is ~20 instructions, an L2 hit ~250 cycles)
 constexpr int kMaskWords = kMaxStrictHorizon / 32;
+constexpr int kSchurMax = 16;                   // pinned rows a few-pin sweep can take (triangular system in local memory)
+constexpr size_t kMaxAutoSmem = 72 * 1024;       // per block: three blocks of two warps still fit one SM
+constexpr size_t kMaxDynamicSmem = 200 * 1024;
 
 // Cost-to-go of the backward sweep, kept projectively: 1/2 x'(P/pi)x + (v/pi)'x.  A free stage multiplies the scale by
 // its own sigma = pi (R + B'W B) instead of dividing by it, so the reciprocal (needed only for the stored feedback gains)
@@ -143,7 +164,6 @@ __device__ __forceinline__ void backward_pinned(const RiccatiParams& P, CostToGo
 
 // multiword bit helpers of the active-set masks (once per tick, not per stage)
 __device__ __forceinline__ bool get_bit(const uint32_t* m, int j) { return (m[j >> 5] >> (j & 31)) & 1u; }
-__device__ __forceinline__ void set_bit(uint32_t* m, int j) { m[j >> 5] |= 1u << (j & 31); }
 
 __device__ __forceinline__ int row_status(const uint32_t* lo, const uint32_t* hi, int j) {
     return get_bit(hi, j) ? 1 : (get_bit(lo, j) ? -1 : 0);
@@ -199,17 +219,59 @@ __device__ __noinline__ void predict_active_set(uint32_t* p_lo, uint32_t* p_hi, 
     }
 }
 
-// LANES = columns per warp (compile time: record strides become immediates).
-template <int LANES>
+// Bound series repacked per launch as (lo, hi) pairs: one 16-byte load per stage, 32-bit sample index.
+// by_column = 0: one run of `ns` pairs per (series, axis); 1: one run per column of the launch (scenarios that bring
+// their own series: the run of a column follows the processing order).
+__global__ void k_pack_bounds(const RiccatiParams P, double2* __restrict__ out, int runs, int by_column) {
+    const ColumnBatch& B = P.cb;
+    const int ns = B.n_uniform;
+    const long long total = (long long)runs * ns;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long run = e / ns;
+        const int s = (int)(e - run * ns);
+        long long bz;
+        int axis;
+        if (by_column) {
+            const long long c = P.col_begin + run;
+            if (c >= P.col_end) continue;
+            axis = (int)(c / B.B);
+            const int slot = (int)(c - (long long)axis * B.B);
+            bz = B.order ? B.order[slot] : slot;
+        } else {
+            const int naxes = B.bound_axis_offset ? 2 : 1;
+            bz = run / naxes;
+            axis = (int)(run - bz * naxes);
+        }
+        const long long off = bz * B.bound_scn_stride + (long long)axis * B.bound_axis_offset + (long long)s * B.bound_stride;
+        out[e] = make_double2(B.z_min[off], B.z_max[off]);
+    }
+}
+
+// LANES = columns per warp (compile time: record strides become immediates).  SMEM: the per-plan stage tables and the
+// feed-forward terms of the table stages live in shared memory (else: tables through L1, terms in global scratch).
+template <int LANES, bool SMEM>
 __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P) {
+    extern __shared__ double2 dyn_smem[];
     const ColumnBatch& B = P.cb;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int N = P.N;
+    constexpr int KS = 2 * LANES;                 // doubles between consecutive stages in the feed-forward scratch (two warps per block)
+    if (SMEM) {
+        const double2* src = reinterpret_cast<const double2*>(P.tab);
+        const int n2 = (N + 4) * 8;
+        for (int k = threadIdx.x; k < n2; k += blockDim.x) dyn_smem[k] = __ldg(src + k);
+        __syncthreads();
+    }
+    // per-plan stage tables, eight 16-byte words per stage
+    const double2* const tab2 = SMEM ? dyn_smem : reinterpret_cast<const double2*>(P.tab);
+    // feed-forward terms of the table stages: [stage][column of the block]
+    double* const KC = (SMEM ? reinterpret_cast<double*>(dyn_smem + (N + 4) * 8) : P.nkc + (size_t)blockIdx.x * (N + 4) * KS) +
+                       ((threadIdx.x >> 5) * LANES + lane);
     if (lane >= LANES) return;
     const long long cl = (long long)P.col_begin + warp * LANES + lane;
     if (cl >= P.col_end) return;
     const int c = (int)cl;
-    const int N = P.N;
     const int NW = (N + 31) >> 5;
     constexpr int GS = 2 * LANES;                 // double2 elements between consecutive stages of a column
 
@@ -222,8 +284,8 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     int ticks = B.ticks_override > 0 ? B.ticks_override : n - 1;
     if (n < 1 || ticks < 0) ticks = 0;
     const long long bz = B.bounds_index ? B.bounds_index[b] : ((B.bounds_batch == 1) ? 0 : b);
-    const double* __restrict__ plo = B.z_min + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
-    const double* __restrict__ phi = B.z_max + bz * B.bound_scn_stride + axis * B.bound_axis_offset;
+    // (lo, hi) pairs of this column's series (k_pack_bounds)
+    const double2* __restrict__ pb = P.pk + (P.pk_by_column ? (long long)(c - P.col_begin) : bz * (B.bound_axis_offset ? 2 : 1) + axis) * B.n_uniform;
     double* ph = axis ? B.hist[1] : B.hist[0];
     if (ph) ph += (long long)b * B.hist_scn_stride;
     uint8_t* pf = B.flags ? B.flags + ((long long)b * B.n_max) * 2 + axis : nullptr;
@@ -236,14 +298,15 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     const double impulse = push ? B.impulse[b] : 0.0;
     const int ftick = push ? (B.force_tick ? B.force_tick[b] : -1) : -1;
     const int last = n - 1;
-    const int bstride = B.bound_stride;
-    double2* __restrict__ G = P.gains + ((size_t)warp * N * LANES + lane) * 2;    // record j: G[j * GS], G[j * GS + 1]
+    double2* __restrict__ G = P.gains + ((size_t)warp * (N + 4) * LANES + lane) * 2;    // record j: G[j * GS], G[j * GS + 1]
 
     double viol = 0.0, lean = 0.0;
     int sweeps_total = 0, notconv = 0;
+    long long general_stages = 0, table_stages = 0;     // statistics: stages that went through the general recursion / the tables
     if (B.write_initial && ticks > 0) {
         const double zmp = x0 - P.hg * x2;
-        const double below = plo[0] - zmp, above = zmp - phi[0];
+        const double2 b0 = __ldg(pb);
+        const double below = b0.x - zmp, above = zmp - b0.y;
         viol = fmax(fmax(below, above), 0.0);
         lean = fabs(x0 - zmp);
         if (ph) { ph[0] = x0; ph[1] = x1; ph[2] = x2; }
@@ -259,6 +322,7 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     for (int w = 0; w < kMaskWords; ++w) m_lo[w] = m_hi[w] = s_lo[w] = s_hi[w] = 0u;
 
     const double T = P.T, c2 = P.c2, c3 = P.c3, hg = P.hg, Q = P.Q;
+    const int N4 = N & ~3;                          // rows N4 .. N-1: a tail of up to three stages
 
     for (int i = 0; i < ticks; ++i) {
         const int base = i + B.bound_index_bias;      // window row j reads sample min(base + j, last)
@@ -268,6 +332,9 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
         }
         uint32_t zmag_hi = 0x3ff00000u;            // high word of max(1, |z|_inf) of the last forward sweep
         bool converged = false;
+        int jg = 0;                                // first row of the table region in the last sweep
+        bool schur = false;                        // the last sweep was a few-pin sweep (plan in KC, first sample in z_first)
+        double z_first = 0.0;
         for (int sweep = 0; sweep < P.max_sweeps; ++sweep) {
             ++sweeps_total;
             // ---- leading pinned block: rows 0 .. m-1 are all pinned, so their jerks follow from the bounds alone and
@@ -281,10 +348,27 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
             }
             m = m > N ? N : m;
             m &= ~3;                // the sweeps below work in aligned chunks of four stages (a shorter block is only less of a shortcut)
+            // ---- table region: rows jg .. N-1 are free and so is every row after them ------------------------------
+            int jt = -1;            // highest pinned row
+            for (int w = NW - 1; w >= 0; --w) {
+                const uint32_t pinned = m_lo[w] | m_hi[w];
+                if (pinned) { jt = w * 32 + 31 - __clz((int)pinned); break; }
+            }
+            jg = (jt + 4) & ~3;
+            if (jg > N4) jg = N;    // the general recursion takes the unaligned tail too
+            // ---- few pinned rows (typically isolated rows where the plan cuts the corner of a support change): solve
+            //      the unconstrained problem with the tables (rows 0 .. N-1), then correct it with the dense inverse
+            //      Hessian:  z = z_unc - Hinv[:, A] lambda,  Hinv[A, A] lambda = z_unc[A] - b_A   (see few_pin_correction)
+            int na = 0;
+            for (int w = 0; w < NW; ++w) na += __popc(m_lo[w] | m_hi[w]);
+            schur = na > 0 && na <= P.schur_max;
+            if (schur) { m = 0; jg = 0; }
+            const int jhi = jg == N ? N4 : jg;      // the general recursion's aligned chunks cover rows m .. jhi-1
+            general_stages += (jg > m ? jg - m : 0); table_stages += N - jg;
             double s0 = x0, s1 = x1, s2 = x2;
             for (int j = 0; j < m; ++j) {
-                const int off = min(base + j, last) * bstride;
-                const double lo = __ldg(plo + off), hi = __ldg(phi + off);
+                const double2 bd = __ldg(pb + min(base + j, last));
+                const double lo = bd.x, hi = bd.y;
                 const double bnd = get_bit(m_hi, j) ? hi : lo;
                 const double Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, bnd * P.inv_cb)));
                 const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);
@@ -292,38 +376,85 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                 G[j * GS] = make_double2(Jv, Q * (bnd - 0.5 * (lo + hi)));
             }
             const double xm0 = s0, xm1 = s1, xm2 = s2;     // state at the start of stage m
-            const int N4 = N & ~3;                          // rows N4 .. N-1: a tail of up to three stages
-            // ---- backward sweep over rows N-1 .. m --------------------------------------------------------------
+            // ---- backward sweep, table region (rows N-1 .. jg): linear part of the cost-to-go only -----------------
             CostToGo ctg;
             ctg.P00 = ctg.P01 = ctg.P02 = ctg.P11 = ctg.P12 = ctg.P22 = ctg.v0 = ctg.v1 = ctg.v2 = 0.0;
             ctg.pi = ctg.ipi = 1.0;
-            for (int j = N - 1; j >= N4 && j >= m; --j) {            // tail
-                const int off = min(base + j, last) * bstride;
-                const double lo = __ldg(plo + off), hi = __ldg(phi + off);
-                const bool pin_lo = get_bit(m_lo, j), pin_hi = get_bit(m_hi, j);
-                double2 g01, g23;
-                if (pin_lo | pin_hi) backward_pinned(P, ctg, pin_hi ? hi : lo, g01, g23);
-                else backward_free(P, ctg, lo, hi, g01, g23);
-                G[j * GS] = g01; G[j * GS + 1] = g23;
+            if (jg < N) {
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                auto table_backward = [&](int j, double lo, double hi) {
+                    const double2* t = tab2 + j * 8;
+                    const double2 a0 = t[0], a1 = t[1], b0 = t[2], b1 = t[3], e0 = t[4], e1 = t[5], d0 = t[6], d1 = t[7];
+                    const double tq = P.q_half * (lo + hi);       // Q zref
+                    const double n0 = fma(a0.x, v0, fma(a0.y, v1, fma(a1.x, v2, tq * a1.y)));
+                    const double n1 = fma(b0.x, v0, fma(b0.y, v1, fma(b1.x, v2, tq * b1.y)));
+                    const double n2 = fma(e0.x, v0, fma(e0.y, v1, fma(e1.x, v2, tq * e1.y)));
+                    KC[j * KS] = fma(d0.x, v0, fma(d0.y, v1, fma(d1.x, v2, tq * d1.y)));
+                    v0 = n0; v1 = n1; v2 = n2;
+                };
+                for (int j = N - 1; j >= N4; --j) {                      // tail
+                    const double2 bd = __ldg(pb + min(base + j, last));
+                    table_backward(j, bd.x, bd.y);
+                }
+                if (jg < N4) {
+                    double blo[4], bhi[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double2 bd = __ldg(pb + min(base + N4 - 4 + k, last));
+                        blo[k] = bd.x; bhi[k] = bd.y;
+                    }
+                    for (int j = N4 - 4; j >= jg; j -= 4) {
+                        double clo[4], chi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { clo[k] = blo[k]; chi[k] = bhi[k]; }
+                        if (j > jg) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const double2 bd = __ldg(pb + min(base + j - 4 + k, last));
+                                blo[k] = bd.x; bhi[k] = bd.y;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 3; k >= 0; --k) table_backward(j + k, clo[k], chi[k]);
+                    }
+                }
+                if (jg > 0) {       // hand the cost-to-go of stage jg to the general recursion / the costate pass
+                    const double* a = P.aux + jg * 12;
+                    ctg.P00 = __ldg(a + 4); ctg.P01 = __ldg(a + 5); ctg.P02 = __ldg(a + 6);
+                    ctg.P11 = __ldg(a + 7); ctg.P12 = __ldg(a + 8); ctg.P22 = __ldg(a + 9);
+                    ctg.v0 = v0; ctg.v1 = v1; ctg.v2 = v2;
+                }
             }
-            if (m < N4) {
+            // ---- backward sweep, general recursion over rows jg-1 .. m ------------------------------------------------
+            if (jg == N) {
+                for (int j = N - 1; j >= N4 && j >= m; --j) {            // tail
+                    const double2 bd = __ldg(pb + min(base + j, last));
+                    const double lo = bd.x, hi = bd.y;
+                    const bool pin_lo = get_bit(m_lo, j), pin_hi = get_bit(m_hi, j);
+                    double2 g01, g23;
+                    if (pin_lo | pin_hi) backward_pinned(P, ctg, pin_hi ? hi : lo, g01, g23);
+                    else backward_free(P, ctg, lo, hi, g01, g23);
+                    G[j * GS] = g01; G[j * GS + 1] = g23;
+                }
+            }
+            if (m < jhi) {
                 // chunks of four stages, highest first; the bounds of a chunk are fetched while the chunk before it is computed
                 double blo[4], bhi[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int off = min(base + N4 - 4 + k, last) * bstride;
-                    blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                    const double2 bd = __ldg(pb + min(base + jhi - 4 + k, last));
+                    blo[k] = bd.x; bhi[k] = bd.y;
                 }
-                double2* gj = G + (N4 - 4) * GS;
-                for (int j = N4 - 4; j >= m; j -= 4) {
+                double2* gj = G + (jhi - 4) * GS;
+                for (int j = jhi - 4; j >= m; j -= 4) {
                     double clo[4], chi[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) { clo[k] = blo[k]; chi[k] = bhi[k]; }
                     if (j > m) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const int off = min(base + j - 4 + k, last) * bstride;
-                            blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                            const double2 bd = __ldg(pb + min(base + j - 4 + k, last));
+                            blo[k] = bd.x; bhi[k] = bd.y;
                         }
                     }
                     const uint32_t nib_lo = (m_lo[j >> 5] >> (j & 31)) & 15u, nib_hi = (m_hi[j >> 5] >> (j & 31)) & 15u;
@@ -364,7 +495,20 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                 }
                 zmag_hi = max(zmag_hi, (uint32_t)__double2hiint(zi) & 0x7fffffffu);
             };
-            if (m < N4) {
+            // one stage of the table region: s <- Acl_j s - B kc_j, box test (returns 1: below, 2: above, 0: inside)
+            auto table_forward = [&](int j, double lo, double hi, double nk) -> uint32_t {
+                const double2* t = tab2 + j * 8;
+                const double2 a0 = t[0], a1 = t[1], b0 = t[2], b1 = t[3], e0 = t[4], e1 = t[5];
+                const double n0 = fma(a0.x, s0, fma(b0.x, s1, fma(e0.x, s2, c3 * nk)));
+                const double n1 = fma(a0.y, s0, fma(b0.y, s1, fma(e0.y, s2, c2 * nk)));
+                const double n2 = fma(a1.x, s0, fma(b1.x, s1, fma(e1.x, s2, T * nk)));
+                s0 = n0; s1 = n1; s2 = n2;
+                const double zi = fma(-hg, n2, n0);
+                if (schur) { KC[j * KS] = zi; return 0u; }          // unconstrained plan; tested after the correction
+                zmag_hi = max(zmag_hi, (uint32_t)__double2hiint(zi) & 0x7fffffffu);
+                return zi > hi ? 2u : (zi < lo ? 1u : 0u);
+            };
+            if (m < jhi) {
                 // chunks of four stages; gains and bounds of a chunk are fetched while the chunk before it is computed
                 // (an L2 hit is ~250 cycles, a forward stage ~60), and prefetched into L1 kGainPrefetch stages ahead
                 const double2* gj = G + m * GS;
@@ -373,23 +517,25 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     na[k] = gj[k * GS]; nb[k] = gj[k * GS + 1];
-                    const int off = min(base + m + k, last) * bstride;
-                    blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                    const double2 bd = __ldg(pb + min(base + m + k, last));
+                    blo[k] = bd.x; bhi[k] = bd.y;
                 }
-                for (int j = m; j < N4; j += 4) {
+                for (int j = m; j < jhi; j += 4) {
                     double2 ga[4], gb[4];
                     double clo[4], chi[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) { ga[k] = na[k]; gb[k] = nb[k]; clo[k] = blo[k]; chi[k] = bhi[k]; }
                     gj += 4 * GS;
+                    if (j + 4 < jhi) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {            // next chunk (the scratch has slack past the last stage)
-                        na[k] = gj[k * GS]; nb[k] = gj[k * GS + 1];
-                        const int off = min(base + j + 4 + k, last) * bstride;
-                        blo[k] = __ldg(plo + off); bhi[k] = __ldg(phi + off);
+                        for (int k = 0; k < 4; ++k) {
+                            na[k] = gj[k * GS]; nb[k] = gj[k * GS + 1];
+                            const double2 bd = __ldg(pb + min(base + j + 4 + k, last));
+                            blo[k] = bd.x; bhi[k] = bd.y;
+                        }
+                        prefetch_l1(gj + (kGainPrefetch - 4) * GS);
+                        prefetch_l1(gj + (kGainPrefetch - 2) * GS);
                     }
-                    prefetch_l1(gj + (kGainPrefetch - 4) * GS);
-                    prefetch_l1(gj + (kGainPrefetch - 2) * GS);
                     const int w = j >> 5, sh = j & 31;
                     const uint32_t nib_lo = (m_lo[w] >> sh) & 15u, nib_hi = (m_hi[w] >> sh) & 15u;
                     uint32_t new_lo = 0u, new_hi = 0u;
@@ -405,12 +551,145 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                     }
                 }
             }
-            for (int j = (m > N4 ? m : N4); j < N; ++j) {              // tail
-                const int off = min(base + j, last) * bstride;
-                uint32_t kl, kh;
-                forward_stage(__ldg(plo + off), __ldg(phi + off), G[j * GS], G[j * GS + 1], get_bit(m_lo, j) ? 1u : 0u,
-                              get_bit(m_hi, j) ? 1u : 0u, kl, kh);
-                set_status(m_lo, m_hi, j, kh ? 1 : (kl ? -1 : 0));
+            if (jg == N) {
+                for (int j = (m > N4 ? m : N4); j < N; ++j) {              // tail
+                    const double2 bd = __ldg(pb + min(base + j, last));
+                    uint32_t kl, kh;
+                    forward_stage(bd.x, bd.y, G[j * GS], G[j * GS + 1], get_bit(m_lo, j) ? 1u : 0u,
+                                  get_bit(m_hi, j) ? 1u : 0u, kl, kh);
+                    set_status(m_lo, m_hi, j, kh ? 1 : (kl ? -1 : 0));
+                }
+            } else {
+                if (jg < N4) {
+                    double nk[4], blo[4], bhi[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        nk[k] = KC[(jg + k) * KS];
+                        const double2 bd = __ldg(pb + min(base + jg + k, last));
+                        blo[k] = bd.x; bhi[k] = bd.y;
+                    }
+                    for (int j = jg; j < N4; j += 4) {
+                        double ck[4], clo[4], chi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { ck[k] = nk[k]; clo[k] = blo[k]; chi[k] = bhi[k]; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {            // next chunk (the scratch has four stages of slack)
+                            nk[k] = KC[(j + 4 + k) * KS];
+                            const double2 bd = __ldg(pb + min(base + j + 4 + k, last));
+                            blo[k] = bd.x; bhi[k] = bd.y;
+                        }
+                        if (!SMEM) prefetch_l1(KC + (j + kGainPrefetch) * KS);
+                        uint32_t out = 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) out |= table_forward(j + k, clo[k], chi[k], ck[k]) << (2 * k);
+                        if (out) {
+                            changed = true;
+                            const int w = j >> 5, sh = j & 31;
+                            const uint32_t add_lo = (out & 1u) | ((out >> 1) & 2u) | ((out >> 2) & 4u) | ((out >> 3) & 8u);
+                            const uint32_t add_hi = ((out >> 1) & 1u) | ((out >> 2) & 2u) | ((out >> 3) & 4u) | ((out >> 4) & 8u);
+                            m_lo[w] |= add_lo << sh;
+                            m_hi[w] |= add_hi << sh;
+                        }
+                    }
+                }
+                for (int j = N4; j < N; ++j) {                              // tail
+                    const double2 bd = __ldg(pb + min(base + j, last));
+                    const uint32_t r = table_forward(j, bd.x, bd.y, KC[j * KS]);
+                    if (r) { changed = true; set_status(m_lo, m_hi, j, r == 2u ? 1 : -1); }
+                }
+            }
+            // ---- few-pin sweep: dense correction of the unconstrained plan, box test, multipliers --------------------
+            if (schur) {
+                int idx[kSchurMax];
+                double lam[kSchurMax], dinv[kSchurMax], S[kSchurMax * (kSchurMax + 1) / 2];
+                int cnt = 0;
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t bits = m_lo[w] | m_hi[w];
+                    while (bits) {
+                        const int j = w * 32 + __ffs((int)bits) - 1;
+                        bits &= bits - 1u;
+                        const double2 bd = __ldg(pb + min(base + j, last));
+                        idx[cnt] = j;
+                        lam[cnt] = KC[j * KS] - (get_bit(m_hi, j) ? bd.y : bd.x);       // z_unc - b
+                        ++cnt;
+                    }
+                }
+                // S = Hinv[A, A] (packed lower triangle), factorised as L D L' in place
+                for (int k = 0; k < cnt; ++k) {
+                    const double* row = P.hinv + (size_t)idx[k] * N;
+                    for (int l = 0; l <= k; ++l) S[k * (k + 1) / 2 + l] = __ldg(row + idx[l]);
+                }
+                for (int k = 0; k < cnt; ++k) {
+                    double* Lk = S + k * (k + 1) / 2;
+                    for (int l = 0; l < k; ++l) {
+                        const double* Ll = S + l * (l + 1) / 2;
+                        double acc = Lk[l];
+                        for (int q = 0; q < l; ++q) acc = fma(-Lk[q], Ll[q], acc);      // Lk[q] still holds L[k][q] d[q]
+                        Lk[l] = acc;                                                     // = L[k][l] d[l]
+                    }
+                    double d = Lk[k];
+                    for (int l = 0; l < k; ++l) {
+                        const double ld = Lk[l];
+                        const double lv = ld * dinv[l];
+                        d = fma(-ld, lv, d);
+                        Lk[l] = lv;
+                    }
+                    dinv[k] = 1.0 / d;
+                }
+                for (int k = 0; k < cnt; ++k) {                      // L y = r
+                    const double* Lk = S + k * (k + 1) / 2;
+                    double acc = lam[k];
+                    for (int l = 0; l < k; ++l) acc = fma(-Lk[l], lam[l], acc);
+                    lam[k] = acc;
+                }
+                for (int k = 0; k < cnt; ++k) lam[k] *= dinv[k];
+                for (int k = cnt - 1; k >= 0; --k) {                 // L' lambda = y
+                    double acc = lam[k];
+                    for (int l = k + 1; l < cnt; ++l) acc = fma(-S[l * (l + 1) / 2 + k], lam[l], acc);
+                    lam[k] = acc;
+                }
+                // corrected plan, four rows at a time; free rows are tested against the box
+                zmag_hi = 0x3ff00000u;
+                for (int j = 0; j < N; j += 4) {
+                    double z[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) z[k] = KC[min(j + k, N - 1) * KS];
+                    for (int q = 0; q < cnt; ++q) {
+                        const double* row = P.hinv + (size_t)idx[q] * N + j;
+                        const double lq = lam[q];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) z[k] = fma(-lq, __ldg(row + min(k, N - 1 - j)), z[k]);
+                    }
+                    const int w = j >> 5, sh = j & 31;
+                    const uint32_t pinned = ((m_lo[w] | m_hi[w]) >> sh) & 15u;
+                    uint32_t add_lo = 0u, add_hi = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (j + k < N) {
+                            const double2 bd = __ldg(pb + min(base + j + k, last));
+                            if ((pinned >> k) & 1u) {
+                                z[k] = ((m_hi[w] >> (sh + k)) & 1u) ? bd.y : bd.x;
+                            } else {
+                                if (z[k] > bd.y) add_hi |= 1u << k;
+                                else if (z[k] < bd.x) add_lo |= 1u << k;
+                            }
+                            zmag_hi = max(zmag_hi, (uint32_t)__double2hiint(z[k]) & 0x7fffffffu);
+                            KC[(j + k) * KS] = z[k];
+                        }
+                    }
+                    if (j == 0) z_first = z[0];
+                    if (add_lo | add_hi) { changed = true; m_lo[w] |= add_lo << sh; m_hi[w] |= add_hi << sh; }
+                }
+                // multipliers: the gradient on a pinned row is -lambda; a row pinned on the wrong side is released
+                for (int q = 0; q < cnt; ++q) {
+                    const int j = idx[q];
+                    const double mu = -lam[q];
+                    if (get_bit(m_hi, j) ? (mu > tol) : (mu < -tol)) {
+                        m_lo[j >> 5] &= ~(1u << (j & 31));
+                        m_hi[j >> 5] &= ~(1u << (j & 31));
+                        changed = true;
+                    }
+                }
             }
             // ---- costate pass over the leading block, rows m-1 .. 0: lambda_j = grad of the cost-to-go at x_j;
             //      mu_j = R J_j / (CB) + Q (b_j - zref_j) + B/(CB) . lambda_{j+1} ------------------------------------
@@ -439,16 +718,23 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
 
         // ---- apply the first sample: state update, push, outputs ------------------------------------------
         {
-            const int off = min(base, last) * bstride;
-            const double l0 = __ldg(plo + off), h0 = __ldg(phi + off);
+            const double2 bd = __ldg(pb + min(base, last));
+            const double l0 = bd.x, h0 = bd.y;
             const int first_pinned = (int)((m_lo[0] & 1u) | ((m_hi[0] & 1u) << 1));
             const double pred = fma(P.px02, x2, fma(T, x1, x0));      // Px[0] . x
             double z0;
             if (first_pinned) {
                 z0 = (first_pinned & 2) ? h0 : l0;
             } else {
-                const double2 ga = G[0], gb = G[1];
-                const double J0 = fma(ga.x, x0, fma(ga.y, x1, fma(gb.x, x2, gb.y)));
+                double J0;
+                if (schur) {                                     // few-pin sweep: the corrected plan is at hand
+                    J0 = (z_first - pred) * P.inv_cb;
+                } else if (jg > 0) {                             // row 0 went through the general recursion
+                    const double2 ga = G[0], gb = G[1];
+                    J0 = fma(ga.x, x0, fma(ga.y, x1, fma(gb.x, x2, gb.y)));
+                } else {                                         // no pinned row at all: J = -K_0 . x - kc_0
+                    J0 = fma(-__ldg(P.aux + 0), x0, fma(-__ldg(P.aux + 1), x1, fma(-__ldg(P.aux + 2), x2, KC[0])));
+                }
                 z0 = fma(P.cbv, J0, pred);
                 z0 = z0 < l0 ? l0 : (z0 > h0 ? h0 : z0);             // a free row is inside the box; keep it there to the last bit
             }
@@ -471,16 +757,23 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
             if (pplan && i == ticks - 1) {
                 // the previewed ZMP of the last tick (single-tick API): one more forward pass over the final gains
                 double s0 = x0, s1 = x1, s2 = x2;
-                for (int j = 0; j < N; ++j) {
-                    const int o = min(base + j, last) * bstride;
-                    const double2 ga = G[j * GS], gb = G[j * GS + 1];
+                for (int j = 0; schur && j < N; ++j) pplan[j] = KC[j * KS];
+                for (int j = 0; !schur && j < N; ++j) {
+                    const double2 bd = __ldg(pb + min(base + j, last));
                     const bool plo_j = get_bit(m_lo, j), phi_j = get_bit(m_hi, j);
                     double Jv;
-                    if (plo_j | phi_j) Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, (phi_j ? __ldg(phi + o) : __ldg(plo + o)) * P.inv_cb)));
-                    else Jv = fma(ga.x, s0, fma(ga.y, s1, fma(gb.x, s2, gb.y)));
+                    if (plo_j | phi_j) {
+                        Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, (phi_j ? bd.y : bd.x) * P.inv_cb)));
+                    } else if (j < jg) {
+                        const double2 ga = G[j * GS], gb = G[j * GS + 1];
+                        Jv = fma(ga.x, s0, fma(ga.y, s1, fma(gb.x, s2, gb.y)));
+                    } else {
+                        const double* a = P.aux + j * 12;
+                        Jv = fma(-__ldg(a), s0, fma(-__ldg(a + 1), s1, fma(-__ldg(a + 2), s2, KC[j * KS])));
+                    }
                     const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);
                     s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
-                    pplan[j] = (plo_j | phi_j) ? (phi_j ? __ldg(phi + o) : __ldg(plo + o)) : fma(-hg, s2, s0);
+                    pplan[j] = (plo_j | phi_j) ? (phi_j ? bd.y : bd.x) : fma(-hg, s2, s0);
                 }
             }
             if (i == ftick) n1 -= impulse;
@@ -504,12 +797,27 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     if (P.stats) {
         atomicAdd(P.stats, (unsigned long long)sweeps_total);
         atomicAdd(P.stats + 1, 1ull);
+        atomicAdd(P.stats + 2, (unsigned long long)general_stages);
+        atomicAdd(P.stats + 3, (unsigned long long)table_stages);
     }
 }
 
+template <int LANES, bool SMEM>
+int launch_variant(const RiccatiParams& P, unsigned blocks, int threads, size_t smem, cudaStream_t stream) {
+    if (smem > 48 * 1024) {
+        static size_t granted = 0;      // per instantiation; growing it twice from two threads is harmless
+        if (smem > granted) {
+            LIPM_CUDA_TRY(cudaFuncSetAttribute(k_riccati_rollout<LANES, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynamicSmem));
+            granted = kMaxDynamicSmem;
+        }
+    }
+    k_riccati_rollout<LANES, SMEM><<<blocks, threads, smem, stream>>>(P);
+    return LIPM_OK;
+}
+
 template <int LANES>
-void launch_lanes(const RiccatiParams& P, unsigned blocks, int threads, cudaStream_t stream) {
-    k_riccati_rollout<LANES><<<blocks, threads, 0, stream>>>(P);
+int launch_lanes(const RiccatiParams& P, unsigned blocks, int threads, size_t smem, cudaStream_t stream) {
+    return smem ? launch_variant<LANES, true>(P, blocks, threads, smem, stream) : launch_variant<LANES, false>(P, blocks, threads, 0, stream);
 }
 
 int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream) {
@@ -527,30 +835,61 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
     LaunchState state;
     LIPM_CUDA_TRY(state.begin(stream));
     P.stats = state.stats();
-    // per-stage feedback data: 32 bytes per stage and column; batches beyond 4 GiB of it run in several launches
-    const size_t per_col = (size_t)P.N * 32;
-    long long cols_per_launch = (long long)((size_t)4 << 30) / (long long)per_col;
-    cols_per_launch -= cols_per_launch % lanes;
-    if (cols_per_launch < lanes) cols_per_launch = lanes;
-    if (cols_per_launch > ncols) cols_per_launch = ((long long)ncols + lanes - 1) / lanes * lanes;
-    StreamBuffer scratch;
-    // (+ kGainPrefetch stages of slack: the forward sweep looks ahead without range checks)
-    LIPM_CUDA_TRY(scratch.alloc((size_t)cols_per_launch * per_col + (size_t)(kGainPrefetch + 8) * 32 * 32, stream));
-    P.gains = scratch.as<double2>();
     const int warps_per_block = 2;
+    // shared memory: the per-plan stage tables (128 B per stage) and the feed-forward terms of the block's table stages
+    // (8 B per stage and column).  When that is too much for three blocks per SM (long horizons, wide warps) the tables
+    // are read through L1 and the terms go to global scratch.
+    const size_t smem_bytes = (size_t)(P.N + 4) * (128 + 8 * warps_per_block * lanes);
+    const bool in_smem = plan->riccati_scratch == 1 || (plan->riccati_scratch == 0 && smem_bytes <= kMaxAutoSmem);
+    if (in_smem && smem_bytes > kMaxDynamicSmem) {
+        set_error("active-set kernel: %zu bytes of shared memory requested (horizon %d, %d columns per warp)", smem_bytes, P.N, lanes);
+        return LIPM_E_UNSUPPORTED;
+    }
+    const size_t smem = in_smem ? smem_bytes : 0;
+    // bound series as (lo, hi) pairs: per (series, axis) when the series are shared or indexed, per column otherwise
+    const ColumnBatch& cb = P.cb;
+    const int ns = cb.n_uniform;
+    P.pk_by_column = (!cb.bounds_index && cb.bounds_batch != 1) ? 1 : 0;
+    // scratch per column: feedback data of the general recursion (32 B per stage), the table stages' feed-forward when it
+    // is not in shared memory (8 B per stage), the column's own bound pairs; batches beyond 4 GiB run in several launches
+    const size_t per_col = (size_t)(P.N + 4) * (in_smem ? 32 : 40) + (P.pk_by_column ? (size_t)ns * 16 : 0);
+    long long cols_per_launch = (long long)((size_t)4 << 30) / (long long)per_col;
+    const int cols_per_block = warps_per_block * lanes;
+    cols_per_launch -= cols_per_launch % cols_per_block;
+    if (cols_per_launch < cols_per_block) cols_per_launch = cols_per_block;
+    if (cols_per_launch > ncols) cols_per_launch = ((long long)ncols + cols_per_block - 1) / cols_per_block * cols_per_block;
+    const size_t gain_bytes = (size_t)cols_per_launch * (P.N + 4) * 32 + (size_t)(kGainPrefetch + 8) * 32 * 32;
+    const size_t kc_bytes = in_smem ? 0 : (size_t)cols_per_launch * (P.N + 4) * 8 + (size_t)(kGainPrefetch + 8) * 64 * 8;
+    const long long pk_runs = P.pk_by_column ? cols_per_launch : (long long)cb.bounds_batch * (cb.bound_axis_offset ? 2 : 1);
+    const size_t pk_bytes = (size_t)pk_runs * ns * 16;
+    StreamBuffer scratch;
+    LIPM_CUDA_TRY(scratch.alloc(gain_bytes + kc_bytes + pk_bytes, stream));
+    P.gains = scratch.as<double2>();
+    P.nkc = in_smem ? nullptr : reinterpret_cast<double*>(scratch.as<unsigned char>() + gain_bytes);
+    double2* pk = reinterpret_cast<double2*>(scratch.as<unsigned char>() + gain_bytes + kc_bytes);
+    P.pk = pk;
     for (long long c0 = 0; c0 < ncols; c0 += cols_per_launch) {
         P.col_begin = (int)c0;
         P.col_end = (int)(c0 + cols_per_launch < ncols ? c0 + cols_per_launch : ncols);
+        if (P.pk_by_column || c0 == 0) {
+            const long long runs = P.pk_by_column ? (long long)(P.col_end - P.col_begin) : pk_runs;
+            const long long total = runs * ns;
+            const unsigned pblocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)plan->sm_count * 16);
+            k_pack_bounds<<<pblocks ? pblocks : 1, 256, 0, stream>>>(P, pk, (int)runs, P.pk_by_column);
+            LIPM_CUDA_TRY(cudaGetLastError());
+        }
         const long long warps = ((long long)(P.col_end - P.col_begin) + lanes - 1) / lanes;
         const long long blocks = (warps + warps_per_block - 1) / warps_per_block;
+        int rc;
         switch (lanes) {
-            case 1: launch_lanes<1>(P, (unsigned)blocks, 32 * warps_per_block, stream); break;
-            case 2: launch_lanes<2>(P, (unsigned)blocks, 32 * warps_per_block, stream); break;
-            case 4: launch_lanes<4>(P, (unsigned)blocks, 32 * warps_per_block, stream); break;
-            case 8: launch_lanes<8>(P, (unsigned)blocks, 32 * warps_per_block, stream); break;
-            case 16: launch_lanes<16>(P, (unsigned)blocks, 32 * warps_per_block, stream); break;
-            default: launch_lanes<32>(P, (unsigned)blocks, 32 * warps_per_block, stream); break;
+            case 1: rc = launch_lanes<1>(P, (unsigned)blocks, 32 * warps_per_block, smem, stream); break;
+            case 2: rc = launch_lanes<2>(P, (unsigned)blocks, 32 * warps_per_block, smem, stream); break;
+            case 4: rc = launch_lanes<4>(P, (unsigned)blocks, 32 * warps_per_block, smem, stream); break;
+            case 8: rc = launch_lanes<8>(P, (unsigned)blocks, 32 * warps_per_block, smem, stream); break;
+            case 16: rc = launch_lanes<16>(P, (unsigned)blocks, 32 * warps_per_block, smem, stream); break;
+            default: rc = launch_lanes<32>(P, (unsigned)blocks, 32 * warps_per_block, smem, stream); break;
         }
+        if (rc != LIPM_OK) return rc;
         LIPM_CUDA_TRY(cudaGetLastError());
     }
     LIPM_CUDA_TRY(state.publish(plan->d_stats));
@@ -558,6 +897,58 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
 }
 
 }  // namespace
+
+// Per-plan tables of the stages whose later rows are all free (host, once per plan).  Stage j, j = N-1 .. 0, with
+// W = P_{j+1} + Q C'C:  sigma = R + B'W B,  K = B'W A / sigma,  Acl = A - B K,  P_j = Acl'W Acl + R K'K  (Joseph form).
+// tab[j] = four groups of four: group g < 3 = (Acl[0][g], Acl[1][g], Acl[2][g], -(Acl'C')_g), group 3 = (-B / sigma, C B / sigma),
+// so that  v_j = sum_r group_g[r] v_{j+1,r} + Q zref group_g[3]  and  -kc_j = group_3 . (v_{j+1}, Q zref).
+int build_riccati_tables(lipm_plan* plan) {
+    const lipm_plan_desc_t& d = plan->desc;
+    const int N = plan->N;
+    const double T = d.dt, c2 = d.dt * d.dt / 2.0, c3 = d.dt * d.dt * d.dt / 6.0, hg = d.h / d.g;
+    const double A[3][3] = {{1.0, T, c2}, {0.0, 1.0, T}, {0.0, 0.0, 1.0}};
+    const double Bv[3] = {c3, c2, T};
+    const double Cv[3] = {1.0, 0.0, -hg};
+    std::vector<double> tab((size_t)(N + 4) * 16, 0.0), aux((size_t)(N + 1) * 12, 0.0);
+    double Pm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int j = N - 1; j >= 0; --j) {
+        double W[3][3], WB[3], K[3], Acl[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) W[r][c] = Pm[r][c] + d.Q * Cv[r] * Cv[c];
+        double sigma = d.R;
+        for (int r = 0; r < 3; ++r) {
+            WB[r] = W[r][0] * Bv[0] + W[r][1] * Bv[1] + W[r][2] * Bv[2];
+        }
+        for (int r = 0; r < 3; ++r) sigma += Bv[r] * WB[r];
+        for (int c = 0; c < 3; ++c) K[c] = (A[0][c] * WB[0] + A[1][c] * WB[1] + A[2][c] * WB[2]) / sigma;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Acl[r][c] = A[r][c] - Bv[r] * K[c];
+        double WA[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) WA[r][c] = W[r][0] * Acl[0][c] + W[r][1] * Acl[1][c] + W[r][2] * Acl[2][c];
+        double Pn[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                Pn[r][c] = Acl[0][r] * WA[0][c] + Acl[1][r] * WA[1][c] + Acl[2][r] * WA[2][c] + d.R * K[r] * K[c];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Pm[r][c] = 0.5 * (Pn[r][c] + Pn[c][r]);
+        double* t = &tab[(size_t)j * 16];
+        for (int g = 0; g < 3; ++g) {
+            t[4 * g + 0] = Acl[0][g]; t[4 * g + 1] = Acl[1][g]; t[4 * g + 2] = Acl[2][g];
+            t[4 * g + 3] = -(Acl[0][g] * Cv[0] + Acl[1][g] * Cv[1] + Acl[2][g] * Cv[2]);
+        }
+        t[12] = -Bv[0] / sigma; t[13] = -Bv[1] / sigma; t[14] = -Bv[2] / sigma;
+        t[15] = (Bv[0] * Cv[0] + Bv[1] * Cv[1] + Bv[2] * Cv[2]) / sigma;
+        double* a = &aux[(size_t)j * 12];
+        a[0] = K[0]; a[1] = K[1]; a[2] = K[2];
+        a[4] = Pm[0][0]; a[5] = Pm[0][1]; a[6] = Pm[0][2]; a[7] = Pm[1][1]; a[8] = Pm[1][2]; a[9] = Pm[2][2];
+    }
+    LIPM_CUDA_TRY(cudaMalloc(&plan->d_ric_tab, tab.size() * sizeof(double)));
+    LIPM_CUDA_TRY(cudaMalloc(&plan->d_ric_aux, aux.size() * sizeof(double)));
+    LIPM_CUDA_TRY(cudaMemcpy(plan->d_ric_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    LIPM_CUDA_TRY(cudaMemcpy(plan->d_ric_aux, aux.data(), aux.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return LIPM_OK;
+}
 
 int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
     const lipm_plan_desc_t& d = plan->desc;
@@ -590,7 +981,9 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
         P.a2[r] = A[6 + r] - Bv[2] * ca[r] / plan->pu00;
     }
     P.hg2x = 2.0 * P.hg; P.hgsq = P.hg * P.hg;
-    P.col_begin = 0; P.col_end = cb.ncols; P.gains = nullptr;
+    P.col_begin = 0; P.col_end = cb.ncols; P.gains = nullptr; P.nkc = nullptr;
+    P.tab = plan->d_ric_tab; P.aux = plan->d_ric_aux; P.pk = nullptr; P.pk_by_column = 0;
+    P.hinv = plan->d_hinv; P.schur_max = plan->riccati_few_pins <= 0 ? 0 : (plan->riccati_few_pins > kSchurMax ? kSchurMax : plan->riccati_few_pins);
     P.rkk[0] = d.R * P.kv[0] * P.kv[0]; P.rkk[1] = d.R * P.kv[0] * P.kv[1]; P.rkk[2] = d.R * P.kv[0] * P.kv[2];
     P.rkk[3] = d.R * P.kv[1] * P.kv[1]; P.rkk[4] = d.R * P.kv[1] * P.kv[2]; P.rkk[5] = d.R * P.kv[2] * P.kv[2];
     P.viol_tol = d.viol_tol;

@@ -84,6 +84,8 @@ OPT_SINGLE_CTA_F16 = 3
 OPT_STRICT_SOLVER = 4
 OPT_RICCATI_LANES = 5
 OPT_MAX_SWEEPS = 6
+OPT_RICCATI_SCRATCH = 7
+OPT_FEW_PIN_ROWS = 8
 # solver of the FP64 strict mode: both return the unique minimiser of the reference's QP
 SOLVER_ACTIVE_SET = 0   # default: primal-dual active set + O(N) Riccati sweeps (csrc/lipm_rollout_riccati.cu)
 SOLVER_ADMM = 1         # ADMM on the condensed QP, FP64 tensor pipe (csrc/lipm_rollout_strict.cu)
@@ -300,6 +302,14 @@ class LipmPlan:
     def set_riccati_lanes(self, lanes: int) -> None:
         """Columns per warp of the active-set kernel (0 = automatic); results do not depend on it."""
         _check(self._lib.lipm_set_option(self._handle, OPT_RICCATI_LANES, int(lanes)))
+
+    def set_riccati_scratch(self, where: int) -> None:
+        """Feed-forward terms of the active-set kernel's table stages: 0 automatic, 1 shared memory, 2 global scratch."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_RICCATI_SCRATCH, int(where)))
+
+    def set_few_pin_rows(self, rows: int) -> None:
+        """Active-set kernel: pinned rows up to which a sweep uses table solve + dense correction (0 = never, the default; up to 16)."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_FEW_PIN_ROWS, int(rows)))
 
     def set_max_sweeps(self, sweeps: int) -> None:
         """Active-set corrections per QP before the solve is reported as not converged (0 = default 64)."""
