@@ -34,7 +34,7 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s, p->d_ric_tab, p->d_ric_aux};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s, p->d_ric_tab, p->d_ric_aux, p->d_kx, p->d_hl, p->d_acp};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }
@@ -214,6 +214,10 @@ int lipm_set_option(lipm_plan_t* plan, int option, long long value) {
         case LIPM_OPT_RICCATI_LANES:
             if (!plan || value < 0 || value > 32 || (value & (value - 1)) != 0) { set_error("lipm_set_option(RICCATI_LANES): need a plan and 0 or a power of two <= 32"); return LIPM_E_INVALID; }
             plan->riccati_lanes = (int)value;
+            return LIPM_OK;
+        case LIPM_OPT_ROW_PARALLEL:
+            if (!plan || (value != 0 && value != 1)) { set_error("lipm_set_option(ROW_PARALLEL): need a plan and 0 / 1"); return LIPM_E_INVALID; }
+            plan->rowpar_off = value ? 0 : 1;
             return LIPM_OK;
         case LIPM_OPT_FEW_PIN_ROWS:
             if (!plan || value < 0 || value > 16) { set_error("lipm_set_option(FEW_PIN_ROWS): need a plan and a value in [0, 16]"); return LIPM_E_INVALID; }

@@ -128,6 +128,10 @@ struct lipm_plan {
     int riccati_scratch;  // feed-forward terms of the table stages: 0 automatic, 1 shared memory, 2 global scratch
     double* d_ric_tab;    // [N + 4][16] per-stage tables of the active-set kernel's free tail (build_riccati_tables)
     double* d_ric_aux;    // [N + 1][12] K_j, P_j of the same stages
+    double* d_kx;         // Kx = H^-1 G Px of every sub-horizon (row-parallel kernel): [(N-L)][3] per leading block L
+    double* d_hl;         // inverses of the trailing blocks H[L:, L:], L = 0 .. N-1 (N <= 160 only)
+    double* d_acp;        // [N+1][12] powers of the pinned-stage matrix, Ac^m and Ac^m bc
+    int rowpar_off;       // 1: FP64 active-set walks skip the row-parallel first stage (lipm_set_option)
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch (copied from the launch's own state)
@@ -138,6 +142,24 @@ namespace lipm {
 // plan construction (lipm_plan.cu)
 int build_plan_matrices(lipm_plan* plan);
 int build_riccati_tables(lipm_plan* plan);        // lipm_rollout_riccati.cu
+int build_rowpar_tables(lipm_plan* plan);         // lipm_rollout_rowpar.cu
+
+// Row-parallel first stage of the active-set solver (lipm_rollout_rowpar.cu) and its hand-over to k_riccati_rollout.
+constexpr int kRowparWords = 5;        // 32-row words of a column: horizons up to 160
+constexpr int kRowparMaxPins = 16;     // pinned rows a row-parallel sweep can take
+struct ParkRecord {                    // a column that left the row-parallel kernel: where and in which state
+    int tick, sweeps, notconv, pad;
+    double x[3];
+    double viol, lean;
+    uint32_t m_lo[kRowparWords], m_hi[kRowparWords];
+};
+struct RowparScratch {
+    StreamBuffer buf;
+    ParkRecord* park = nullptr;        // [ncols]
+    int* park_list = nullptr;          // [ncols] parked columns
+    int* park_count = nullptr;
+    unsigned long long* stats = nullptr;
+};
 
 // One "column" = one axis of one scenario.  The rollout kernels receive this flat description.
 struct ColumnBatch {
@@ -183,7 +205,9 @@ int build_unit_order(int num_units, int width, int ncols, int B, const int* orde
 int launch_pack_outcomes(int B, const double* max_violation, const double* lean_max, const int32_t* status, const int32_t* iters,
                          double fall_lean, lipm_outcome_t* outcome, cudaStream_t stream);
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
-int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // active set + Riccati sweeps
+int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // active set: row-parallel stage, then Riccati sweeps
+bool rowpar_eligible(const lipm_plan* plan, const ColumnBatch& cb);
+int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16p(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // CTA pairs (cta_group::2)

@@ -361,6 +361,9 @@ int build_plan_matrices(lipm_plan* plan) {
 
     rc = build_riccati_tables(plan);
     if (rc != LIPM_OK) return rc;
+    rc = build_rowpar_tables(plan);
+    if (rc != LIPM_OK) return rc;
+    LIPM_CUDA_TRY(cudaDeviceSynchronize());
 
     int info[4];
     LIPM_CUDA_TRY(cudaMemcpy(info, plan->d_info, sizeof(info), cudaMemcpyDeviceToHost));

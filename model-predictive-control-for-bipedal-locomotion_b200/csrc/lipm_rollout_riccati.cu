@@ -76,6 +76,9 @@ struct RiccatiParams {
     const double2* pk;      // bound series repacked as (lo, hi) pairs (k_pack_bounds)
     const double* hinv;     // [N][N] inverse Hessian in ZMP coordinates (plan->d_hinv, symmetric): few-pin solves
     int schur_max;          // pinned rows up to which a sweep uses the table solve + dense correction (0: never)
+    const ParkRecord* park; // resume mode: columns parked by the row-parallel kernel (nullptr: whole walks)
+    const int* park_list;   // [*park_count] their column numbers
+    const int* park_count;
     int pk_by_column;       // 1: one run of pairs per column of the launch; 0: one per (series, axis)
     unsigned long long* stats;   // [0] sweep pairs, [1] columns, [2] stages of the general recursion, [3] table stages
 };
@@ -270,8 +273,14 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                        ((threadIdx.x >> 5) * LANES + lane);
     if (lane >= LANES) return;
     const long long cl = (long long)P.col_begin + warp * LANES + lane;
-    if (cl >= P.col_end) return;
-    const int c = (int)cl;
+    int c;
+    if (P.park) {
+        if (cl >= *P.park_count) return;
+        c = P.park_list[cl];
+    } else {
+        if (cl >= P.col_end) return;
+        c = (int)cl;
+    }
     const int NW = (N + 31) >> 5;
     constexpr int GS = 2 * LANES;                 // double2 elements between consecutive stages of a column
 
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     double viol = 0.0, lean = 0.0;
     int sweeps_total = 0, notconv = 0;
     long long general_stages = 0, table_stages = 0;     // statistics: stages that went through the general recursion / the tables
-    if (B.write_initial && ticks > 0) {
+    if (B.write_initial && ticks > 0 && !P.park) {
         const double zmp = x0 - P.hg * x2;
         const double2 b0 = __ldg(pb);
         const double below = b0.x - zmp, above = zmp - b0.y;
@@ -324,10 +333,19 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     const double T = P.T, c2 = P.c2, c3 = P.c3, hg = P.hg, Q = P.Q;
     const int N4 = N & ~3;                          // rows N4 .. N-1: a tail of up to three stages
 
-    for (int i = 0; i < ticks; ++i) {
+    int i_begin = 0;
+    if (P.park) {
+        // resume a column of the row-parallel kernel: its tick, state, running outcomes and current set
+        const ParkRecord& rec = P.park[c];
+        i_begin = rec.tick; sweeps_total = rec.sweeps; notconv = rec.notconv;
+        x0 = rec.x[0]; x1 = rec.x[1]; x2 = rec.x[2]; viol = rec.viol; lean = rec.lean;
+#pragma unroll
+        for (int w = 0; w < kRowparWords; ++w) { m_lo[w] = s_lo[w] = rec.m_lo[w]; m_hi[w] = s_hi[w] = rec.m_hi[w]; }
+    }
+    for (int i = i_begin; i < ticks; ++i) {
         const int base = i + B.bound_index_bias;      // window row j reads sample min(base + j, last)
         // ---- guess: extrapolated from the last two ticks' sets (plain shift by default) --------------------
-        if (i > 0) {
+        if (i > i_begin) {
             predict_active_set(s_lo, s_hi, m_lo, m_hi, N, NW);
         }
         uint32_t zmag_hi = 0x3ff00000u;            // high word of max(1, |z|_inf) of the last forward sweep
@@ -797,8 +815,10 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     if (P.stats) {
         atomicAdd(P.stats, (unsigned long long)sweeps_total);
         atomicAdd(P.stats + 1, 1ull);
-        atomicAdd(P.stats + 2, (unsigned long long)general_stages);
-        atomicAdd(P.stats + 3, (unsigned long long)table_stages);
+        if (!P.park) {
+            atomicAdd(P.stats + 2, (unsigned long long)general_stages);
+            atomicAdd(P.stats + 3, (unsigned long long)table_stages);
+        }
     }
 }
 
@@ -831,10 +851,13 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
         lanes = 1;
         while (lanes < 32 && (long long)ncols > want_warps * lanes) lanes <<= 1;
     }
+    if (P.park && plan->riccati_lanes <= 0 && lanes > 1) lanes >>= 1;      // resume: a fraction of the columns is left
     P.lanes = lanes;
     LaunchState state;
-    LIPM_CUDA_TRY(state.begin(stream));
-    P.stats = state.stats();
+    if (!P.stats) {                 // (resume: the statistics words of the row-parallel stage are continued)
+        LIPM_CUDA_TRY(state.begin(stream));
+        P.stats = state.stats();
+    }
     const int warps_per_block = 2;
     // shared memory: the per-plan stage tables (128 B per stage) and the feed-forward terms of the block's table stages
     // (8 B per stage and column).  When that is too much for three blocks per SM (long horizons, wide warps) the tables
@@ -892,7 +915,7 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
         if (rc != LIPM_OK) return rc;
         LIPM_CUDA_TRY(cudaGetLastError());
     }
-    LIPM_CUDA_TRY(state.publish(plan->d_stats));
+    LIPM_CUDA_TRY(cudaMemcpyAsync(plan->d_stats, P.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     return LIPM_OK;
 }
 
@@ -950,7 +973,26 @@ int build_riccati_tables(lipm_plan* plan) {
     return LIPM_OK;
 }
 
+static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* resume, cudaStream_t stream);
+
+// Default FP64 strict solver: walks on shared bound series start on the row-parallel kernel; the columns it parks (sets
+// too large for it) and every other batch run on the thread-per-column Riccati kernel.
 int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
+    if (plan->N > kMaxStrictHorizon) {
+        set_error("strict mode: horizon %d exceeds this build's limit %d", plan->N, kMaxStrictHorizon);
+        return LIPM_E_UNSUPPORTED;
+    }
+    if (!rowpar_eligible(plan, cb)) return launch_riccati_stage(plan, cb, nullptr, stream);
+    RowparScratch rs;
+    LaunchState state;
+    LIPM_CUDA_TRY(state.begin(stream));
+    rs.stats = state.stats();
+    int rc = launch_rowpar(plan, cb, rs, stream);
+    if (rc != LIPM_OK) return rc;
+    return launch_riccati_stage(plan, cb, &rs, stream);
+}
+
+static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* resume, cudaStream_t stream) {
     const lipm_plan_desc_t& d = plan->desc;
     if (plan->N > kMaxStrictHorizon) {
         set_error("strict mode: horizon %d exceeds this build's limit %d", plan->N, kMaxStrictHorizon);
@@ -983,12 +1025,14 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
     P.hg2x = 2.0 * P.hg; P.hgsq = P.hg * P.hg;
     P.col_begin = 0; P.col_end = cb.ncols; P.gains = nullptr; P.nkc = nullptr;
     P.tab = plan->d_ric_tab; P.aux = plan->d_ric_aux; P.pk = nullptr; P.pk_by_column = 0;
+    P.park = nullptr; P.park_list = nullptr; P.park_count = nullptr;
     P.hinv = plan->d_hinv; P.schur_max = plan->riccati_few_pins <= 0 ? 0 : (plan->riccati_few_pins > kSchurMax ? kSchurMax : plan->riccati_few_pins);
     P.rkk[0] = d.R * P.kv[0] * P.kv[0]; P.rkk[1] = d.R * P.kv[0] * P.kv[1]; P.rkk[2] = d.R * P.kv[0] * P.kv[2];
     P.rkk[3] = d.R * P.kv[1] * P.kv[1]; P.rkk[4] = d.R * P.kv[1] * P.kv[2]; P.rkk[5] = d.R * P.kv[2] * P.kv[2];
     P.viol_tol = d.viol_tol;
     P.mu_eps = 1e-12;
     P.stats = nullptr;
+    if (resume) { P.park = resume->park; P.park_list = resume->park_list; P.park_count = resume->park_count; P.stats = resume->stats; }
     return launch_kernel(plan, P, stream);
 }
 

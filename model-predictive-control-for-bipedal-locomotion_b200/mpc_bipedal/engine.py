@@ -86,6 +86,7 @@ OPT_RICCATI_LANES = 5
 OPT_MAX_SWEEPS = 6
 OPT_RICCATI_SCRATCH = 7
 OPT_FEW_PIN_ROWS = 8
+OPT_ROW_PARALLEL = 9
 # solver of the FP64 strict mode: both return the unique minimiser of the reference's QP
 SOLVER_ACTIVE_SET = 0   # default: primal-dual active set + O(N) Riccati sweeps (csrc/lipm_rollout_riccati.cu)
 SOLVER_ADMM = 1         # ADMM on the condensed QP, FP64 tensor pipe (csrc/lipm_rollout_strict.cu)
@@ -310,6 +311,10 @@ class LipmPlan:
     def set_few_pin_rows(self, rows: int) -> None:
         """Active-set kernel: pinned rows up to which a sweep uses table solve + dense correction (0 = never, the default; up to 16)."""
         _check(self._lib.lipm_set_option(self._handle, OPT_FEW_PIN_ROWS, int(rows)))
+
+    def set_row_parallel(self, on: bool) -> None:
+        """FP64 active-set walks on shared / indexed bound series start on the row-parallel kernel (default on)."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_ROW_PARALLEL, 1 if on else 0))
 
     def set_max_sweeps(self, sweeps: int) -> None:
         """Active-set corrections per QP before the solve is reported as not converged (0 = default 64)."""

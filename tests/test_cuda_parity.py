@@ -233,7 +233,18 @@ def test_batch_results_do_not_depend_on_batch_layout(engine, plan150):
     # per-scenario bounds (B,n,2) give the same bits as the shared (n,2) series
     per = plan150.rollout(engine.MODE_STRICT, zero[pick], zero[pick], np.repeat(z_min[None], 3, 0),
                           np.repeat(z_max[None], 3, 0), impulse=impulse[pick], force_tick=tick[pick])
-    assert np.array_equal(per["y_hist"].cpu().numpy(), sub["y_hist"])
+    # (the default FP64 solver starts shared series on its row-parallel kernel and per-scenario series on the Riccati
+    # kernel: two formulations of the same optimum, equal to rounding amplified by the walk, not to the bit)
+    if plan150.solver == engine.SOLVER_ADMM:
+        assert np.array_equal(per["y_hist"].cpu().numpy(), sub["y_hist"])
+    else:
+        assert rel_err(per["y_hist"].cpu().numpy(), sub["y_hist"]) < REL
+        plan150.set_row_parallel(False)
+        try:
+            sub2 = plan150.rollout(engine.MODE_STRICT, zero[pick], zero[pick], z_min, z_max, impulse=impulse[pick], force_tick=tick[pick])
+            assert np.array_equal(per["y_hist"].cpu().numpy(), sub2["y_hist"].cpu().numpy())
+        finally:
+            plan150.set_row_parallel(True)
 
 
 def test_tick_ranges_do_not_change_results(engine):
