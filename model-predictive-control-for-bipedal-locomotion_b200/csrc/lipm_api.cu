@@ -34,7 +34,7 @@ struct DeviceGuard {
 
 void free_plan_buffers(lipm_plan* p) {
     void* ptrs[] = {p->d_px, p->d_pu, p->d_abc, p->d_tinv, p->d_g, p->d_gpx, p->d_work,
-                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s, p->d_ric_tab, p->d_ric_aux, p->d_kx, p->d_hl, p->d_acp};
+                    p->d_hinv, p->d_minv, p->d_mfrag, p->d_hfrag, p->d_gain, p->d_info, p->d_stats, p->d_bf16, p->d_f16s, p->d_ric_tab, p->d_ric_aux, p->d_kx};
     for (void* q : ptrs)
         if (q) cudaFree(q);
 }

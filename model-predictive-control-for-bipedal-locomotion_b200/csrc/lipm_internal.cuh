@@ -128,9 +128,7 @@ struct lipm_plan {
     int riccati_scratch;  // feed-forward terms of the table stages: 0 automatic, 1 shared memory, 2 global scratch
     double* d_ric_tab;    // [N + 4][16] per-stage tables of the active-set kernel's free tail (build_riccati_tables)
     double* d_ric_aux;    // [N + 1][12] K_j, P_j of the same stages
-    double* d_kx;         // Kx = H^-1 G Px of every sub-horizon (row-parallel kernel): [(N-L)][3] per leading block L
-    double* d_hl;         // inverses of the trailing blocks H[L:, L:], L = 0 .. N-1 (N <= 160 only)
-    double* d_acp;        // [N+1][12] powers of the pinned-stage matrix, Ac^m and Ac^m bc
+    double* d_kx;         // [N][3] Kx = H^-1 G Px: state part of the unconstrained plan (row-parallel kernel, N <= 160)
     int rowpar_off;       // 1: FP64 active-set walks skip the row-parallel first stage (lipm_set_option)
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
@@ -153,11 +151,15 @@ struct ParkRecord {                    // a column that left the row-parallel ke
     double viol, lean;
     uint32_t m_lo[kRowparWords], m_hi[kRowparWords];
 };
+constexpr int kRowparLists = 3;        // hand-over lists of a rollout: row-parallel -> Riccati -> row-parallel -> Riccati
 struct RowparScratch {
     StreamBuffer buf;
+    double* u = nullptr;               // shared preview terms
+    double2* pk = nullptr;             // bound pairs per (series, axis)
+    int* n_series = nullptr;
     ParkRecord* park = nullptr;        // [ncols]
-    int* park_list = nullptr;          // [ncols] parked columns
-    int* park_count = nullptr;
+    int* lists = nullptr;              // [kRowparLists][ncols] parked columns
+    int* counts = nullptr;             // [kRowparLists] (+ padding)
     unsigned long long* stats = nullptr;
 };
 
@@ -207,7 +209,8 @@ int launch_pack_outcomes(int B, const double* max_violation, const double* lean_
 int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // active set: row-parallel stage, then Riccati sweeps
 bool rowpar_eligible(const lipm_plan* plan, const ColumnBatch& cb);
-int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cudaStream_t stream);
+int rowpar_prepare(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cudaStream_t stream);
+int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& rs, int in_list, int out_list, cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16p(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // CTA pairs (cta_group::2)

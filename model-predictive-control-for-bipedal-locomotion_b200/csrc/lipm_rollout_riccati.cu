@@ -76,9 +76,12 @@ struct RiccatiParams {
     const double2* pk;      // bound series repacked as (lo, hi) pairs (k_pack_bounds)
     const double* hinv;     // [N][N] inverse Hessian in ZMP coordinates (plan->d_hinv, symmetric): few-pin solves
     int schur_max;          // pinned rows up to which a sweep uses the table solve + dense correction (0: never)
-    const ParkRecord* park; // resume mode: columns parked by the row-parallel kernel (nullptr: whole walks)
+    ParkRecord* park;       // resume mode: records of the columns parked by the row-parallel kernel (nullptr: whole walks)
     const int* park_list;   // [*park_count] their column numbers
     const int* park_count;
+    int* back_list;         // resume mode: columns handed back to the row-parallel kernel once their set is small again
+    int* back_count;        //   (nullptr: every column is finished here)
+    int back_pins;          // ... small = at most this many pinned rows on kBackStreak consecutive ticks
     int pk_by_column;       // 1: one run of pairs per column of the launch; 0: one per (series, axis)
     unsigned long long* stats;   // [0] sweep pairs, [1] columns, [2] stages of the general recursion, [3] table stages
 };
@@ -91,6 +94,7 @@ __device__ __forceinline__ int biased_exponent(double x) { return (__double2hiin
 
 constexpr int kGainPrefetch = 16;  // stages of look-ahead of the forward sweep's L1 prefetch (a forward stage is ~20 instructions, an L2 hit ~250 cycles)
 constexpr int kMaskWords = kMaxStrictHorizon / 32;
+constexpr int kBackStreak = 3;
 constexpr int kSchurMax = 16;                   // pinned rows a few-pin sweep can take (triangular system in local memory)
 constexpr size_t kMaxAutoSmem = 72 * 1024;       // per block: three blocks of two warps still fit one SM
 constexpr size_t kMaxDynamicSmem = 200 * 1024;
@@ -333,7 +337,8 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
     const double T = P.T, c2 = P.c2, c3 = P.c3, hg = P.hg, Q = P.Q;
     const int N4 = N & ~3;                          // rows N4 .. N-1: a tail of up to three stages
 
-    int i_begin = 0;
+    int i_begin = 0, calm = 0;
+    bool handed_back = false;
     if (P.park) {
         // resume a column of the row-parallel kernel: its tick, state, running outcomes and current set
         const ParkRecord& rec = P.park[c];
@@ -806,7 +811,28 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
             x0 = n0; x1 = n1; x2 = n2;
             if (!converged) break;
         }
+        // ---- resume mode: the push is absorbed (few pinned rows for a few ticks): back to the row-parallel kernel ---------
+        if (P.back_list && i + 1 < ticks) {
+            int pins = 0;
+            for (int w = 0; w < NW; ++w) pins += __popc(m_lo[w] | m_hi[w]);
+            calm = pins <= P.back_pins ? calm + 1 : 0;
+            if (calm >= kBackStreak) {
+                ParkRecord& rec = P.park[c];
+                rec.tick = i + 1; rec.sweeps = sweeps_total; rec.notconv = notconv;
+                rec.x[0] = x0; rec.x[1] = x1; rec.x[2] = x2; rec.viol = viol; rec.lean = lean;
+#pragma unroll
+                for (int w = 0; w < kRowparWords; ++w) {        // the guess of the next tick: the set moved up by one row
+                    rec.m_lo[w] = (m_lo[w] >> 1) | ((w + 1 < kMaskWords ? m_lo[w + 1] : 0u) << 31);
+                    rec.m_hi[w] = (m_hi[w] >> 1) | ((w + 1 < kMaskWords ? m_hi[w + 1] : 0u) << 31);
+                }
+                P.back_list[atomicAdd(P.back_count, 1)] = c;
+                if (P.stats) atomicAdd(P.stats + 3, 1ull);          // statistics: [3] columns handed back
+                handed_back = true;
+                break;
+            }
+        }
     }
+    if (handed_back) return;
 
     if (B.max_violation) B.max_violation[b * 2 + axis] = viol;
     if (B.lean_max) B.lean_max[b * 2 + axis] = lean;
@@ -973,26 +999,31 @@ int build_riccati_tables(lipm_plan* plan) {
     return LIPM_OK;
 }
 
-static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* resume, cudaStream_t stream);
+static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* rs, int in_list, int back_list, cudaStream_t stream);
 
-// Default FP64 strict solver: walks on shared bound series start on the row-parallel kernel; the columns it parks (sets
-// too large for it) and every other batch run on the thread-per-column Riccati kernel.
+// Default FP64 strict solver.  Walks on shared bound series start on the row-parallel kernel (lipm_rollout_rowpar.cu); a
+// column whose active set outgrows it continues here, and goes back once the set is small again:
+//   row-parallel (all columns) -> Riccati (parked, hands back) -> row-parallel (handed back) -> Riccati (the rest).
+// Every other batch (own series per scenario, single ticks, horizons beyond 160) runs here from the first tick.
 int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
     if (plan->N > kMaxStrictHorizon) {
         set_error("strict mode: horizon %d exceeds this build's limit %d", plan->N, kMaxStrictHorizon);
         return LIPM_E_UNSUPPORTED;
     }
-    if (!rowpar_eligible(plan, cb)) return launch_riccati_stage(plan, cb, nullptr, stream);
+    if (!rowpar_eligible(plan, cb)) return launch_riccati_stage(plan, cb, nullptr, -1, -1, stream);
     RowparScratch rs;
     LaunchState state;
     LIPM_CUDA_TRY(state.begin(stream));
     rs.stats = state.stats();
-    int rc = launch_rowpar(plan, cb, rs, stream);
+    int rc = rowpar_prepare(plan, cb, rs, stream);
     if (rc != LIPM_OK) return rc;
-    return launch_riccati_stage(plan, cb, &rs, stream);
+    if ((rc = launch_rowpar(plan, cb, rs, -1, 0, stream)) != LIPM_OK) return rc;
+    if ((rc = launch_riccati_stage(plan, cb, &rs, 0, 1, stream)) != LIPM_OK) return rc;
+    if ((rc = launch_rowpar(plan, cb, rs, 1, 2, stream)) != LIPM_OK) return rc;
+    return launch_riccati_stage(plan, cb, &rs, 2, -1, stream);
 }
 
-static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* resume, cudaStream_t stream) {
+static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* rs, int in_list, int back_list, cudaStream_t stream) {
     const lipm_plan_desc_t& d = plan->desc;
     if (plan->N > kMaxStrictHorizon) {
         set_error("strict mode: horizon %d exceeds this build's limit %d", plan->N, kMaxStrictHorizon);
@@ -1025,14 +1056,20 @@ static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const Ro
     P.hg2x = 2.0 * P.hg; P.hgsq = P.hg * P.hg;
     P.col_begin = 0; P.col_end = cb.ncols; P.gains = nullptr; P.nkc = nullptr;
     P.tab = plan->d_ric_tab; P.aux = plan->d_ric_aux; P.pk = nullptr; P.pk_by_column = 0;
-    P.park = nullptr; P.park_list = nullptr; P.park_count = nullptr;
+    P.park = nullptr; P.park_list = nullptr; P.park_count = nullptr; P.back_list = nullptr; P.back_count = nullptr; P.back_pins = 0;
     P.hinv = plan->d_hinv; P.schur_max = plan->riccati_few_pins <= 0 ? 0 : (plan->riccati_few_pins > kSchurMax ? kSchurMax : plan->riccati_few_pins);
     P.rkk[0] = d.R * P.kv[0] * P.kv[0]; P.rkk[1] = d.R * P.kv[0] * P.kv[1]; P.rkk[2] = d.R * P.kv[0] * P.kv[2];
     P.rkk[3] = d.R * P.kv[1] * P.kv[1]; P.rkk[4] = d.R * P.kv[1] * P.kv[2]; P.rkk[5] = d.R * P.kv[2] * P.kv[2];
     P.viol_tol = d.viol_tol;
     P.mu_eps = 1e-12;
     P.stats = nullptr;
-    if (resume) { P.park = resume->park; P.park_list = resume->park_list; P.park_count = resume->park_count; P.stats = resume->stats; }
+    if (rs) {
+        P.park = rs->park; P.park_list = rs->lists + (size_t)in_list * cb.ncols; P.park_count = rs->counts + in_list; P.stats = rs->stats;
+        if (back_list >= 0) {
+            P.back_list = rs->lists + (size_t)back_list * cb.ncols; P.back_count = rs->counts + back_list;
+            P.back_pins = kRowparMaxPins - 4;      // some room for the set to grow again before the row-parallel kernel would park it
+        }
+    }
     return launch_kernel(plan, P, stream);
 }
 

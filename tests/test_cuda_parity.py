@@ -40,6 +40,11 @@ def rel_err(got, want):
     return float(np.max(np.abs(np.asarray(got) - np.asarray(want))) / max(np.max(np.abs(want)), 1e-300))
 
 
+def rel_err_mm(got, want):
+    """Relative error of a trajectory with a millimetre floor on the scale (walks of a few samples stay near zero)."""
+    return float(np.max(np.abs(np.asarray(got) - np.asarray(want))) / max(np.max(np.abs(want)), 1e-3))
+
+
 # ----------------------------------------------------------------------------- plan matrices
 @pytest.mark.parametrize("N,h", [(150, 0.75), (100, 0.62), (16, 0.9), (37, 0.75)])
 def test_plan_matrices(engine, N, h):
@@ -238,7 +243,7 @@ def test_batch_results_do_not_depend_on_batch_layout(engine, plan150):
     if plan150.solver == engine.SOLVER_ADMM:
         assert np.array_equal(per["y_hist"].cpu().numpy(), sub["y_hist"])
     else:
-        assert rel_err(per["y_hist"].cpu().numpy(), sub["y_hist"]) < REL
+        assert rel_err_mm(per["y_hist"].cpu().numpy(), sub["y_hist"]) < REL
         plan150.set_row_parallel(False)
         try:
             sub2 = plan150.rollout(engine.MODE_STRICT, zero[pick], zero[pick], z_min, z_max, impulse=impulse[pick], force_tick=tick[pick])
@@ -342,6 +347,58 @@ def test_one_plan_on_two_streams(engine, plan150):
                 assert torch.equal(got[key], want[key]), (attempt, key)
 
 
+def test_row_parallel_stage_agrees_with_riccati_kernel(engine):
+    """The default FP64 solver starts walks on shared series on the row-parallel kernel (dense corrections with the
+    inverse Hessian), parks columns whose set outgrows it on the Riccati kernel and takes them back when the push is
+    absorbed.  The same sweep with that stage switched off runs on the Riccati kernel alone: both are the optimum of the
+    same QPs, so the walks agree to 1e-9 relative, the flags bit for bit, and the outcome verdicts are the same --
+    including scenarios that fall (parked for good) and ones that recover (parked and handed back)."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(384, seed=5)
+    plan = engine.get_plan(150, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R)
+    zero = np.zeros((384, 3))
+    runs = {}
+    for on in (True, False):
+        plan.set_row_parallel(on)
+        try:
+            out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, impulse=impulse, force_tick=tick, want_readout=True)
+            runs[on] = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+            if on:
+                st = plan.stats()
+        finally:
+            plan.set_row_parallel(True)
+    a, b = runs[True], runs[False]
+    assert st["debug_cycles_contraction"] > 50 and st["debug_cycles_iteration"] > 10      # columns parked / handed back
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert np.array_equal(a["flags"], b["flags"])
+    for key in ("x_hist", "y_hist", "zmp", "com"):
+        scale = np.maximum(1.0, np.abs(b[key]).reshape(384, -1).max(axis=1))
+        diff = np.abs(a[key] - b[key]).reshape(384, -1).max(axis=1)
+        assert (diff / scale).max() < REL, key
+    fell_a, fell_b = engine.unpack_outcome_host(a["outcome"])["fell"], engine.unpack_outcome_host(b["outcome"])["fell"]
+    assert np.array_equal(fell_a, fell_b) and 0 < fell_a.sum() < 384
+    assert a["max_violation"].max() < 1e-9
+    # indexed series of different lengths (the parameter sweep's layout): same agreement
+    nA, nB = 300, 260
+    zmin2 = np.stack([z_min[:nA], np.concatenate([z_min[40:40 + nB], np.repeat(z_min[39 + nB:40 + nB], nA - nB, 0)])])
+    zmax2 = np.stack([z_max[:nA], np.concatenate([z_max[40:40 + nB], np.repeat(z_max[39 + nB:40 + nB], nA - nB, 0)])])
+    idx = (np.arange(96) % 2).astype(np.int32)
+    n_steps = np.where(idx == 0, nA, nB).astype(np.int32)
+    n_steps[5] = 200                                   # a walk shorter than its series: falls back to the Riccati kernel
+    zero = np.zeros((96, 3))
+    runs = {}
+    for on in (True, False):
+        plan.set_row_parallel(on)
+        try:
+            out = plan.rollout(engine.MODE_STRICT, zero, zero, zmin2, zmax2, n_steps=n_steps, bounds_index=idx,
+                               impulse=impulse[:96] * 0.6, force_tick=(tick[:96] % 150).astype(np.int32))
+            runs[on] = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+        finally:
+            plan.set_row_parallel(True)
+    a, b = runs[True], runs[False]
+    assert np.array_equal(a["flags"], b["flags"]) and (a["status"] == 0).all()
+    assert rel_err_mm(a["y_hist"], b["y_hist"]) < REL and rel_err_mm(a["x_hist"], b["x_hist"]) < REL
+
+
 def test_ragged_walks(engine, plan150):
     """n_steps per scenario: each walk equals the same walk run alone on its truncated series;
     the last bound row is what gets repeated past the end (zmp_controller.py:81-88)."""
@@ -355,10 +412,26 @@ def test_ragged_walks(engine, plan150):
         for b, n in enumerate(n_steps):
             one = plan150.rollout(mode, zero[:1], zero[:1], z_min[:n], z_max[:n], impulse=impulse[b:b + 1],
                                   force_tick=tick[b:b + 1])
-            assert np.array_equal(one["y_hist"][0].cpu().numpy(), out["y_hist"][b, :n]), (mode, b)
-            assert np.array_equal(one["x_hist"][0].cpu().numpy(), out["x_hist"][b, :n])
+            if mode == engine.MODE_STRICT and plan150.solver == engine.SOLVER_ACTIVE_SET:
+                # ragged walks on a shared series run on the Riccati kernel, the single walk on the row-parallel one:
+                # two formulations of the same optimum (bit for bit with the row-parallel stage off, below)
+                assert rel_err_mm(one["y_hist"][0].cpu().numpy(), out["y_hist"][b, :n]) < REL, (mode, b)
+                assert rel_err_mm(one["x_hist"][0].cpu().numpy(), out["x_hist"][b, :n]) < REL
+            else:
+                assert np.array_equal(one["y_hist"][0].cpu().numpy(), out["y_hist"][b, :n]), (mode, b)
+                assert np.array_equal(one["x_hist"][0].cpu().numpy(), out["x_hist"][b, :n])
             assert np.array_equal(one["flags"][0].cpu().numpy(), out["flags"][b, :n])
             assert not out["y_hist"][b, n:].any()              # untouched past the end
+    if plan150.solver == engine.SOLVER_ACTIVE_SET:
+        plan150.set_row_parallel(False)
+        try:
+            out = plan150.rollout(engine.MODE_STRICT, zero, zero, z_min[:70], z_max[:70], n_steps=n_steps, impulse=impulse, force_tick=tick)
+            for b, n in enumerate(n_steps):
+                one = plan150.rollout(engine.MODE_STRICT, zero[:1], zero[:1], z_min[:n], z_max[:n], impulse=impulse[b:b + 1],
+                                      force_tick=tick[b:b + 1])
+                assert np.array_equal(one["y_hist"][0].cpu().numpy(), out["y_hist"][b, :n].cpu().numpy()), b
+        finally:
+            plan150.set_row_parallel(True)
 
 
 def test_unconstrained_large_ragged_batch(engine, plan150):

@@ -37,9 +37,7 @@ def main():
             st = plan.stats()
             res[on] = {k: v.clone() for k, v in r.items() if torch.is_tensor(v)}
             out[f"{name}_rowpar{on}"] = {"ms": ms, "M_solves_per_s": solves / ms / 1e3, "sweeps": st["group_iterations"], "columns": st["units"],
-                                             "parked_stage1": st["debug_cycles_contraction"] & 0xffffffff, "parked_stage2": st["debug_cycles_contraction"] >> 32,
-                                             "stage2_park_mean_L": (st["debug_cycles_iteration"] >> 32) / max(1, st["debug_cycles_contraction"] >> 32),
-                                             "stage2_park_mean_pins": (st["debug_cycles_iteration"] & 0xffffffff) / max(1, st["debug_cycles_contraction"] >> 32)} if on else {"ms": ms}
+                                             "parked": st["debug_cycles_contraction"], "handed_back": st["debug_cycles_iteration"]} if on else {"ms": ms}
             print(json.dumps({f"{name}_rowpar{on}": out[f"{name}_rowpar{on}"]}), flush=True)
         a, b = res[1], res[0]
         d = max(float((a["x_hist"] - b["x_hist"]).abs().max()), float((a["y_hist"] - b["y_hist"]).abs().max()))
