@@ -660,15 +660,21 @@ def run_ours(args, rank, world, local_rank):
         kernel_s = np.mean(step_ms) * 1e-3
         peak = measure_fp64_peak(torch, device)
         if active_set:
-            # one sweep pair = N stages x (backward 75 + forward 17 FP64 multiply-adds) ~ 184 N flops
+            # one sweep pair of the Riccati recursion = N stages x (backward 75 + forward 17 FP64 multiply-adds)
+            # ~ 184 N flops; the row-parallel stage does less arithmetic per sweep on the ticks it takes, so this is
+            # an upper estimate of the work actually executed (the time is that of ALL kernels of the step)
             flops = RICCATI_FLOPS_PER_STAGE * N * iters
             traffic = ncu_traffic("k_riccati_rollout", B)
-            roofline = {"bound": "fp64 pipe (not tensor, not hbm: scalar FP64 recursions, one dependent chain per column; latency "
-                                 "bound at this batch)",
-                        "kernel": "k_riccati_rollout (active set + Riccati sweeps, one thread per column)",
+            st = stats                       # of the last timed step
+            roofline = {"bound": "fp64 pipe (not tensor, not hbm: scalar FP64 recursions with one dependent chain per column; "
+                                 "latency bound: the step ends with the walks of the scenarios that fall)",
+                        "kernel": "k_riccati_rollout (active set + Riccati sweeps, one thread per column: the columns the "
+                                  "row-parallel kernel k_rowpar_rollout parks after a strong push; ~80 % of the step)",
+                        "columns_parked_on_the_riccati_kernel": int(st.get("debug_cycles_contraction", 0)),
+                        "columns_handed_back": int(st.get("debug_cycles_iteration", 0)),
                         "note": "achieved = sweep pairs x N x %d flops (the active-set algorithm's own work; the ADMM formulation "
-                                "needs ~150x more flops per solve, see admm_tensor_path); peak = cuBLAS DGEMM measured in this run "
-                                "(B200's FP64 FMA pipe and DMMA have the same nominal rate)" % RICCATI_FLOPS_PER_STAGE}
+                                "needs ~150x more flops per solve, see admm_tensor_path) / time of the whole step; peak = cuBLAS "
+                                "DGEMM measured in this run (B200's FP64 FMA pipe and DMMA have the same nominal rate)" % RICCATI_FLOPS_PER_STAGE}
         else:
             flops = 2.0 * N * N * iters                      # K_exec * 2 N^2 per solve
             traffic = ncu_traffic("k_strict_rollout_f16" if precision == engine.PRECISION_F16X3 else "k_strict_rollout<", B)
@@ -679,7 +685,7 @@ def run_ours(args, rank, world, local_rank):
                                         "(MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_step": flops})
         if active_set:
-            solver_block = {"name": "active set + Riccati sweeps (LIPM_SOLVER_ACTIVE_SET)",
+            solver_block = {"name": "active set (LIPM_SOLVER_ACTIVE_SET): row-parallel kernel with dense corrections, Riccati sweeps for large sets",
                             "mean_sweep_pairs_per_solve": iters / max(solves_per_step, 1),
                             "mean_sweep_pairs_per_solve_x_axis": out["iters"][:, 0].sum().item() / max(B * (n - 1), 1),
                             "mean_sweep_pairs_per_solve_y_axis": out["iters"][:, 1].sum().item() / max(B * (n - 1), 1),
@@ -702,9 +708,10 @@ def run_ours(args, rank, world, local_rank):
                     "median_ms_per_call": round(1e3 * float(np.median(e2e_calls)), 2),
                     "host_loadavg": list(os.getloadavg()),
                     "note": "value = mean over the calls (wall clock, NumPy in / NumPy out, all histories copied back)"},
-            # per timed step: k_tick_span + k_order_keys + k_unit_work + the rollout kernel + k_pack_outcomes (the CUB
-            # sort passes between them are library kernels and not counted); unconstrained: preview + rollout + pack
-            "gpu_launches": ((4 if active_set else 5) if mode == engine.MODE_STRICT else 3) * args.steps,
+            # per timed step: k_tick_span + k_order_keys (+ k_unit_work, ADMM) + the rollout kernels + k_pack_outcomes (the
+            # CUB sort passes between them are library kernels and not counted).  Active set: k_rowpar_pack, k_preview_u,
+            # 2 x k_rowpar_rollout, 2 x (k_pack_bounds + k_riccati_rollout).  Unconstrained: preview + rollout + pack
+            "gpu_launches": ((11 if active_set else 5) if mode == engine.MODE_STRICT else 3) * args.steps,
             "clocks": clocks.summary(),
             "roofline": roofline,
             "checks": {"not_converged_columns": status_bad, "max_zmp_violation_m": max_viol},

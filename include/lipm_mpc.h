@@ -205,9 +205,10 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
                                       the unconstrained problem with the per-plan tables and correct it with the dense
                                       inverse Hessian (0 = never, the default: in the one-thread-per-column kernel the
                                       Riccati recursion is faster; up to 16); both give the same optimum           */
-#define LIPM_OPT_ROW_PARALLEL 9     /* plan required; 1 (default) / 0: FP64 active-set walks on shared or indexed bound series
-                                      start on the row-parallel kernel (csrc/lipm_rollout_rowpar.cu); 0 keeps the whole walk
-                                      on the thread-per-column Riccati kernel.  Same optimum either way (tested)         */
+#define LIPM_OPT_ROW_PARALLEL 9     /* plan required; 1 (default): FP64 active-set walks on shared or indexed bound series of up
+                                      to 16384 columns start on the row-parallel kernel (csrc/lipm_rollout_rowpar.cu); 2: whatever
+                                      the batch size; 0: never (the whole walk on the thread-per-column Riccati kernel).  Same
+                                      optimum either way (walks agree to 1e-9, flags bit for bit: tested)                    */
 #define LIPM_OPT_MAX_SWEEPS 6      /* plan required; active-set corrections per QP before it is reported as
                                       not converged (0 -> 64)                                                    */
 

@@ -129,7 +129,7 @@ struct lipm_plan {
     double* d_ric_tab;    // [N + 4][16] per-stage tables of the active-set kernel's free tail (build_riccati_tables)
     double* d_ric_aux;    // [N + 1][12] K_j, P_j of the same stages
     double* d_kx;         // [N][3] Kx = H^-1 G Px: state part of the unconstrained plan (row-parallel kernel, N <= 160)
-    int rowpar_off;       // 1: FP64 active-set walks skip the row-parallel first stage (lipm_set_option)
+    int rowpar_off;       // 1: FP64 active-set walks skip the row-parallel stage; -1: they use it whatever the batch size; 0: automatic
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
     unsigned long long* d_stats;   // [0] group iterations, [1] units of the last strict launch (copied from the launch's own state)

@@ -40,6 +40,7 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kTickTile = 8;          // ticks per block of k_preview_u
+constexpr int kRowparMaxColumns = 16384;
 
 struct RowparParams {
     ColumnBatch cb;
@@ -426,6 +427,10 @@ int build_rowpar_tables(lipm_plan* plan) {
 // series shared or indexed (a series per scenario has no shared preview term), preview scratch within bounds.
 bool rowpar_eligible(const lipm_plan* plan, const ColumnBatch& cb) {
     if (plan->rowpar_off || !plan->d_kx) return false;
+    // One warp per column pays while the batch is small enough to be latency bound on the thread-per-column kernel
+    // (8192 columns: 46 against 49 ms with pushes, 9 against 22 ms without); a 32768-column bucket of the parameter
+    // sweep fills the machine with full warps of the Riccati kernel and is 25 % faster there.
+    if (plan->rowpar_off != -1 && cb.ncols > kRowparMaxColumns) return false;
     if (plan->N > 32 * kRowparWords) return false;
     if (cb.ticks_override > 0 || cb.zmp_plan) return false;
     if (!cb.bounds_index && cb.bounds_batch != 1) return false;

@@ -312,9 +312,10 @@ class LipmPlan:
         """Active-set kernel: pinned rows up to which a sweep uses table solve + dense correction (0 = never, the default; up to 16)."""
         _check(self._lib.lipm_set_option(self._handle, OPT_FEW_PIN_ROWS, int(rows)))
 
-    def set_row_parallel(self, on: bool) -> None:
-        """FP64 active-set walks on shared / indexed bound series start on the row-parallel kernel (default on)."""
-        _check(self._lib.lipm_set_option(self._handle, OPT_ROW_PARALLEL, 1 if on else 0))
+    def set_row_parallel(self, on) -> None:
+        """FP64 active-set walks on shared / indexed bound series start on the row-parallel kernel: True (default) for
+        batches of up to 16384 columns, False never, 2 whatever the batch size."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_ROW_PARALLEL, 2 if on == 2 else (1 if on else 0)))
 
     def set_max_sweeps(self, sweeps: int) -> None:
         """Active-set corrections per QP before the solve is reported as not converged (0 = default 64)."""
