@@ -670,8 +670,8 @@ def run_ours(args, rank, world, local_rank):
                                  "latency bound: the step ends with the walks of the scenarios that fall)",
                         "kernel": "k_riccati_rollout (active set + Riccati sweeps, one thread per column: the columns the "
                                   "row-parallel kernel k_rowpar_rollout parks after a strong push; ~80 % of the step)",
-                        "columns_parked_on_the_riccati_kernel": int(st.get("debug_cycles_contraction", 0)),
-                        "columns_handed_back": int(st.get("debug_cycles_iteration", 0)),
+                        "columns_parked_on_the_riccati_kernel": int(st.get("columns_parked", 0)),
+                        "columns_handed_back": int(st.get("columns_handed_back", 0)),
                         "note": "achieved = sweep pairs x N x %d flops (the active-set algorithm's own work; the ADMM formulation "
                                 "needs ~150x more flops per solve, see admm_tensor_path) / time of the whole step; peak = cuBLAS "
                                 "DGEMM measured in this run (B200's FP64 FMA pipe and DMMA have the same nominal rate)" % RICCATI_FLOPS_PER_STAGE}

@@ -389,14 +389,31 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
             const int jhi = jg == N ? N4 : jg;      // the general recursion's aligned chunks cover rows m .. jhi-1
             general_stages += (jg > m ? jg - m : 0); table_stages += N - jg;
             double s0 = x0, s1 = x1, s2 = x2;
-            for (int j = 0; j < m; ++j) {
-                const double2 bd = __ldg(pb + min(base + j, last));
-                const double lo = bd.x, hi = bd.y;
-                const double bnd = get_bit(m_hi, j) ? hi : lo;
-                const double Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, bnd * P.inv_cb)));
-                const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);
-                s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
-                G[j * GS] = make_double2(Jv, Q * (bnd - 0.5 * (lo + hi)));
+            if (m > 0) {
+                // chunks of four rows (m is a multiple of four); the bounds of a chunk are fetched while the chunk before it
+                // is computed, the pin bits come one nibble per chunk
+                double2 nb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nb[k] = __ldg(pb + min(base + k, last));
+                for (int j = 0; j < m; j += 4) {
+                    double2 cb4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cb4[k] = nb[k];
+                    if (j + 4 < m) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nb[k] = __ldg(pb + min(base + j + 4 + k, last));
+                    }
+                    const uint32_t nib_hi = (m_hi[j >> 5] >> (j & 31)) & 15u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double lo = cb4[k].x, hi = cb4[k].y;
+                        const double bnd = ((nib_hi >> k) & 1u) ? hi : lo;
+                        const double Jv = fma(P.kv[2], s2, fma(P.kv[1], s1, fma(P.kv[0], s0, bnd * P.inv_cb)));
+                        const double f0 = fma(c2, s2, fma(T, s1, s0)), f1 = fma(T, s2, s1);
+                        s0 = fma(c3, Jv, f0); s1 = fma(c2, Jv, f1); s2 = fma(T, Jv, s2);
+                        G[(j + k) * GS] = make_double2(Jv, Q * (bnd - 0.5 * (lo + hi)));
+                    }
+                }
             }
             const double xm0 = s0, xm1 = s1, xm2 = s2;     // state at the start of stage m
             // ---- backward sweep, table region (rows N-1 .. jg): linear part of the cost-to-go only -----------------
@@ -720,20 +737,37 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                 double l0 = fma(ctg.P02, xm2, fma(ctg.P01, xm1, fma(ctg.P00, xm0, ctg.v0))) * ctg.ipi;
                 double l1 = fma(ctg.P12, xm2, fma(ctg.P11, xm1, fma(ctg.P01, xm0, ctg.v1))) * ctg.ipi;
                 double l2 = fma(ctg.P22, xm2, fma(ctg.P12, xm1, fma(ctg.P02, xm0, ctg.v2))) * ctg.ipi;
-                for (int j = m - 1; j >= 0; --j) {
-                    const double2 rec = G[j * GS];
-                    const double mu = fma(P.r_cb, rec.x, rec.y + fma(P.bc[2], l2, fma(P.bc[1], l1, P.bc[0] * l0)));
-                    const bool pin_hi = get_bit(m_hi, j);
-                    if (pin_hi ? (mu > tol) : (mu < -tol)) {
-                        m_lo[j >> 5] &= ~(1u << (j & 31));
-                        m_hi[j >> 5] &= ~(1u << (j & 31));
+                // chunks of four rows, highest first; the records of a chunk (written by the forward pass over the block: L2
+                // hits) are fetched while the chunk before it is computed, the set is read and corrected one nibble per chunk
+                double2 nr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nr[k] = G[(m - 4 + k) * GS];
+                for (int j = m - 4; j >= 0; j -= 4) {
+                    double2 rec[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) rec[k] = nr[k];
+                    if (j > 0) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nr[k] = G[(j - 4 + k) * GS];
+                    }
+                    const int w = j >> 5, sh = j & 31;
+                    const uint32_t nib_hi = (m_hi[w] >> sh) & 15u;
+                    uint32_t release = 0u;
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) {
+                        const double mu = fma(P.r_cb, rec[k].x, rec[k].y + fma(P.bc[2], l2, fma(P.bc[1], l1, P.bc[0] * l0)));
+                        if (((nib_hi >> k) & 1u) ? (mu > tol) : (mu < -tol)) release |= 1u << k;
+                        const double e2 = fma(hg, l0, l2), rj = P.R * rec[k].x;
+                        const double t0 = fma(P.a2[0], e2, fma(P.a1[0], l1, rj * P.kv[0]));
+                        const double t1 = fma(P.a2[1], e2, fma(P.a1[1], l1, rj * P.kv[1]));
+                        const double t2 = fma(P.a2[2], e2, fma(P.a1[2], l1, rj * P.kv[2]));
+                        l0 = t0; l1 = t1; l2 = t2;
+                    }
+                    if (release) {
+                        m_lo[w] &= ~(release << sh);
+                        m_hi[w] &= ~(release << sh);
                         changed = true;
                     }
-                    const double e2 = fma(hg, l0, l2), rj = P.R * rec.x;
-                    const double t0 = fma(P.a2[0], e2, fma(P.a1[0], l1, rj * P.kv[0]));
-                    const double t1 = fma(P.a2[1], e2, fma(P.a1[1], l1, rj * P.kv[1]));
-                    const double t2 = fma(P.a2[2], e2, fma(P.a1[2], l1, rj * P.kv[2]));
-                    l0 = t0; l1 = t1; l2 = t2;
                 }
             }
             if (!changed) { converged = true; break; }
@@ -851,10 +885,12 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
 template <int LANES, bool SMEM>
 int launch_variant(const RiccatiParams& P, unsigned blocks, int threads, size_t smem, cudaStream_t stream) {
     if (smem > 48 * 1024) {
-        static size_t granted = 0;      // per instantiation; growing it twice from two threads is harmless
-        if (smem > granted) {
+        static bool granted[64] = {};   // per instantiation and device (the attribute belongs to the device's copy of the
+        int dev = 0;                    // kernel); setting it twice from two threads is harmless
+        LIPM_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !granted[dev]) {
             LIPM_CUDA_TRY(cudaFuncSetAttribute(k_riccati_rollout<LANES, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynamicSmem));
-            granted = kMaxDynamicSmem;
+            if (dev >= 0 && dev < 64) granted[dev] = true;
         }
     }
     k_riccati_rollout<LANES, SMEM><<<blocks, threads, smem, stream>>>(P);

@@ -228,8 +228,12 @@ class LipmPlan:
         """Work accounting of the last strict launch (synchronises)."""
         out = np.zeros(4, dtype=np.uint64)
         _check(self._lib.lipm_plan_stats(self._handle, out.ctypes.data))
+        # ADMM kernels: [0] iterations of the solver groups, [1] units.  Active-set solver: [0] sweep pairs, [1] columns,
+        # [2] columns the row-parallel kernel parked on the Riccati kernel (Riccati kernel alone: stages of the general
+        # recursion), [3] columns handed back (alone: table stages).  The old key names stay for the tools.
         return {"group_iterations": int(out[0]), "units": int(out[1]),
-                "debug_cycles_contraction": int(out[2]), "debug_cycles_iteration": int(out[3])}
+                "debug_cycles_contraction": int(out[2]), "debug_cycles_iteration": int(out[3]),
+                "sweep_pairs": int(out[0]), "columns": int(out[1]), "columns_parked": int(out[2]), "columns_handed_back": int(out[3])}
 
     # ------------------------------------------------------------------ walks
     def rollout(self, mode: int, x0, y0, z_min, z_max, *, n_steps=None, impulse=None, force_tick=None,

@@ -367,7 +367,7 @@ def test_row_parallel_stage_agrees_with_riccati_kernel(engine):
         finally:
             plan.set_row_parallel(True)
     a, b = runs[True], runs[False]
-    assert st["debug_cycles_contraction"] > 50 and st["debug_cycles_iteration"] > 10      # columns parked / handed back
+    assert st["columns_parked"] > 50 and st["columns_handed_back"] > 10
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     assert np.array_equal(a["flags"], b["flags"])
     for key in ("x_hist", "y_hist", "zmp", "com"):
