@@ -260,7 +260,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_rowpar_rollout(const Ro
                 // S = Hinv[A, A]: lane q loads row q
                 if (lane < na) {
                     const double* row = P.hinv + (size_t)ws.idx[lane] * N;
-                    for (int l = 0; l <= lane; ++l) ws.S[lane * (lane + 1) / 2 + l] = __ldg(row + ws.idx[l]);
+                    double* mine = ws.S + lane * (lane + 1) / 2;
+                    int l = 0;
+                    for (; l + 3 <= lane; l += 4) {               // four loads in flight (L2 / L1 hits)
+                        const int i0 = ws.idx[l], i1 = ws.idx[l + 1], i2 = ws.idx[l + 2], i3 = ws.idx[l + 3];
+                        const double h0 = __ldg(row + i0), h1 = __ldg(row + i1), h2 = __ldg(row + i2), h3 = __ldg(row + i3);
+                        mine[l] = h0; mine[l + 1] = h1; mine[l + 2] = h2; mine[l + 3] = h3;
+                    }
+                    for (; l <= lane; ++l) mine[l] = __ldg(row + ws.idx[l]);
                 }
                 __syncwarp();
                 // L D L' (right-looking, lane = row; below the diagonal the entries stay unscaled: M = L d)
@@ -270,7 +277,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_rowpar_rollout(const Ro
                     if (lane > p && lane < na) {
                         double* mine = ws.S + lane * (lane + 1) / 2;
                         const double lqp = mine[p] * di;
-                        for (int l = p + 1; l <= lane; ++l) mine[l] = fma(-lqp, ws.S[l * (l + 1) / 2 + p], mine[l]);
+                        int l = p + 1;
+                        for (; l + 3 <= lane; l += 4) {           // loads first: the stores of a batch cannot alias its loads
+                            const double a0 = ws.S[l * (l + 1) / 2 + p], a1 = ws.S[(l + 1) * (l + 2) / 2 + p];
+                            const double a2 = ws.S[(l + 2) * (l + 3) / 2 + p], a3 = ws.S[(l + 3) * (l + 4) / 2 + p];
+                            const double m0 = mine[l], m1 = mine[l + 1], m2 = mine[l + 2], m3 = mine[l + 3];
+                            mine[l] = fma(-lqp, a0, m0); mine[l + 1] = fma(-lqp, a1, m1);
+                            mine[l + 2] = fma(-lqp, a2, m2); mine[l + 3] = fma(-lqp, a3, m3);
+                        }
+                        for (; l <= lane; ++l) mine[l] = fma(-lqp, ws.S[l * (l + 1) / 2 + p], mine[l]);
                     }
                     __syncwarp();
                 }
@@ -288,13 +303,25 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_rowpar_rollout(const Ro
                     __syncwarp();
                 }
                 // correction of my rows
-#pragma unroll 2
-                for (int q = 0; q < na; ++q) {
-                    const double* row = P.hinv + (size_t)ws.idx[q] * N + lane;
-                    const double lq = ws.rr[q];
+                {
+                    int q = 0;
+                    for (; q + 1 < na; q += 2) {                  // two pinned rows at a time: ten loads in flight
+                        const double* ra = P.hinv + (size_t)ws.idx[q] * N + lane;
+                        const double* rb = P.hinv + (size_t)ws.idx[q + 1] * N + lane;
+                        const double la = ws.rr[q], lb = ws.rr[q + 1];
+                        double ha[KR], hb[KR];
 #pragma unroll
-                    for (int k = 0; k < KR; ++k)
-                        if (valid[k]) z[k] = fma(-lq, __ldg(row + 32 * k), z[k]);
+                        for (int k = 0; k < KR; ++k) { ha[k] = valid[k] ? __ldg(ra + 32 * k) : 0.0; hb[k] = valid[k] ? __ldg(rb + 32 * k) : 0.0; }
+#pragma unroll
+                        for (int k = 0; k < KR; ++k) z[k] = fma(-lb, hb[k], fma(-la, ha[k], z[k]));
+                    }
+                    if (q < na) {
+                        const double* row = P.hinv + (size_t)ws.idx[q] * N + lane;
+                        const double lq = ws.rr[q];
+#pragma unroll
+                        for (int k = 0; k < KR; ++k)
+                            if (valid[k]) z[k] = fma(-lq, __ldg(row + 32 * k), z[k]);
+                    }
                 }
             }
             // ---- tests: free rows against the box, pinned rows by the sign of their multiplier (-lambda) ----------------
