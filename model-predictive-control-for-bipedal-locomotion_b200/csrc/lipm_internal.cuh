@@ -146,7 +146,9 @@ int build_rowpar_tables(lipm_plan* plan);         // lipm_rollout_rowpar.cu
 constexpr int kRowparWords = 5;        // 32-row words of a column: horizons up to 160
 constexpr int kRowparMaxPins = 16;     // pinned rows a row-parallel sweep can take
 struct ParkRecord {                    // a column that left the row-parallel kernel: where and in which state
-    int tick, sweeps, notconv, pad;
+    int tick, sweeps, notconv;
+    int stage;                         // which launch of the sequence resumes it next (0: none; kept by column, so that the
+                                       // Riccati kernel finds its columns in processing order: similar walks share a warp)
     double x[3];
     double viol, lean;
     uint32_t m_lo[kRowparWords], m_hi[kRowparWords];

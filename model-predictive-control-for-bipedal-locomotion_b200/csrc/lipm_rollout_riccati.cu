@@ -77,11 +77,11 @@ struct RiccatiParams {
     const double* hinv;     // [N][N] inverse Hessian in ZMP coordinates (plan->d_hinv, symmetric): few-pin solves
     int schur_max;          // pinned rows up to which a sweep uses the table solve + dense correction (0: never)
     ParkRecord* park;       // resume mode: records of the columns parked by the row-parallel kernel (nullptr: whole walks)
-    const int* park_list;   // [*park_count] their column numbers
-    const int* park_count;
+    int park_stage;         // ... those whose record carries this stage number (columns stay in processing order)
     int* back_list;         // resume mode: columns handed back to the row-parallel kernel once their set is small again
     int* back_count;        //   (nullptr: every column is finished here)
     int back_pins;          // ... small = at most this many pinned rows on kBackStreak consecutive ticks
+    int back_stage;         // stage number of the launch that takes them
     int pk_by_column;       // 1: one run of pairs per column of the launch; 0: one per (series, axis)
     unsigned long long* stats;   // [0] sweep pairs, [1] columns, [2] stages of the general recursion, [3] table stages
 };
@@ -277,14 +277,9 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
                        ((threadIdx.x >> 5) * LANES + lane);
     if (lane >= LANES) return;
     const long long cl = (long long)P.col_begin + warp * LANES + lane;
-    int c;
-    if (P.park) {
-        if (cl >= *P.park_count) return;
-        c = P.park_list[cl];
-    } else {
-        if (cl >= P.col_end) return;
-        c = (int)cl;
-    }
+    if (cl >= P.col_end) return;
+    const int c = (int)cl;
+    if (P.park && P.park[c].stage != P.park_stage) return;      // resume mode: only the columns parked for this launch
     const int NW = (N + 31) >> 5;
     constexpr int GS = 2 * LANES;                 // double2 elements between consecutive stages of a column
 
@@ -852,7 +847,7 @@ __global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P
             calm = pins <= P.back_pins ? calm + 1 : 0;
             if (calm >= kBackStreak) {
                 ParkRecord& rec = P.park[c];
-                rec.tick = i + 1; rec.sweeps = sweeps_total; rec.notconv = notconv;
+                rec.tick = i + 1; rec.sweeps = sweeps_total; rec.notconv = notconv; rec.stage = P.back_stage;
                 rec.x[0] = x0; rec.x[1] = x1; rec.x[2] = x2; rec.viol = viol; rec.lean = lean;
 #pragma unroll
                 for (int w = 0; w < kRowparWords; ++w) {        // the guess of the next tick: the set moved up by one row
@@ -1092,7 +1087,7 @@ static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const Ro
     P.hg2x = 2.0 * P.hg; P.hgsq = P.hg * P.hg;
     P.col_begin = 0; P.col_end = cb.ncols; P.gains = nullptr; P.nkc = nullptr;
     P.tab = plan->d_ric_tab; P.aux = plan->d_ric_aux; P.pk = nullptr; P.pk_by_column = 0;
-    P.park = nullptr; P.park_list = nullptr; P.park_count = nullptr; P.back_list = nullptr; P.back_count = nullptr; P.back_pins = 0;
+    P.park = nullptr; P.park_stage = 0; P.back_list = nullptr; P.back_count = nullptr; P.back_pins = 0; P.back_stage = 0;
     P.hinv = plan->d_hinv; P.schur_max = plan->riccati_few_pins <= 0 ? 0 : (plan->riccati_few_pins > kSchurMax ? kSchurMax : plan->riccati_few_pins);
     P.rkk[0] = d.R * P.kv[0] * P.kv[0]; P.rkk[1] = d.R * P.kv[0] * P.kv[1]; P.rkk[2] = d.R * P.kv[0] * P.kv[2];
     P.rkk[3] = d.R * P.kv[1] * P.kv[1]; P.rkk[4] = d.R * P.kv[1] * P.kv[2]; P.rkk[5] = d.R * P.kv[2] * P.kv[2];
@@ -1100,10 +1095,11 @@ static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const Ro
     P.mu_eps = 1e-12;
     P.stats = nullptr;
     if (rs) {
-        P.park = rs->park; P.park_list = rs->lists + (size_t)in_list * cb.ncols; P.park_count = rs->counts + in_list; P.stats = rs->stats;
+        P.park = rs->park; P.park_stage = in_list + 1; P.stats = rs->stats;
         if (back_list >= 0) {
             P.back_list = rs->lists + (size_t)back_list * cb.ncols; P.back_count = rs->counts + back_list;
             P.back_pins = kRowparMaxPins - 4;      // some room for the set to grow again before the row-parallel kernel would park it
+            P.back_stage = back_list + 1;
         }
     }
     return launch_kernel(plan, P, stream);

@@ -58,6 +58,7 @@ struct RowparParams {
     int* park_count;
     const int* in_list;         // resume: the columns k_riccati_rollout handed back (nullptr: all columns from tick 0)
     const int* in_count;
+    int park_stage;             // stage number written into the records of the columns parked by this launch
     unsigned long long* stats;  // [0] sweeps, [1] columns (of the columns that finish here)
 };
 
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_rowpar_rollout(const Ro
         }
         if (lane == 0) {
             ParkRecord& rec = P.park[c];
-            rec.tick = park_tick; rec.sweeps = sweeps_total; rec.notconv = notconv;
+            rec.tick = park_tick; rec.sweeps = sweeps_total; rec.notconv = notconv; rec.stage = P.park_stage;
             rec.x[0] = x0; rec.x[1] = x1; rec.x[2] = x2; rec.viol = viol; rec.lean = lean;
 #pragma unroll
             for (int k = 0; k < kRowparWords; ++k) { rec.m_lo[k] = 0u; rec.m_hi[k] = 0u; }
@@ -486,6 +487,7 @@ int rowpar_prepare(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cu
     rs.counts = reinterpret_cast<int*>(p);
     rs.lists = rs.counts + 8;
     LIPM_CUDA_TRY(cudaMemsetAsync(rs.counts, 0, 8 * sizeof(int), stream));
+    LIPM_CUDA_TRY(cudaMemsetAsync(rs.park, 0, rec_bytes, stream));
     {
         const long long total = (long long)runs * cb.n_uniform;
         const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)plan->sm_count * 16);
@@ -522,6 +524,7 @@ int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& r
     P.park = rs.park; P.park_list = rs.lists + (size_t)out_list * cb.ncols; P.park_count = rs.counts + out_list;
     P.in_list = in_list < 0 ? nullptr : rs.lists + (size_t)in_list * cb.ncols;
     P.in_count = in_list < 0 ? nullptr : rs.counts + in_list;
+    P.park_stage = out_list + 1;
     P.stats = rs.stats;
     const unsigned blocks = (unsigned)((cb.ncols + kWarpsPerBlock - 1) / kWarpsPerBlock);
     k_rowpar_rollout<kRowparWords><<<blocks, 32 * kWarpsPerBlock, 0, stream>>>(P);
