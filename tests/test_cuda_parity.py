@@ -399,6 +399,45 @@ def test_row_parallel_stage_agrees_with_riccati_kernel(engine):
     assert rel_err_mm(a["y_hist"], b["y_hist"]) < REL and rel_err_mm(a["x_hist"], b["x_hist"]) < REL
 
 
+def test_riccati_kernel_options_do_not_change_the_optimum(engine):
+    """Launch-shape and placement options of the thread-per-column kernel (columns per warp, stage tables and
+    feed-forward terms in shared memory or through L1 / global scratch) do not change a bit; few-pin sweeps (table solve +
+    dense correction instead of the Riccati recursion when at most 16 rows are pinned: LIPM_OPT_FEW_PIN_ROWS, off by
+    default) are another formulation of the same optimum: flags bit for bit, walks to 1e-9."""
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(48, seed=9)
+    n = 200
+    z_max, z_min = z_max[:n], z_min[:n]
+    tick = (tick % 100 + 40).astype(np.int32)
+    plan = engine.get_plan(150, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R)
+    zero = np.zeros((48, 3))
+
+    def run():
+        out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, impulse=impulse * 0.7, force_tick=tick)
+        return {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+
+    plan.set_row_parallel(False)
+    try:
+        base = run()
+        assert (base["status"] == 0).all()
+        for lanes, scratch in ((4, 0), (32, 0), (8, 2), (8, 1)):
+            plan.set_riccati_lanes(lanes)
+            plan.set_riccati_scratch(scratch)
+            got = run()
+            for key in ("x_hist", "y_hist", "flags", "iters"):
+                assert np.array_equal(got[key], base[key]), (lanes, scratch, key)
+        plan.set_riccati_lanes(0)
+        plan.set_riccati_scratch(0)
+        plan.set_few_pin_rows(16)
+        few = run()
+        assert np.array_equal(few["flags"], base["flags"]) and (few["status"] == 0).all()
+        assert rel_err_mm(few["y_hist"], base["y_hist"]) < REL and rel_err_mm(few["x_hist"], base["x_hist"]) < REL
+    finally:
+        plan.set_few_pin_rows(0)
+        plan.set_riccati_lanes(0)
+        plan.set_riccati_scratch(0)
+        plan.set_row_parallel(True)
+
+
 def test_ragged_walks(engine, plan150):
     """n_steps per scenario: each walk equals the same walk run alone on its truncated series;
     the last bound row is what gets repeated past the end (zmp_controller.py:81-88)."""
