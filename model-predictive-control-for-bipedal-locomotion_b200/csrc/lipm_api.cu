@@ -219,6 +219,10 @@ int lipm_set_option(lipm_plan_t* plan, int option, long long value) {
             if (!plan || value < 0 || value > 2) { set_error("lipm_set_option(ROW_PARALLEL): need a plan and 0 / 1 / 2"); return LIPM_E_INVALID; }
             plan->rowpar_off = value == 0 ? 1 : (value == 2 ? -1 : 0);
             return LIPM_OK;
+        case LIPM_OPT_WALK_CHUNKS:
+            if (!plan || value < 0 || value > kRowparMaxChunks) { set_error("lipm_set_option(WALK_CHUNKS): need a plan and a value in [0, %d]", kRowparMaxChunks); return LIPM_E_INVALID; }
+            plan->rowpar_chunks = (int)value;
+            return LIPM_OK;
         case LIPM_OPT_FEW_PIN_ROWS:
             if (!plan || value < 0 || value > 16) { set_error("lipm_set_option(FEW_PIN_ROWS): need a plan and a value in [0, 16]"); return LIPM_E_INVALID; }
             plan->riccati_few_pins = (int)value;

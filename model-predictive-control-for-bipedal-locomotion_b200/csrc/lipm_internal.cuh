@@ -129,6 +129,7 @@ struct lipm_plan {
     double* d_ric_tab;    // [N + 4][16] per-stage tables of the active-set kernel's free tail (build_riccati_tables)
     double* d_ric_aux;    // [N + 1][12] K_j, P_j of the same stages
     double* d_kx;         // [N][3] Kx = H^-1 G Px: state part of the unconstrained plan (row-parallel kernel, N <= 160)
+    int rowpar_chunks;    // slot chunks of an active-set rollout on side streams (LIPM_OPT_WALK_CHUNKS): 0 automatic, 1 none, 2..4
     int rowpar_off;       // 1: FP64 active-set walks skip the row-parallel stage; -1: they use it whatever the batch size; 0: automatic
     int force_segments;   // >0: tick ranges per unit of the FP64 strict kernel (lipm_set_option; 0 = automatic)
     int* d_info;          // [4] factorisation status words
@@ -153,16 +154,21 @@ struct ParkRecord {                    // a column that left the row-parallel ke
     double viol, lean;
     uint32_t m_lo[kRowparWords], m_hi[kRowparWords];
 };
-constexpr int kRowparLists = 3;        // hand-over lists of a rollout: row-parallel -> Riccati -> row-parallel -> Riccati
+constexpr int kRowparLists = 3;        // hand-over lists of a chunk: row-parallel -> Riccati -> row-parallel -> Riccati
+constexpr int kRowparMaxChunks = 4;    // slot chunks of a rollout, each with its own hand-over lists (and side stream)
 struct RowparScratch {
     StreamBuffer buf;
     double* u = nullptr;               // shared preview terms
     double2* pk = nullptr;             // bound pairs per (series, axis)
     int* n_series = nullptr;
     ParkRecord* park = nullptr;        // [ncols]
-    int* lists = nullptr;              // [kRowparLists][ncols] parked columns
-    int* counts = nullptr;             // [kRowparLists] (+ padding)
+    int* lists = nullptr;              // [chunks][kRowparLists][ncols] parked columns
+    int* counts = nullptr;             // [chunks][4]
+    int ncols = 0;
     unsigned long long* stats = nullptr;
+    int* list(int chunk, int l) const { return lists + ((size_t)chunk * kRowparLists + l) * ncols; }
+    int* count(int chunk, int l) const { return counts + chunk * 4 + l; }
+    static int stage(int chunk, int l) { return 1 + chunk * 4 + l; }   // stage number in the records of list l of a chunk
 };
 
 // One "column" = one axis of one scenario.  The rollout kernels receive this flat description.
@@ -212,7 +218,8 @@ int launch_strict_rollout(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t s
 int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // active set: row-parallel stage, then Riccati sweeps
 bool rowpar_eligible(const lipm_plan* plan, const ColumnBatch& cb);
 int rowpar_prepare(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cudaStream_t stream);
-int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& rs, int in_list, int out_list, cudaStream_t stream);
+int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& rs, int chunk, int chunks, int in_list, int out_list,
+                  cudaStream_t stream);
 int launch_strict_rollout_f16(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16s(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);
 int launch_strict_rollout_f16p(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream);   // CTA pairs (cta_group::2)

@@ -972,8 +972,8 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
         if (rc != LIPM_OK) return rc;
         LIPM_CUDA_TRY(cudaGetLastError());
     }
-    LIPM_CUDA_TRY(cudaMemcpyAsync(plan->d_stats, P.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
-    return LIPM_OK;
+    if (!P.park) LIPM_CUDA_TRY(cudaMemcpyAsync(plan->d_stats, P.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    return LIPM_OK;        // (resume mode: the caller files the statistics of the whole sequence)
 }
 
 }  // namespace
@@ -1030,31 +1030,91 @@ int build_riccati_tables(lipm_plan* plan) {
     return LIPM_OK;
 }
 
-static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* rs, int in_list, int back_list, cudaStream_t stream);
+static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* rs, int chunk, int in_list, int back_list,
+                                cudaStream_t stream);
+
+namespace {
+// side streams / events of one chunked rollout, released on every exit path (a stream with pending work is released by
+// the runtime once that work has completed)
+struct SideStreams {
+    cudaStream_t stream[kRowparMaxChunks] = {};
+    cudaEvent_t ready[kRowparMaxChunks] = {}, done[kRowparMaxChunks] = {};
+    int count = 0;
+    cudaError_t create(int n) {
+        for (int k = 0; k < n; ++k) {
+            cudaError_t e = cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+            count = k + 1;
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    ~SideStreams() {
+        for (int k = 0; k < count; ++k) {
+            if (ready[k]) cudaEventDestroy(ready[k]);
+            if (done[k]) cudaEventDestroy(done[k]);
+            if (stream[k]) cudaStreamDestroy(stream[k]);
+        }
+    }
+};
+}  // namespace
 
 // Default FP64 strict solver.  Walks on shared bound series start on the row-parallel kernel (lipm_rollout_rowpar.cu); a
 // column whose active set outgrows it continues here, and goes back once the set is small again:
 //   row-parallel (all columns) -> Riccati (parked, hands back) -> row-parallel (handed back) -> Riccati (the rest).
+// The Riccati stage is bound by the latency of its longest walks and leaves most of the machine idle, the row-parallel
+// stage by throughput.  Batches of 1024 scenarios or more are therefore cut into chunks of the processing order (early
+// pushes first: the walks that spend longest on the Riccati kernel): the row-parallel passes of the chunks run one
+// after the other on the caller's stream, and each chunk's remaining three launches follow on a side stream as soon as
+// its first pass is done, beside the first passes of the later chunks.
 // Every other batch (own series per scenario, single ticks, horizons beyond 160) runs here from the first tick.
 int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaStream_t stream) {
     if (plan->N > kMaxStrictHorizon) {
         set_error("strict mode: horizon %d exceeds this build's limit %d", plan->N, kMaxStrictHorizon);
         return LIPM_E_UNSUPPORTED;
     }
-    if (!rowpar_eligible(plan, cb)) return launch_riccati_stage(plan, cb, nullptr, -1, -1, stream);
+    if (!rowpar_eligible(plan, cb)) return launch_riccati_stage(plan, cb, nullptr, 0, -1, -1, stream);
     RowparScratch rs;
     LaunchState state;
     LIPM_CUDA_TRY(state.begin(stream));
     rs.stats = state.stats();
     int rc = rowpar_prepare(plan, cb, rs, stream);
     if (rc != LIPM_OK) return rc;
-    if ((rc = launch_rowpar(plan, cb, rs, -1, 0, stream)) != LIPM_OK) return rc;
-    if ((rc = launch_riccati_stage(plan, cb, &rs, 0, 1, stream)) != LIPM_OK) return rc;
-    if ((rc = launch_rowpar(plan, cb, rs, 1, 2, stream)) != LIPM_OK) return rc;
-    return launch_riccati_stage(plan, cb, &rs, 2, -1, stream);
+    const int chunks = plan->rowpar_chunks > 0 ? (plan->rowpar_chunks < cb.B ? plan->rowpar_chunks : 1) : (cb.B >= 1024 ? kRowparMaxChunks : 1);
+    if (chunks == 1) {
+        if ((rc = launch_rowpar(plan, cb, rs, 0, 1, -1, 0, stream)) != LIPM_OK) return rc;
+        if ((rc = launch_riccati_stage(plan, cb, &rs, 0, 0, 1, stream)) != LIPM_OK) return rc;
+        if ((rc = launch_rowpar(plan, cb, rs, 0, 1, 1, 2, stream)) != LIPM_OK) return rc;
+        rc = launch_riccati_stage(plan, cb, &rs, 0, 2, -1, stream);
+    } else {
+        SideStreams side;
+        LIPM_CUDA_TRY(side.create(chunks));
+        for (int k = 0; k < chunks && rc == LIPM_OK; ++k) {
+            if ((rc = launch_rowpar(plan, cb, rs, k, chunks, -1, 0, stream)) != LIPM_OK) break;
+            LIPM_CUDA_TRY(cudaEventRecord(side.ready[k], stream));
+            LIPM_CUDA_TRY(cudaStreamWaitEvent(side.stream[k], side.ready[k], 0));
+            if ((rc = launch_riccati_stage(plan, cb, &rs, k, 0, 1, side.stream[k])) != LIPM_OK) break;
+            if ((rc = launch_rowpar(plan, cb, rs, k, chunks, 1, 2, side.stream[k])) != LIPM_OK) break;
+            if ((rc = launch_riccati_stage(plan, cb, &rs, k, 2, -1, side.stream[k])) != LIPM_OK) break;
+            LIPM_CUDA_TRY(cudaEventRecord(side.done[k], side.stream[k]));
+        }
+        // join: whatever was enqueued on the side streams precedes everything the caller enqueues next (and the release of
+        // the scratch buffers below)
+        for (int k = 0; k < chunks; ++k) {
+            if (cudaEventQuery(side.done[k]) != cudaErrorInvalidResourceHandle) cudaStreamWaitEvent(stream, side.done[k], 0);
+        }
+        if (rc != LIPM_OK) {
+            for (int k = 0; k < chunks; ++k) cudaStreamSynchronize(side.stream[k]);     // error path: nothing may outlive the scratch
+        }
+    }
+    if (rc != LIPM_OK) return rc;
+    LIPM_CUDA_TRY(cudaMemcpyAsync(plan->d_stats, rs.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    return LIPM_OK;
 }
 
-static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* rs, int in_list, int back_list, cudaStream_t stream) {
+static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch* rs, int chunk, int in_list, int back_list,
+                                cudaStream_t stream) {
     const lipm_plan_desc_t& d = plan->desc;
     if (plan->N > kMaxStrictHorizon) {
         set_error("strict mode: horizon %d exceeds this build's limit %d", plan->N, kMaxStrictHorizon);
@@ -1095,11 +1155,11 @@ static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const Ro
     P.mu_eps = 1e-12;
     P.stats = nullptr;
     if (rs) {
-        P.park = rs->park; P.park_stage = in_list + 1; P.stats = rs->stats;
+        P.park = rs->park; P.park_stage = RowparScratch::stage(chunk, in_list); P.stats = rs->stats;
         if (back_list >= 0) {
-            P.back_list = rs->lists + (size_t)back_list * cb.ncols; P.back_count = rs->counts + back_list;
+            P.back_list = rs->list(chunk, back_list); P.back_count = rs->count(chunk, back_list);
             P.back_pins = kRowparMaxPins - 4;      // some room for the set to grow again before the row-parallel kernel would park it
-            P.back_stage = back_list + 1;
+            P.back_stage = RowparScratch::stage(chunk, back_list);
         }
     }
     return launch_kernel(plan, P, stream);

@@ -59,6 +59,7 @@ struct RowparParams {
     const int* in_list;         // resume: the columns k_riccati_rollout handed back (nullptr: all columns from tick 0)
     const int* in_count;
     int park_stage;             // stage number written into the records of the columns parked by this launch
+    int slot_begin, slot_count; // fresh start: the slots (both axes) of this launch
     unsigned long long* stats;  // [0] sweeps, [1] columns (of the columns that finish here)
 };
 
@@ -140,8 +141,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) k_rowpar_rollout(const Ro
         if (cl >= *P.in_count) return;
         c = P.in_list[cl];
     } else {
-        if (cl >= B.ncols) return;
-        c = (int)cl;
+        if (cl >= 2LL * P.slot_count) return;
+        const int ax = (int)(cl / P.slot_count);
+        c = ax * B.B + P.slot_begin + (int)(cl - (long long)ax * P.slot_count);
     }
     WarpScratch& ws = scratch[wib];
     const int N = P.N;
@@ -477,7 +479,7 @@ int rowpar_prepare(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cu
     const size_t pk_bytes = (size_t)runs * cb.n_uniform * sizeof(double2);
     const size_t ns_bytes = (((size_t)cb.bounds_batch * sizeof(int)) + 15) & ~(size_t)15;
     const size_t rec_bytes = (size_t)cb.ncols * sizeof(ParkRecord);
-    const size_t list_bytes = (((size_t)cb.ncols * kRowparLists + 8) * sizeof(int) + 15) & ~(size_t)15;
+    const size_t list_bytes = (((size_t)cb.ncols * kRowparLists * kRowparMaxChunks + 4 * kRowparMaxChunks) * sizeof(int) + 15) & ~(size_t)15;
     LIPM_CUDA_TRY(rs.buf.alloc(u_bytes + pk_bytes + ns_bytes + rec_bytes + list_bytes, stream));
     unsigned char* p = rs.buf.as<unsigned char>();
     rs.u = reinterpret_cast<double*>(p); p += u_bytes;
@@ -485,8 +487,9 @@ int rowpar_prepare(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cu
     int* n_series = reinterpret_cast<int*>(p); p += ns_bytes;
     rs.park = reinterpret_cast<ParkRecord*>(p); p += rec_bytes;
     rs.counts = reinterpret_cast<int*>(p);
-    rs.lists = rs.counts + 8;
-    LIPM_CUDA_TRY(cudaMemsetAsync(rs.counts, 0, 8 * sizeof(int), stream));
+    rs.lists = rs.counts + 4 * kRowparMaxChunks;
+    rs.ncols = cb.ncols;
+    LIPM_CUDA_TRY(cudaMemsetAsync(rs.counts, 0, 4 * kRowparMaxChunks * sizeof(int), stream));
     LIPM_CUDA_TRY(cudaMemsetAsync(rs.park, 0, rec_bytes, stream));
     {
         const long long total = (long long)runs * cb.n_uniform;
@@ -508,9 +511,10 @@ int rowpar_prepare(lipm_plan* plan, const ColumnBatch& cb, RowparScratch& rs, cu
     return LIPM_OK;
 }
 
-// One pass of the row-parallel kernel: all columns from tick 0 (in_list < 0) or the columns of hand-over list `in_list`;
-// the columns it parks go to list `out_list`.
-int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& rs, int in_list, int out_list, cudaStream_t stream) {
+// One pass of the row-parallel kernel over slot chunk `chunk` of `chunks`: its columns from tick 0 (in_list < 0) or the
+// columns of the chunk's hand-over list `in_list`; the columns it parks go to the chunk's list `out_list`.
+int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& rs, int chunk, int chunks, int in_list, int out_list,
+                  cudaStream_t stream) {
     const lipm_plan_desc_t& d = plan->desc;
     RowparParams P;
     P.cb = cb;
@@ -521,12 +525,16 @@ int launch_rowpar(lipm_plan* plan, const ColumnBatch& cb, const RowparScratch& r
     P.cbv = plan->pu00; P.inv_cb = 1.0 / plan->pu00; P.px02 = P.c2 - P.hg;
     P.viol_tol = d.viol_tol; P.mu_eps = 1e-12;
     P.hinv = plan->d_hinv; P.kx = plan->d_kx; P.u = rs.u; P.pk = rs.pk; P.n_series = rs.n_series;
-    P.park = rs.park; P.park_list = rs.lists + (size_t)out_list * cb.ncols; P.park_count = rs.counts + out_list;
-    P.in_list = in_list < 0 ? nullptr : rs.lists + (size_t)in_list * cb.ncols;
-    P.in_count = in_list < 0 ? nullptr : rs.counts + in_list;
-    P.park_stage = out_list + 1;
+    P.park = rs.park; P.park_list = rs.list(chunk, out_list); P.park_count = rs.count(chunk, out_list);
+    P.in_list = in_list < 0 ? nullptr : rs.list(chunk, in_list);
+    P.in_count = in_list < 0 ? nullptr : rs.count(chunk, in_list);
+    P.park_stage = RowparScratch::stage(chunk, out_list);
+    P.slot_begin = (int)((long long)cb.B * chunk / chunks);
+    P.slot_count = (int)((long long)cb.B * (chunk + 1) / chunks) - P.slot_begin;
     P.stats = rs.stats;
-    const unsigned blocks = (unsigned)((cb.ncols + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const long long warps = 2LL * P.slot_count;          // (a hand-over list holds at most the chunk's columns)
+    const unsigned blocks = (unsigned)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (blocks == 0) return LIPM_OK;
     k_rowpar_rollout<kRowparWords><<<blocks, 32 * kWarpsPerBlock, 0, stream>>>(P);
     LIPM_CUDA_TRY(cudaGetLastError());
     return LIPM_OK;

@@ -87,6 +87,7 @@ OPT_MAX_SWEEPS = 6
 OPT_RICCATI_SCRATCH = 7
 OPT_FEW_PIN_ROWS = 8
 OPT_ROW_PARALLEL = 9
+OPT_WALK_CHUNKS = 10
 # solver of the FP64 strict mode: both return the unique minimiser of the reference's QP
 SOLVER_ACTIVE_SET = 0   # default: primal-dual active set + O(N) Riccati sweeps (csrc/lipm_rollout_riccati.cu)
 SOLVER_ADMM = 1         # ADMM on the condensed QP, FP64 tensor pipe (csrc/lipm_rollout_strict.cu)
@@ -320,6 +321,10 @@ class LipmPlan:
         """FP64 active-set walks on shared / indexed bound series start on the row-parallel kernel: True (default) for
         batches of up to 16384 columns, False never, 2 whatever the batch size."""
         _check(self._lib.lipm_set_option(self._handle, OPT_ROW_PARALLEL, 2 if on == 2 else (1 if on else 0)))
+
+    def set_walk_chunks(self, chunks: int) -> None:
+        """``LIPM_OPT_WALK_CHUNKS``: 0 automatic, 1 no side streams, 2..4 chunks of the batch overlapped on side streams."""
+        _check(self._lib.lipm_set_option(self._handle, OPT_WALK_CHUNKS, int(chunks)))
 
     def set_max_sweeps(self, sweeps: int) -> None:
         """Active-set corrections per QP before the solve is reported as not converged (0 = default 64)."""

@@ -399,6 +399,44 @@ def test_row_parallel_stage_agrees_with_riccati_kernel(engine):
     assert rel_err_mm(a["y_hist"], b["y_hist"]) < REL and rel_err_mm(a["x_hist"], b["x_hist"]) < REL
 
 
+def test_walk_chunks_on_side_streams_are_bit_identical(engine):
+    """LIPM_OPT_WALK_CHUNKS: batches of 1024 scenarios or more are cut into four chunks of the processing order whose
+    Riccati / hand-back stages run on side streams of the library beside the row-parallel passes of the later chunks.
+    A column does the same arithmetic wherever it runs: every output equals the serial run (one chunk, caller's stream
+    only) bit for bit, for the automatic setting on 1024 scenarios and for forced chunk counts on a ragged 97."""
+    import torch
+    cfg, z_max, z_min, impulse, tick = push_sweep_inputs(1024, seed=11)
+    n = 160
+    z_max, z_min = z_max[:n], z_min[:n]
+    tick = (tick % 90 + 30).astype(np.int32)
+    plan = engine.get_plan(150, cfg.h, cfg.g, cfg.dt, cfg.Q, cfg.R)
+
+    def run(b):
+        zero = np.zeros((b, 3))
+        out = plan.rollout(engine.MODE_STRICT, zero, zero, z_min, z_max, impulse=impulse[:b], force_tick=tick[:b], want_readout=True)
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}, plan.stats()
+
+    try:
+        plan.set_walk_chunks(1)
+        base, st1 = run(1024)
+        assert (base["status"] == 0).all() and st1["columns_parked"] > 100
+        plan.set_walk_chunks(0)
+        got, st0 = run(1024)
+        assert st0 == st1
+        for key in base:
+            assert np.array_equal(got[key], base[key]), key
+        plan.set_walk_chunks(1)
+        base, _ = run(97)
+        for chunks in (2, 3, 4):
+            plan.set_walk_chunks(chunks)
+            got, _ = run(97)
+            for key in base:
+                assert np.array_equal(got[key], base[key]), (chunks, key)
+    finally:
+        plan.set_walk_chunks(0)
+
+
 def test_riccati_kernel_options_do_not_change_the_optimum(engine):
     """Launch-shape and placement options of the thread-per-column kernel (columns per warp, stage tables and
     feed-forward terms in shared memory or through L1 / global scratch) do not change a bit; few-pin sweeps (table solve +
