@@ -710,9 +710,9 @@ def run_ours(args, rank, world, local_rank):
                     "note": "value = mean over the calls (wall clock, NumPy in / NumPy out, all histories copied back)"},
             # per timed step: k_tick_span + k_order_keys (+ k_unit_work, ADMM) + the rollout kernels + k_pack_outcomes (the
             # CUB sort passes between them are library kernels and not counted).  Active set: k_rowpar_pack, k_preview_u,
-            # then per chunk of the batch (four from 1024 scenarios on, LIPM_OPT_WALK_CHUNKS) 2 x k_rowpar_rollout and
+            # then per chunk of the batch (four from 4096 scenarios on, LIPM_OPT_WALK_CHUNKS) 2 x k_rowpar_rollout and
             # 2 x (k_pack_bounds + k_riccati_rollout).  Unconstrained: preview + rollout + pack
-            "gpu_launches": ((5 + 6 * (4 if B >= 1024 else 1) if active_set else 5) if mode == engine.MODE_STRICT else 3) * args.steps,
+            "gpu_launches": ((5 + 6 * (4 if B >= 4096 else 1) if active_set else 5) if mode == engine.MODE_STRICT else 3) * args.steps,
             "clocks": clocks.summary(),
             "roofline": roofline,
             "checks": {"not_converged_columns": status_bad, "max_zmp_violation_m": max_viol},

@@ -256,8 +256,12 @@ __global__ void k_pack_bounds(const RiccatiParams P, double2* __restrict__ out, 
 
 // LANES = columns per warp (compile time: record strides become immediates).  SMEM: the per-plan stage tables and the
 // feed-forward terms of the table stages live in shared memory (else: tables through L1, terms in global scratch).
+// Registers: blocks of 64 threads.  Narrow warps (the resumed columns of a push sweep, small batches) are bound by the number
+// of warps an SM holds -- a warp owns registers for 32 threads however few of them carry a column -- so they are capped at
+// 200 registers (five blocks per SM, ~130 bytes of spills off the stage loops; push sweep of 1024 ... 8192 scenarios 3-5 %
+// faster); full warps are bound by the FP64 pipe and keep all ~236 (four blocks per SM; the cap costs them 3-8 %).
 template <int LANES, bool SMEM>
-__global__ void __launch_bounds__(64, 4) k_riccati_rollout(const RiccatiParams P) {
+__global__ void __maxnreg__(LANES <= 4 ? 200 : 255) k_riccati_rollout(const RiccatiParams P) {
     extern __shared__ double2 dyn_smem[];
     const ColumnBatch& B = P.cb;
     const int lane = threadIdx.x & 31;
@@ -908,7 +912,9 @@ int launch_kernel(lipm_plan* plan, const RiccatiParams& P0, cudaStream_t stream)
         lanes = 1;
         while (lanes < 32 && (long long)ncols > want_warps * lanes) lanes <<= 1;
     }
-    if (P.park && plan->riccati_lanes <= 0 && lanes > 1) lanes >>= 1;      // resume: a fraction of the columns is left
+    // resume: a third of the columns is left, in runs of the processing order, and the columns that share a warp no longer
+    // follow the same path through the stage types (measured best at 1024 ... 8192 scenarios: a quarter of the width)
+    if (P.park && plan->riccati_lanes <= 0) lanes = lanes >= 4 ? lanes >> 2 : 1;
     P.lanes = lanes;
     LaunchState state;
     if (!P.stats) {                 // (resume: the statistics words of the row-parallel stage are continued)
@@ -1064,7 +1070,7 @@ struct SideStreams {
 // column whose active set outgrows it continues here, and goes back once the set is small again:
 //   row-parallel (all columns) -> Riccati (parked, hands back) -> row-parallel (handed back) -> Riccati (the rest).
 // The Riccati stage is bound by the latency of its longest walks and leaves most of the machine idle, the row-parallel
-// stage by throughput.  Batches of 1024 scenarios or more are therefore cut into chunks of the processing order (early
+// stage by throughput.  Batches of 4096 scenarios or more are therefore cut into chunks of the processing order (early
 // pushes first: the walks that spend longest on the Riccati kernel): the row-parallel passes of the chunks run one
 // after the other on the caller's stream, and each chunk's remaining three launches follow on a side stream as soon as
 // its first pass is done, beside the first passes of the later chunks.
@@ -1081,7 +1087,7 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
     rs.stats = state.stats();
     int rc = rowpar_prepare(plan, cb, rs, stream);
     if (rc != LIPM_OK) return rc;
-    const int chunks = plan->rowpar_chunks > 0 ? (plan->rowpar_chunks < cb.B ? plan->rowpar_chunks : 1) : (cb.B >= 1024 ? kRowparMaxChunks : 1);
+    const int chunks = plan->rowpar_chunks > 0 ? (plan->rowpar_chunks < cb.B ? plan->rowpar_chunks : 1) : (cb.B >= 4096 ? kRowparMaxChunks : 1);
     if (chunks == 1) {
         if ((rc = launch_rowpar(plan, cb, rs, 0, 1, -1, 0, stream)) != LIPM_OK) return rc;
         if ((rc = launch_riccati_stage(plan, cb, &rs, 0, 0, 1, stream)) != LIPM_OK) return rc;

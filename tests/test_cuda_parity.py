@@ -400,10 +400,10 @@ def test_row_parallel_stage_agrees_with_riccati_kernel(engine):
 
 
 def test_walk_chunks_on_side_streams_are_bit_identical(engine):
-    """LIPM_OPT_WALK_CHUNKS: batches of 1024 scenarios or more are cut into four chunks of the processing order whose
+    """LIPM_OPT_WALK_CHUNKS: batches of 4096 scenarios or more are cut into four chunks of the processing order whose
     Riccati / hand-back stages run on side streams of the library beside the row-parallel passes of the later chunks.
     A column does the same arithmetic wherever it runs: every output equals the serial run (one chunk, caller's stream
-    only) bit for bit, for the automatic setting on 1024 scenarios and for forced chunk counts on a ragged 97."""
+    only) bit for bit, for four chunks on 1024 scenarios and for forced chunk counts on a ragged 97."""
     import torch
     cfg, z_max, z_min, impulse, tick = push_sweep_inputs(1024, seed=11)
     n = 160
@@ -421,7 +421,7 @@ def test_walk_chunks_on_side_streams_are_bit_identical(engine):
         plan.set_walk_chunks(1)
         base, st1 = run(1024)
         assert (base["status"] == 0).all() and st1["columns_parked"] > 100
-        plan.set_walk_chunks(0)
+        plan.set_walk_chunks(4)
         got, st0 = run(1024)
         assert st0 == st1
         for key in base:
