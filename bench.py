@@ -396,6 +396,12 @@ def param_sweep_leg(torch, dist, engine, device, rank, world, per_gpu=131072):
         w = sweeps.run_shard(cfg, warm, rank, world, precision=precision)          # plans of all 8 CoM heights, kernels
         parallel.gather_by_index(w["record"], w["index"], len(warm), world)
         torch.cuda.synchronize(device)
+        # one untimed pass at full size: the stream-ordered pool grows to the sweep's scratch size on first use (page
+        # mapping: the first pass varied between 0.65 and 0.96 s from box to box), like the warm-up steps of the headline
+        t_first = time.perf_counter()
+        sweeps.run_shard(cfg, table, rank, world, precision=precision)
+        torch.cuda.synchronize(device)
+        t_first = time.perf_counter() - t_first
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -414,7 +420,7 @@ def param_sweep_leg(torch, dist, engine, device, rank, world, per_gpu=131072):
         else:
             solves = agg[2].item()
         rec = parallel.unpack_outcomes(gathered)
-        result[tag] = {"seconds": seconds, "seconds_walks": t_walks, "seconds_all_gather_and_scatter": seconds - t_walks,
+        result[tag] = {"seconds": seconds, "seconds_first_untimed_pass_this_rank": t_first, "seconds_walks": t_walks, "seconds_all_gather_and_scatter": seconds - t_walks,
                        "qp_solves": int(solves), "qp_solves_per_s": solves / seconds,
                        "not_converged": int((rec["status"] != 0).sum().item()), "fallen": int(rec["fell"].sum().item()),
                        "max_zmp_violation_m": rec["max_violation"].max().item(),
@@ -665,6 +671,9 @@ def run_ours(args, rank, world, local_rank):
             # an upper estimate of the work actually executed (the time is that of ALL kernels of the step)
             flops = RICCATI_FLOPS_PER_STAGE * N * iters
             traffic = ncu_traffic("k_riccati_rollout", B)
+            if traffic is not None:
+                traffic["launch"] = ("the longest of the step's Riccati launches (first chunk of the processing order, parked columns); "
+                                     "the step has two such launches per chunk")
             st = stats                       # of the last timed step
             roofline = {"bound": "fp64 pipe (not tensor, not hbm: scalar FP64 recursions with one dependent chain per column; "
                                  "latency bound: the step ends with the walks of the scenarios that fall)",
@@ -672,6 +681,8 @@ def run_ours(args, rank, world, local_rank):
                                   "row-parallel kernel k_rowpar_rollout parks after a strong push; ~80 % of the step)",
                         "columns_parked_on_the_riccati_kernel": int(st.get("columns_parked", 0)),
                         "columns_handed_back": int(st.get("columns_handed_back", 0)),
+                        "latency_floor": "the heaviest scenario of this sweep run ALONE (two columns, one warp each) takes 27 ms "
+                                         "(profiles/r02_park_probe_b4096.json): one dependent chain of ~650 sweep pairs",
                         "note": "achieved = sweep pairs x N x %d flops (the active-set algorithm's own work; the ADMM formulation "
                                 "needs ~150x more flops per solve, see admm_tensor_path) / time of the whole step; peak = cuBLAS "
                                 "DGEMM measured in this run (B200's FP64 FMA pipe and DMMA have the same nominal rate)" % RICCATI_FLOPS_PER_STAGE}

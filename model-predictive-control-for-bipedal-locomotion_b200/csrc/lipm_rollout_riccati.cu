@@ -1096,20 +1096,26 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
     } else {
         SideStreams side;
         LIPM_CUDA_TRY(side.create(chunks));
+        // (no early return between here and the join: a failed call sets rc and leaves the loop)
+        auto cuda_ok = [&rc](cudaError_t e, const char* what) {
+            if (e == cudaSuccess) return true;
+            set_error("%s failed: %s (chunked active-set rollout)", what, cudaGetErrorString(e));
+            rc = LIPM_E_CUDA;
+            return false;
+        };
         for (int k = 0; k < chunks && rc == LIPM_OK; ++k) {
             if ((rc = launch_rowpar(plan, cb, rs, k, chunks, -1, 0, stream)) != LIPM_OK) break;
-            LIPM_CUDA_TRY(cudaEventRecord(side.ready[k], stream));
-            LIPM_CUDA_TRY(cudaStreamWaitEvent(side.stream[k], side.ready[k], 0));
+            if (!cuda_ok(cudaEventRecord(side.ready[k], stream), "cudaEventRecord")) break;
+            if (!cuda_ok(cudaStreamWaitEvent(side.stream[k], side.ready[k], 0), "cudaStreamWaitEvent")) break;
             if ((rc = launch_riccati_stage(plan, cb, &rs, k, 0, 1, side.stream[k])) != LIPM_OK) break;
             if ((rc = launch_rowpar(plan, cb, rs, k, chunks, 1, 2, side.stream[k])) != LIPM_OK) break;
             if ((rc = launch_riccati_stage(plan, cb, &rs, k, 2, -1, side.stream[k])) != LIPM_OK) break;
-            LIPM_CUDA_TRY(cudaEventRecord(side.done[k], side.stream[k]));
+            if (!cuda_ok(cudaEventRecord(side.done[k], side.stream[k]), "cudaEventRecord")) break;
         }
         // join: whatever was enqueued on the side streams precedes everything the caller enqueues next (and the release of
         // the scratch buffers below)
-        for (int k = 0; k < chunks; ++k) {
-            if (cudaEventQuery(side.done[k]) != cudaErrorInvalidResourceHandle) cudaStreamWaitEvent(stream, side.done[k], 0);
-        }
+        // (an event that was never recorded -- a chunk after a failed launch -- makes the wait a no-op)
+        for (int k = 0; k < chunks; ++k) cudaStreamWaitEvent(stream, side.done[k], 0);
         if (rc != LIPM_OK) {
             for (int k = 0; k < chunks; ++k) cudaStreamSynchronize(side.stream[k]);     // error path: nothing may outlive the scratch
         }
