@@ -145,7 +145,10 @@ int build_rowpar_tables(lipm_plan* plan);         // lipm_rollout_rowpar.cu
 
 // Row-parallel first stage of the active-set solver (lipm_rollout_rowpar.cu) and its hand-over to k_riccati_rollout.
 constexpr int kRowparWords = 5;        // 32-row words of a column: horizons up to 160
-constexpr int kRowparMaxPins = 16;     // pinned rows a row-parallel sweep can take
+#ifndef LIPM_ROWPAR_MAX_PINS
+#define LIPM_ROWPAR_MAX_PINS 16       // (at most 32: one lane per row of the small system)
+#endif
+constexpr int kRowparMaxPins = LIPM_ROWPAR_MAX_PINS;     // pinned rows a row-parallel sweep can take
 struct ParkRecord {                    // a column that left the row-parallel kernel: where and in which state
     int tick, sweeps, notconv;
     int stage;                         // which launch of the sequence resumes it next (0: none; kept by column, so that the
