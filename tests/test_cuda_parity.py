@@ -403,7 +403,8 @@ def test_walk_chunks_on_side_streams_are_bit_identical(engine):
     """LIPM_OPT_WALK_CHUNKS: batches of 4096 scenarios or more are cut into four chunks of the processing order whose
     Riccati / hand-back stages run on side streams of the library beside the row-parallel passes of the later chunks.
     A column does the same arithmetic wherever it runs: every output equals the serial run (one chunk, caller's stream
-    only) bit for bit, for four chunks on 1024 scenarios and for forced chunk counts on a ragged 97."""
+    only) bit for bit: four chunks on 1024 scenarios, forced chunk counts on 97 scenarios (chunks of unequal size), and three
+    chunks on the parameter sweep's layout (indexed series of different lengths)."""
     import torch
     cfg, z_max, z_min, impulse, tick = push_sweep_inputs(1024, seed=11)
     n = 160
@@ -433,6 +434,28 @@ def test_walk_chunks_on_side_streams_are_bit_identical(engine):
             got, _ = run(97)
             for key in base:
                 assert np.array_equal(got[key], base[key]), (chunks, key)
+        # indexed series of different lengths (the parameter sweep's layout)
+        nA, nB = 160, 130
+        zmin2 = np.stack([z_min[:nA], np.concatenate([z_min[20:20 + nB], np.repeat(z_min[19 + nB:20 + nB], nA - nB, 0)])])
+        zmax2 = np.stack([z_max[:nA], np.concatenate([z_max[20:20 + nB], np.repeat(z_max[19 + nB:20 + nB], nA - nB, 0)])])
+        idx = (np.arange(203) % 2).astype(np.int32)
+        n_steps = np.where(idx == 0, nA, nB).astype(np.int32)
+        zero = np.zeros((203, 3))
+
+        def run_indexed():
+            out = plan.rollout(engine.MODE_STRICT, zero, zero, zmin2, zmax2, n_steps=n_steps, bounds_index=idx,
+                               impulse=impulse[:203] * 0.8, force_tick=(tick[:203] % 80 + 20).astype(np.int32), want_readout=True)
+            torch.cuda.synchronize()
+            return {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}, plan.stats()
+
+        plan.set_walk_chunks(1)
+        base, st1 = run_indexed()
+        assert st1["columns_parked"] > 10 and (base["status"] == 0).all()
+        plan.set_walk_chunks(3)
+        got, st3 = run_indexed()
+        assert st3 == st1
+        for key in base:
+            assert np.array_equal(got[key], base[key]), ("indexed", key)
     finally:
         plan.set_walk_chunks(0)
 
