@@ -94,7 +94,13 @@ __device__ __forceinline__ int biased_exponent(double x) { return (__double2hiin
 
 constexpr int kGainPrefetch = 16;  // stages of look-ahead of the forward sweep's L1 prefetch (a forward stage is ~20 instructions, an L2 hit ~250 cycles)
 constexpr int kMaskWords = kMaxStrictHorizon / 32;
-constexpr int kBackStreak = 3;
+#ifndef LIPM_BACK_STREAK
+#define LIPM_BACK_STREAK 3
+#endif
+#ifndef LIPM_BACK_MARGIN
+#define LIPM_BACK_MARGIN 4        // a column is handed back when its set is this much below the row-parallel kernel's limit ...
+#endif
+constexpr int kBackStreak = LIPM_BACK_STREAK;      // ... on this many consecutive ticks
 constexpr int kSchurMax = 16;                   // pinned rows a few-pin sweep can take (triangular system in local memory)
 constexpr size_t kMaxAutoSmem = 72 * 1024;       // per block: three blocks of two warps still fit one SM
 constexpr size_t kMaxDynamicSmem = 200 * 1024;
@@ -1168,9 +1174,9 @@ static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const Ro
     P.stats = nullptr;
     if (rs) {
         P.park = rs->park; P.park_stage = RowparScratch::stage(chunk, in_list); P.stats = rs->stats;
-        if (back_list >= 0) {
+        if (back_list >= 0 && LIPM_BACK_MARGIN < kRowparMaxPins) {
             P.back_list = rs->list(chunk, back_list); P.back_count = rs->count(chunk, back_list);
-            P.back_pins = kRowparMaxPins - 4;      // some room for the set to grow again before the row-parallel kernel would park it
+            P.back_pins = kRowparMaxPins - LIPM_BACK_MARGIN;      // some room for the set to grow again before the row-parallel kernel would park it
             P.back_stage = RowparScratch::stage(chunk, back_list);
         }
     }
