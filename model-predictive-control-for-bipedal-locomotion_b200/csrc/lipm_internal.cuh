@@ -159,6 +159,7 @@ struct ParkRecord {                    // a column that left the row-parallel ke
 };
 constexpr int kRowparLists = 3;        // hand-over lists of a chunk: row-parallel -> Riccati -> row-parallel -> Riccati
 constexpr int kRowparMaxChunks = 4;    // slot chunks of a rollout, each with its own hand-over lists (and side stream)
+constexpr int kRowparAutoChunks = 4;   // ... chosen automatically for batches of 4096 scenarios or more
 struct RowparScratch {
     StreamBuffer buf;
     double* u = nullptr;               // shared preview terms

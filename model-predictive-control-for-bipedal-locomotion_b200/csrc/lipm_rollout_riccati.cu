@@ -1093,7 +1093,7 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
     rs.stats = state.stats();
     int rc = rowpar_prepare(plan, cb, rs, stream);
     if (rc != LIPM_OK) return rc;
-    const int chunks = plan->rowpar_chunks > 0 ? (plan->rowpar_chunks < cb.B ? plan->rowpar_chunks : 1) : (cb.B >= 4096 ? kRowparMaxChunks : 1);
+    const int chunks = plan->rowpar_chunks > 0 ? (plan->rowpar_chunks < cb.B ? plan->rowpar_chunks : 1) : (cb.B >= 4096 ? kRowparAutoChunks : 1);
     if (chunks == 1) {
         if ((rc = launch_rowpar(plan, cb, rs, 0, 1, -1, 0, stream)) != LIPM_OK) return rc;
         if ((rc = launch_riccati_stage(plan, cb, &rs, 0, 0, 1, stream)) != LIPM_OK) return rc;
