@@ -496,6 +496,20 @@ def run_ours(args, rank, world, local_rank):
 
     slots = 128 if precision == engine.PRECISION_F16X3 else 8      # columns a solver unit iterates together
     iters = out["iters"].sum().item() if mode == engine.MODE_STRICT else 0
+    # latency floor of the active-set path, measured live: the scenario with the most sweep pairs run ALONE (its two
+    # columns have the machine to themselves); no launch shape can bring the step below the walk of its slowest column
+    floor_ms = None
+    if rank == 0 and active_set and mode == engine.MODE_STRICT:
+        worst = int(out["iters"].sum(dim=1).argmax().item())
+        one = {}
+        run_one = lambda: plan.rollout(mode, x0[:1], y0[:1], zmin_d, zmax_d, impulse=imp_d[worst:worst + 1].contiguous(),
+                                       force_tick=tick_d[worst:worst + 1].contiguous(), out=one)
+        run_one()
+        torch.cuda.synchronize(device)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(); run_one(); f1.record()
+        torch.cuda.synchronize(device)
+        floor_ms = f0.elapsed_time(f1)
     stats = plan.stats() if mode == engine.MODE_STRICT else {"group_iterations": 0, "units": 0}
     status_bad = int((out["status"] != 0).sum().item())
     max_viol = out["max_violation"].max().item()
@@ -681,8 +695,11 @@ def run_ours(args, rank, world, local_rank):
                                   "row-parallel kernel k_rowpar_rollout parks after a strong push; ~80 % of the step)",
                         "columns_parked_on_the_riccati_kernel": int(st.get("columns_parked", 0)),
                         "columns_handed_back": int(st.get("columns_handed_back", 0)),
-                        "latency_floor": "the heaviest scenario of this sweep run ALONE (two columns, one warp each) takes 27 ms "
-                                         "(profiles/r02_park_probe_b4096.json): one dependent chain of ~650 sweep pairs",
+                        "latency_floor": {"heaviest_scenario_alone_ms": floor_ms, "step_ms": float(np.mean(step_ms)),
+                                          "frac": (floor_ms / float(np.mean(step_ms))) if floor_ms else None,
+                                          "note": "the scenario with the most sweep pairs of this sweep run ALONE, measured in this "
+                                                  "run (two columns, one warp each: one dependent chain of ~650 sweep pairs on its "
+                                                  "pushed axis); frac = that walk / the whole 4096-scenario step"},
                         "note": "achieved = sweep pairs x N x %d flops (the active-set algorithm's own work; the ADMM formulation "
                                 "needs ~150x more flops per solve, see admm_tensor_path) / time of the whole step; peak = cuBLAS "
                                 "DGEMM measured in this run (B200's FP64 FMA pipe and DMMA have the same nominal rate)" % RICCATI_FLOPS_PER_STAGE}

@@ -266,8 +266,11 @@ __global__ void k_pack_bounds(const RiccatiParams P, double2* __restrict__ out, 
 // of warps an SM holds -- a warp owns registers for 32 threads however few of them carry a column -- so they are capped at
 // 200 registers (five blocks per SM, ~130 bytes of spills off the stage loops; push sweep of 1024 ... 8192 scenarios 3-5 %
 // faster); full warps are bound by the FP64 pipe and keep all ~236 (four blocks per SM; the cap costs them 3-8 %).
+#ifndef LIPM_RICCATI_NARROW_REGS
+#define LIPM_RICCATI_NARROW_REGS 200
+#endif
 template <int LANES, bool SMEM>
-__global__ void __maxnreg__(LANES <= 4 ? 200 : 255) k_riccati_rollout(const RiccatiParams P) {
+__global__ void __maxnreg__(LANES <= 4 ? LIPM_RICCATI_NARROW_REGS : 255) k_riccati_rollout(const RiccatiParams P) {
     extern __shared__ double2 dyn_smem[];
     const ColumnBatch& B = P.cb;
     const int lane = threadIdx.x & 31;
