@@ -211,7 +211,7 @@ int lipm_rollout_ex(lipm_plan_t* plan, int mode, const lipm_rollout_io_t* io, vo
                                       optimum either way (walks agree to 1e-9, flags bit for bit: tested)                    */
 #define LIPM_OPT_WALK_CHUNKS 10     /* plan required; FP64 active-set walks that start on the row-parallel kernel: the batch is cut into
                                       this many chunks of the processing order whose later stages overlap on side streams of the
-                                      library (0 automatic: 4 from 4096 scenarios on, 1: everything on the caller's stream, up to 4);
+                                      library (0 automatic: 4 from 4096 scenarios on when the call carries a push, 1: everything on the caller's stream, up to 4);
                                       every column does the same arithmetic whatever the value (bit-identical: tested)         */
 #define LIPM_OPT_MAX_SWEEPS 6      /* plan required; active-set corrections per QP before it is reported as
                                       not converged (0 -> 64)                                                    */

@@ -125,7 +125,10 @@ struct WarpScratch {
     double dinv[kRowparMaxPins];
     int idx[kRowparMaxPins];
 };
-constexpr int kWarpsPerBlock = 8;
+#ifndef LIPM_ROWPAR_WARPS_PER_BLOCK
+#define LIPM_ROWPAR_WARPS_PER_BLOCK 8
+#endif
+constexpr int kWarpsPerBlock = LIPM_ROWPAR_WARPS_PER_BLOCK;
 
 // KR = rows per lane (row r = lane + 32 k)
 template <int KR>
