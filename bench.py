@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=device)
 
     B = args.batch
-    cfg, z_max, z_min, F, tick = sweep_inputs(B, seed=rank)
+    cfg, z_max, z_min, F, tick = sweep_inputs(B, seed=0 if args.same_sweep else rank)
     n = len(z_min)
     solves_per_step = B * 2 * (n - 1)
     precision = engine.PRECISION_F16X3 if args.precision == "f16x3" else engine.PRECISION_FP64
@@ -797,6 +797,7 @@ def main():
     ap.add_argument("--mode", choices=["strict", "unconstrained"], default="strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reduced", action="store_true", help="skip the reduced-precision leg")
+    ap.add_argument("--same-sweep", action="store_true", help="diagnostic: every rank runs the sweep of rank 0 (default: each rank draws its own)")
     ap.add_argument("--no-extras", action="store_true", help="skip the one-number summaries of the other BASELINE configs")
     ap.add_argument("--precision", choices=["fp64", "f16x3"], default="fp64")
     ap.add_argument("--solver", choices=["active_set", "admm"], default="active_set",

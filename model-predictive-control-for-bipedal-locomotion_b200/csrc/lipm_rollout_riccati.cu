@@ -43,6 +43,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 namespace lipm {
@@ -1049,8 +1051,7 @@ static int launch_riccati_stage(lipm_plan* plan, const ColumnBatch& cb, const Ro
                                 cudaStream_t stream);
 
 namespace {
-// side streams / events of one chunked rollout, released on every exit path (a stream with pending work is released by
-// the runtime once that work has completed)
+// side streams / events of one chunked rollout
 struct SideStreams {
     cudaStream_t stream[kRowparMaxChunks] = {};
     cudaEvent_t ready[kRowparMaxChunks] = {}, done[kRowparMaxChunks] = {};
@@ -1072,6 +1073,47 @@ struct SideStreams {
             if (stream[k]) cudaStreamDestroy(stream[k]);
         }
     }
+};
+
+// Side-stream sets are kept per device and handed out for the duration of one call's ENQUEUE (creating and destroying four
+// streams and eight events per rollout is a dozen driver calls on the host path of a 38 ms step, and it showed with eight
+// ranks on one host).  A set may be reused as soon as the call that held it has returned: the waits of that call were
+// enqueued with the events' state at that time, and work on a reused stream simply queues behind the earlier call's.
+// The sets live until the process ends (a host application that resets the device must not call the library afterwards
+// with plans created before the reset -- the same rule as for the plans themselves).
+class SidePool {
+public:
+    SideStreams* acquire(int device, cudaError_t* err) {
+        *err = cudaSuccess;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto& idle = idle_[device & 63];
+            if (!idle.empty()) {
+                SideStreams* s = idle.back().release();
+                idle.pop_back();
+                return s;
+            }
+        }
+        std::unique_ptr<SideStreams> fresh(new SideStreams());
+        *err = fresh->create(kRowparMaxChunks);
+        return *err == cudaSuccess ? fresh.release() : nullptr;
+    }
+    void release(int device, SideStreams* s) {
+        std::lock_guard<std::mutex> lock(mu_);
+        idle_[device & 63].emplace_back(s);
+    }
+private:
+    std::mutex mu_;
+    std::vector<std::unique_ptr<SideStreams>> idle_[64];
+};
+SidePool& side_pool() {
+    static SidePool* pool = new SidePool();       // never destroyed: no CUDA calls from static destructors at exit
+    return *pool;
+}
+struct SideLease {
+    int device = 0;
+    SideStreams* set = nullptr;
+    ~SideLease() { if (set) side_pool().release(device, set); }
 };
 }  // namespace
 
@@ -1107,8 +1149,14 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
         if ((rc = launch_rowpar(plan, cb, rs, 0, 1, 1, 2, stream)) != LIPM_OK) return rc;
         rc = launch_riccati_stage(plan, cb, &rs, 0, 2, -1, stream);
     } else {
-        SideStreams side;
-        LIPM_CUDA_TRY(side.create(chunks));
+        SideLease lease;
+        LIPM_CUDA_TRY(cudaGetDevice(&lease.device));
+        {
+            cudaError_t err = cudaSuccess;
+            lease.set = side_pool().acquire(lease.device, &err);
+            LIPM_CUDA_TRY(err);
+        }
+        SideStreams& side = *lease.set;
         // (no early return between here and the join: a failed call sets rc and leaves the loop)
         auto cuda_ok = [&rc](cudaError_t e, const char* what) {
             if (e == cudaSuccess) return true;
