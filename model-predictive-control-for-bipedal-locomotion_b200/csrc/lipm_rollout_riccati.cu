@@ -1175,7 +1175,8 @@ int launch_strict_rollout_riccati(lipm_plan* plan, const ColumnBatch& cb, cudaSt
         }
         // join: whatever was enqueued on the side streams precedes everything the caller enqueues next (and the release of
         // the scratch buffers below)
-        // (an event that was never recorded -- a chunk after a failed launch -- makes the wait a no-op)
+        // (after a failed launch the events of the later chunks carry no record of this call: waiting on a pooled event's
+        // earlier, completed record -- or on none -- returns at once)
         for (int k = 0; k < chunks; ++k) cudaStreamWaitEvent(stream, side.done[k], 0);
         if (rc != LIPM_OK) {
             for (int k = 0; k < chunks; ++k) cudaStreamSynchronize(side.stream[k]);     // error path: nothing may outlive the scratch
